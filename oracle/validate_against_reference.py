@@ -1,0 +1,214 @@
+"""
+Pin the oracle: run the reference itself (from /root/reference, build container
+only) and the numpy oracle on identical synthetic inputs and compare.
+
+    python -m oracle.validate_against_reference            # small + medium worlds
+
+`build_case` / `run_reference` are also used by tests/golden/make_golden.py to
+produce the committed golden fixtures.
+"""
+
+import os
+import sys
+import tempfile
+from types import SimpleNamespace
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from xanthos_b200 import synthetic  # noqa: E402
+from oracle import ref_loader, pet as opet, abcd as oabcd, mrtm as omrtm, calibrate as ocal  # noqa: E402
+from oracle.calendar_utils import set_month_arrays  # noqa: E402
+
+
+def build_case(nrow=24, ncol=48, ncell=300, n_basins=6, start_yr=1999, end_yr=2001, seed=11,
+               spinup=36, routing_spinup=4, nlcs=8):
+    """All inputs of one parity case (host numpy, reference layouts)."""
+    w = synthetic.make_world(nrow, ncol, ncell, n_basins, seed=seed)
+    m = (end_yr - start_yr + 1) * 12
+    case = dict(
+        nrow=nrow, ncol=ncol, ncell=ncell, n_basins=w.n_basins, start_yr=start_yr, end_yr=end_yr,
+        nmonths=m, spinup=spinup, routing_spinup=routing_spinup, dt=3 * 3600,
+        coords=w.coords, flow_dir=w.flow_dir, flow_dist=w.flow_dist, velocity=w.velocity,
+        area=w.area, basin_ids=w.basin_ids, lat=w.lat.copy(),
+    )
+    pm = synthetic.pm_inputs(w, start_yr, end_yr, nlcs=nlcs, lc_years=(1995, 2000), seed=seed + 1)
+    case.update({'pm_' + k: v for k, v in pm.items() if isinstance(v, np.ndarray)})
+    case.update(pm_nlcs=pm['nlcs'], pm_lc_years=np.array(pm['lc_years']), pm_water_idx=pm['water_idx'],
+                pm_snow_idx=pm['snow_idx'])
+    case.update(synthetic.hs_inputs(w, start_yr, end_yr, seed=seed + 2))
+    case['trn_tas'] = synthetic.thornthwaite_inputs(w, start_yr, end_yr, seed=seed + 3)['tair']
+    ab = synthetic.abcd_inputs(w, m, seed=seed + 4)
+    case.update(abcd_pet=ab['pet'], precip=ab['precip'], tmin=ab['tmin'], abcd_pars=ab['pars'])
+    case['runoff'] = synthetic.runoff_input(w, m, seed=seed + 5)
+    return case
+
+
+def _pm_data(case):
+    keys = ['tair_load', 'TMIN_load', 'rhs_load', 'wind_load', 'rsds_load', 'rlds_load', 'tairprev_load',
+            'lct_load', 'elev', 'alpha', 'lai', 'laimin', 'laimax', 'cL', 'beta', 'rslimit', 'Tminopen',
+            'Tminclose', 'VPDclose', 'VPDopen', 'RBLmin', 'RBLmax', 'rc', 'emiss']
+    return {k: case['pm_' + k] for k in keys}
+
+
+def run_reference(case, ref=None):
+    """Outputs of the reference's own functions for `case`."""
+    ref = ref or ref_loader.load()
+    out = {}
+    n, m = case['ncell'], case['nmonths']
+    sy, ey = case['start_yr'], case['end_yr']
+    s = SimpleNamespace(ngridrow=case['nrow'], ngridcol=case['ncol'], ncell=n, nmonths=m,
+                        StartYear=sy, EndYear=ey)
+
+    # PET
+    data = SimpleNamespace(**{k: np.copy(v) for k, v in _pm_data(case).items()})
+    out['pm_pet'] = ref.pm.run_pmpet(data, n, int(case['pm_nlcs']), sy, ey, int(case['pm_water_idx']),
+                                     int(case['pm_snow_idx']), [int(v) for v in case['pm_lc_years']])
+    hs_data = SimpleNamespace(coords=case['coords'], hs_tas=case['hs_tas'], hs_tmax=case['hs_tmax'],
+                              hs_tmin=case['hs_tmin'])
+    out['hs_pet'] = ref.hs.execute(s, hs_data)
+    tas = np.nan_to_num(np.copy(case['trn_tas']))                              # loader: nan_to_num (data_load.py:138)
+    out['tw_pet'] = ref.tw.execute(tas, np.radians(case['lat']), sy, ey)
+
+    # ABCD
+    with tempfile.TemporaryDirectory() as td:
+        f = os.path.join(td, 'pars.npy')
+        np.save(f, case['abcd_pars'])
+        tmin = np.nan_to_num(case['tmin'])
+        for jobs, tag in ((1, ''), (-1, '_jobs')):
+            r = ref.abcd.abcd_execute(n_basins=case['n_basins'], basin_ids=case['basin_ids'],
+                                      pet=case['abcd_pet'], precip=case['precip'], tmin=tmin,
+                                      calib_file=f, n_months=m, spinup_steps=case['spinup'], jobs=jobs)
+            out['abcd_aet' + tag], out['abcd_q' + tag], out['abcd_sav' + tag] = r[1], r[2], r[3]
+        r = ref.abcd.abcd_execute(n_basins=case['n_basins'], basin_ids=case['basin_ids'],
+                                  pet=case['abcd_pet'], precip=case['precip'], tmin=None,
+                                  calib_file=f, n_months=m, spinup_steps=case['spinup'], jobs=1)
+        out['abcd_q_nosnow'] = r[2]
+
+    # MRTM
+    dsid = ref.mrtm.downstream(case['coords'], case['flow_dir'], s)
+    upid = ref.mrtm.upstream(case['coords'], dsid, s)
+    um = ref.mrtm.upstream_genmatrix(upid)
+    out['dsid'], out['upid'] = dsid, upid
+    um = um.tocsr()
+    out['um_indptr'], out['um_indices'], out['um_data'] = um.indptr, um.indices, um.data
+    ymd = ref.general.set_month_arrays(m, sy, ey)
+    out['ndays'] = ymd[:, 2]
+    S = np.zeros(n)
+    F = np.zeros(n)
+    chs = np.zeros((n, m))
+    avg = np.zeros((n, m))
+    for nm in range(case['routing_spinup']):
+        S, _, F = ref.mrtm.streamrouting(case['flow_dist'], S, F, case['velocity'], case['runoff'][:, nm],
+                                         case['area'], ymd[nm, 2], case['dt'], um)
+    for nm in range(m):
+        S, Favg, F = ref.mrtm.streamrouting(case['flow_dist'], S, F, case['velocity'], case['runoff'][:, nm],
+                                            case['area'], ymd[nm, 2], case['dt'], um)
+        chs[:, nm], avg[:, nm] = S, Favg
+    out['mrtm_chs'], out['mrtm_avg'], out['mrtm_F'] = chs, avg, F
+
+    # calibration objective on the largest basin, a few parameter vectors
+    bc = np.bincount(case['basin_ids'])
+    b = int(np.argmax(bc))
+    idx = np.where(case['basin_ids'] == b)
+    rng = np.random.default_rng(5)
+    cand = np.stack([rng.uniform(1e-4, 1 - 1e-4, 6), rng.uniform(1e-4, 8 - 1e-4, 6),
+                     rng.uniform(1e-4, 1 - 1e-4, 6), rng.uniform(1e-4, 1 - 1e-4, 6),
+                     rng.uniform(1e-4, 1 - 1e-4, 6)], axis=1)
+    tmin = np.nan_to_num(case['tmin'])
+    obs = ref.cal.basin_runoff(cand[0], 0, case['abcd_pet'][idx], case['precip'][idx], tmin[idx], m,
+                               case['spinup'], 'km3_per_mth', case['area'][idx], idx, case['precip'].shape)
+    obs = synthetic.calibration_obs(obs, seed=4)
+    ed = [ref.cal.objective_kge(c, ref.cal.basin_runoff, 0, case['abcd_pet'][idx], case['precip'][idx],
+                                tmin[idx], m, case['spinup'], 'km3_per_mth', case['area'][idx], obs, idx,
+                                case['precip'].shape) for c in cand]
+    out['cal_basin'], out['cal_cand'], out['cal_obs'], out['cal_ed'] = b, cand, obs, np.array(ed)
+    return out
+
+
+def run_oracle(case, fast_upstream=False):
+    """Same outputs from the numpy oracle."""
+    out = {}
+    n, m = case['ncell'], case['nmonths']
+    sy, ey = case['start_yr'], case['end_yr']
+    out['pm_pet'] = opet.pm_pet(_pm_data(case), n, int(case['pm_nlcs']), sy, ey, int(case['pm_water_idx']),
+                                int(case['pm_snow_idx']), [int(v) for v in case['pm_lc_years']])
+    out['hs_pet'] = opet.hs_pet(case['hs_tas'], case['hs_tmax'], case['hs_tmin'], case['coords'][:, 2], sy, ey)
+    out['tw_pet'] = opet.thornthwaite_pet(case['trn_tas'], np.radians(case['lat']), sy, ey)
+    tmin = np.nan_to_num(case['tmin'])
+    r = oabcd.abcd_execute(case['n_basins'], case['basin_ids'], case['abcd_pet'], case['precip'], tmin,
+                           case['abcd_pars'], m, case['spinup'])
+    out['abcd_aet'], out['abcd_q'], out['abcd_sav'] = r[1], r[2], r[3]
+    out['abcd_aet_jobs'], out['abcd_q_jobs'], out['abcd_sav_jobs'] = r[1], r[2], r[3]
+    out['abcd_q_nosnow'] = oabcd.abcd_execute(case['n_basins'], case['basin_ids'], case['abcd_pet'],
+                                              case['precip'], None, case['abcd_pars'], m, case['spinup'])[2]
+    dsid = omrtm.downstream(case['coords'], case['flow_dir'], case['nrow'], case['ncol'])
+    up = omrtm.upstream_fast if fast_upstream else omrtm.upstream
+    upid = up(case['coords'], dsid, case['nrow'], case['ncol'])
+    out['dsid'], out['upid'] = dsid, upid
+    rows = omrtm.gather_rows(upid)
+    cols, sign, cnt = rows
+    out['um_indptr'] = np.concatenate([[0], np.cumsum(cnt)])
+    out['um_indices'] = np.concatenate([cols[i, :cnt[i]] for i in range(n)])
+    out['um_data'] = np.concatenate([sign[i, :cnt[i]] for i in range(n)]).astype(int)
+    ndays = set_month_arrays(m, sy, ey)[:, 2]
+    out['ndays'] = ndays
+    chs, avg, F = omrtm.route(case['runoff'], case['flow_dist'], case['velocity'], case['area'], ndays,
+                              case['dt'], rows, case['routing_spinup'])
+    out['mrtm_chs'], out['mrtm_avg'], out['mrtm_F'] = chs, avg, F
+    return out
+
+
+def oracle_calibration(case, ref_out):
+    b = int(ref_out['cal_basin'])
+    idx = np.where(case['basin_ids'] == b)[0]
+    tmin = np.nan_to_num(case['tmin'])
+    return np.array([ocal.objective_kge(c, case['abcd_pet'][idx], case['precip'][idx], tmin[idx],
+                                        case['nmonths'], case['spinup'], 'km3_per_mth', case['area'][idx],
+                                        ref_out['cal_obs']) for c in ref_out['cal_cand']])
+
+
+def compare(ref_out, ora_out, verbose=True):
+    """Return {name: (bitwise_equal, max_rel_err)}."""
+    res = {}
+    for k, a in ora_out.items():
+        b = ref_out[k]
+        a = np.asarray(a)
+        b = np.asarray(b)
+        same_nan = np.array_equal(np.isnan(a), np.isnan(b)) if a.dtype.kind == 'f' else True
+        bit = bool(same_nan and np.array_equal(np.nan_to_num(a), np.nan_to_num(b)))
+        if a.dtype.kind == 'f':
+            with np.errstate(invalid='ignore', divide='ignore'):
+                den = np.maximum(np.abs(b), 1e-300)
+                rel = np.nanmax(np.abs(a - b) / den) if a.size else 0.0
+        else:
+            rel = 0.0 if bit else np.inf
+        res[k] = (bit, float(rel), bool(same_nan))
+        if verbose:
+            print("  {:16s} bitwise={} nan-pattern={} max_rel={:.3e}".format(k, bit, same_nan, rel))
+    return res
+
+
+def main():
+    ref = ref_loader.load()
+    ok = True
+    for kw in (dict(), dict(nrow=36, ncol=72, ncell=900, n_basins=12, seed=3, start_yr=2096, end_yr=2100,
+                            spinup=48, routing_spinup=12)):
+        case = build_case(**kw)
+        print("case", {k: v for k, v in case.items() if not isinstance(v, np.ndarray)})
+        r = run_reference(case, ref)
+        o = run_oracle(case)
+        res = compare(r, o)
+        ed = oracle_calibration(case, r)
+        rel = np.max(np.abs(ed - r['cal_ed']) / np.abs(r['cal_ed']))
+        print("  {:16s} max_rel={:.3e}".format('cal_ed', rel))
+        for k, (bit, relerr, same_nan) in res.items():
+            ok &= bit
+        ok &= rel < 1e-12
+    print("ORACLE PINNED" if ok else "ORACLE MISMATCH")
+    return 0 if ok else 1
+
+
+if __name__ == '__main__':
+    sys.exit(main())
