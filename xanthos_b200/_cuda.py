@@ -1,0 +1,238 @@
+"""
+ctypes binding of libxanthos_b200.so (the C ABI declared in include/xanthos_b200.h) and the
+device-buffer plumbing around it.
+
+PyTorch is used for exactly three things: owning device memory (`torch.empty(..., device='cuda')`),
+pinned host staging buffers, and CUDA streams.  All arithmetic of the hot path happens inside the
+library's hand-written sm_100a kernels.  There is NO CPU fallback: if the shared library or a CUDA
+device is missing, every compute call raises.
+"""
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libxanthos_b200.so')
+
+XAN_OK, XAN_E_INVALID, XAN_E_CUDA, XAN_E_SPINUP, XAN_E_NOMEM = 0, -1, -2, -3, -4
+MRTM_AUTO, MRTM_GRID, MRTM_TREE = 0, 1, 2
+PM_MAX_CLASSES = 32
+
+
+class ValidationException(Exception):
+    """Same role as xanthos.data_reader.data_load.ValidationException (data_load.py:24)."""
+
+
+class LibraryMissing(RuntimeError):
+    """libxanthos_b200.so has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+
+
+class PmTables(ctypes.Structure):
+    _fields_ = [('nlcs', c_int), ('water_idx', c_int), ('snow_idx', c_int)] + \
+               [(k, POINTER(c_double)) for k in ('cL', 'beta', 'rslimit', 'Tminopen', 'Tminclose', 'VPDclose',
+                                                 'VPDopen', 'RBLmin', 'RBLmax', 'rc', 'emiss',
+                                                 'alpha', 'lai', 'laimin', 'laimax')]
+
+
+# every exported symbol of include/xanthos_b200.h: name -> (restype, argtypes)
+_P = c_void_p
+SIGNATURES = {
+    'xan_version': (c_int, []),
+    'xan_last_error': (c_char_p, []),
+    'xan_device_info': (c_int, [POINTER(c_int)] * 3),
+    'xan_to_month_major': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    'xan_to_cell_major': (c_int, [_P, _P, c_int, c_int, c_int, _P]),
+    'xan_hs_pet': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    'xan_thornthwaite_pet': (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    'xan_thornthwaite_daylight': (c_int, [_P, _P, c_int, _P]),
+    'xan_pm_pet': (c_int, [_P] * 9 + [POINTER(PmTables), POINTER(c_int), _P, c_int, c_int, c_int, c_int, _P]),
+    'xan_abcd_plan_create': (_P, [POINTER(c_int), c_int, c_int]),
+    'xan_abcd_plan_destroy': (None, [_P]),
+    'xan_abcd_run': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    'xan_abcd_kge_batch': (c_int, [_P, POINTER(c_int), c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int,
+                                   c_int, _P, _P, _P]),
+    'xan_mrtm_downstream': (c_int, [POINTER(c_double), POINTER(c_double), c_int, c_int, c_int, POINTER(c_int64)]),
+    'xan_mrtm_upstream': (c_int, [POINTER(c_double), POINTER(c_int64), c_int, c_int, c_int, POINTER(c_int64)]),
+    'xan_mrtm_plan_create': (_P, [POINTER(c_int64), c_int, c_int, c_int]),
+    'xan_mrtm_plan_destroy': (None, [_P]),
+    'xan_mrtm_plan_um_nnz': (c_int, [_P]),
+    'xan_mrtm_plan_um': (c_int, [_P, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+    'xan_mrtm_plan_info': (c_int, [_P, POINTER(c_int)]),
+    'xan_mrtm_plan_packing': (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    'xan_mrtm_route': (c_int, [_P, _P, _P, _P, _P, _P, POINTER(c_int), c_int, c_int, c_int, c_double, c_int,
+                               _P, _P, _P, _P]),
+    'xan_agg_to_year': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    'xan_basin_sum': (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (raises LibraryMissing when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise LibraryMissing("{} not found - build it with `make -C xanthos_b200/csrc` "
+                                 "(or __graft_entry__.build()); there is no CPU fallback".format(LIB_PATH))
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    """Map a C-ABI status to the exception type the reference raises for the same condition."""
+    if rc == XAN_OK:
+        return
+    msg = lib().xan_last_error().decode('utf-8', 'replace')
+    if rc == XAN_E_SPINUP:
+        raise IndexError(msg)                       # abcd.py:253-266
+    if rc == XAN_E_INVALID:
+        raise ValidationException(msg)
+    raise RuntimeError("libxanthos_b200: {} (code {})".format(msg, rc))
+
+
+def check_ptr(p):
+    if not p:
+        raise ValidationException(lib().xan_last_error().decode('utf-8', 'replace'))
+    return p
+
+
+# ------------------------------------------------------------------------------------------------
+# torch plumbing
+# ------------------------------------------------------------------------------------------------
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("xanthos_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return torch
+
+
+def stream_ptr():
+    torch = torch_cuda()
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def padded_ld(ncell):
+    """Row pitch of month-major fields: a multiple of 16 doubles (128 B) so every month row is line aligned."""
+    return (int(ncell) + 15) // 16 * 16
+
+
+def ptr(t):
+    return c_void_p(0) if t is None else c_void_p(t.data_ptr())
+
+
+def as_c(arr, dtype):
+    a = np.ascontiguousarray(arr, dtype=dtype)
+    ct = {np.float64: c_double, np.int32: c_int, np.int64: c_int64}[dtype]
+    return a, a.ctypes.data_as(POINTER(ct))
+
+
+def dev_vector(arr, dtype=np.float64):
+    """Small per-cell vector -> device tensor."""
+    torch = torch_cuda()
+    if isinstance(arr, torch.Tensor):
+        return arr.to(device='cuda', dtype={np.float64: torch.float64, np.int32: torch.int32}[dtype]).contiguous()
+    a = np.ascontiguousarray(np.asarray(arr).reshape(-1), dtype=dtype)
+    return torch.from_numpy(a).cuda()
+
+
+class Field:
+    """
+    A month-major fp64 field resident in HBM: tensor [nmonths, ld], element (m, c) at t[m, c].
+
+    The reference hands [ncell, nmonths] host arrays between its stages; `from_host` / `to_host`
+    are the only places where that layout is converted (one transpose kernel each way).
+    """
+
+    __slots__ = ('t', 'ncell', 'nmonths')
+
+    def __init__(self, t, ncell):
+        self.t = t
+        self.ncell = int(ncell)
+        self.nmonths = int(t.shape[0])
+
+    @property
+    def ld(self):
+        return int(self.t.shape[1])
+
+    @classmethod
+    def empty(cls, ncell, nmonths, ld=None):
+        torch = torch_cuda()
+        ld = ld or padded_ld(ncell)
+        return cls(torch.empty((nmonths, ld), dtype=torch.float64, device='cuda'), ncell)
+
+    @classmethod
+    def from_host(cls, arr, nan_to_num=False, ld=None):
+        """[ncell, nmonths] host array (numpy, ideally in pinned memory) or cuda tensor -> Field."""
+        torch = torch_cuda()
+        if isinstance(arr, Field):
+            return arr
+        if isinstance(arr, torch.Tensor):
+            src = arr.to(device='cuda', dtype=torch.float64, non_blocking=True).contiguous()
+        else:
+            a = np.asarray(arr)
+            if a.dtype != np.float64 or not a.flags['C_CONTIGUOUS']:
+                a = np.ascontiguousarray(a, dtype=np.float64)
+            src = torch.from_numpy(a).to('cuda', non_blocking=True)
+        ncell, nmonths = src.shape
+        f = cls.empty(ncell, nmonths, ld)
+        check(lib().xan_to_month_major(ptr(src), ptr(f.t), ncell, nmonths, f.ld, int(bool(nan_to_num)), stream_ptr()))
+        return f
+
+    def to_device_cell_major(self):
+        torch = torch_cuda()
+        out = torch.empty((self.ncell, self.nmonths), dtype=torch.float64, device='cuda')
+        check(lib().xan_to_cell_major(ptr(self.t), ptr(out), self.ncell, self.nmonths, self.ld, stream_ptr()))
+        return out
+
+    def to_host(self):
+        """Field -> [ncell, nmonths] numpy array backed by pinned memory (torch's caching host allocator)."""
+        torch = torch_cuda()
+        dev = self.to_device_cell_major()
+        host = torch.empty((self.ncell, self.nmonths), dtype=torch.float64, pin_memory=True)
+        host.copy_(dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()
+
+
+# Device copies of arrays handed back to the caller, so that the next stage of
+# Components.simulation (PET -> runoff -> routing) finds its input already in HBM.
+_resident = {}
+
+
+def remember(host_array, field):
+    import weakref
+    key = id(host_array)
+    _resident[key] = (weakref.ref(host_array, lambda _r, k=key: _resident.pop(k, None)), field)
+    return host_array
+
+
+def resident(host_array):
+    hit = _resident.get(id(host_array))
+    if hit is not None and hit[0]() is host_array:
+        return hit[1]
+    return None
+
+
+def forget_all():
+    _resident.clear()
+
+
+def as_field(x, nan_to_num=False):
+    """Field for `x`: an existing Field, the device copy of a previously returned array, or a fresh upload."""
+    if x is None:
+        return None
+    if isinstance(x, Field):
+        return x
+    f = resident(x)
+    if f is not None:
+        return f
+    return Field.from_host(x, nan_to_num=nan_to_num)

@@ -1,0 +1,582 @@
+// ABCD runoff kernels (xanthos/runoff/abcd.py) and the batched calibration objective
+// (xanthos/calibrate/calibrate_abcd.py).  fp64, month-major fields, compiled with -fmad=false.
+//
+// Structure of one run (ABCD.emulate, abcd.py:305-311):
+//   1. abcd_spinup_kernel   - thread per cell, state (snowpack, SW, G) in registers for the whole
+//                             spin-up; only the three "December" snapshots leave the SM.
+//   2. abcd_reinit_kernel   - block per basin, deterministic nanmean over the basin's cells
+//                             (set_vals, abcd.py:246-282).
+//   3. abcd_sim_kernel      - thread per cell, state in registers, streams AET / Q / SW out.
+#include "common.cuh"
+
+#include <vector>
+#include <algorithm>
+#include <numeric>
+
+struct xan_abcd_plan {
+    int ncell = 0;
+    int n_basins = 0;
+    int max_basin_cells = 0;
+    std::vector<int> h_offsets;   // [n_basins + 1]
+    std::vector<int> h_order;     // cells sorted by basin (stable)
+    int *d_basin_idx = nullptr;   // [ncell] row of the parameter table, < 0 = not simulated
+    int *d_order = nullptr;       // [n_live]
+    int *d_offsets = nullptr;     // [n_basins + 1]
+};
+
+namespace xan {
+
+constexpr double TRAIN = 2.5;   // abcd.py:103
+constexpr double TSNOW = 0.6;   // abcd.py:104
+constexpr double SW_INIT = 100.0, GW_INIT = 500.0;   // abcd.py:82-84
+
+struct AbcdPar {
+    double a2, b, b_over_a, c, d, d1, m;
+};
+
+__device__ __forceinline__ AbcdPar load_par(const double *__restrict__ pars, int row, bool snow) {
+    AbcdPar q;
+    const double a = pars[row * 5 + 0];
+    q.b = pars[row * 5 + 1] * 1000;   // :48
+    q.c = pars[row * 5 + 2];
+    q.d = pars[row * 5 + 3];
+    q.m = snow ? pars[row * 5 + 4] : 0.0;
+    q.a2 = a * 2;                     // :54
+    q.b_over_a = q.b / a;             // :55
+    q.d1 = q.d + 1;                   // :56
+    return q;
+}
+
+// numpy.maximum / numpy.minimum propagate NaN (abcd.py:223-224)
+__device__ __forceinline__ double np_maximum(double a, double b) {
+    return (isnan(a) || isnan(b)) ? (a + b) : (a >= b ? a : b);
+}
+__device__ __forceinline__ double np_minimum(double a, double b) {
+    return (isnan(a) || isnan(b)) ? (a + b) : (a <= b ? a : b);
+}
+
+// One month of ABCD.abcd_dist (abcd.py:171-228) for one cell.
+template <bool SNOW>
+__device__ __forceinline__ void abcd_step(bool first, double p, double e, double t, const AbcdPar &par,
+                                          double &snowpack, double &sw, double &g, double &aet_out,
+                                          double &q_out) {
+    double rain = p, snm = 0.0;
+    if (SNOW) {
+        const bool allrain = t > TRAIN;
+        const bool mixed = (t <= TRAIN) && (t >= TSNOW);
+        const bool allsnow = t < TSNOW;
+        double snow = 0.0;                                                    // :141-169
+        rain = 0.0;
+        if (mixed) {
+            snow = p * (TRAIN - t) / (TRAIN - TSNOW);
+            rain = p - snow;
+        } else if (allrain) {
+            rain = p;
+        } else if (allsnow) {
+            snow = p;
+        }
+        snowpack = (first ? 0.0 : snowpack) + snow;                           // :178-181
+        if (allrain) snm = snowpack * par.m;                                  // :189-192
+        else if (mixed) snm = (snowpack * par.m) * ((TRAIN - t) / (TRAIN - TSNOW));
+        snowpack = snowpack - snm;                                            // :195
+    }
+    const double w = first ? (rain + sw) : (rain + sw + snm);                 // :198-201
+    const double x = (w + par.b) / par.a2;                                    // :204-205
+    const double y = x - sqrt(x * x - (w * par.b_over_a));                    // :206
+    const double swt = y * exp(-e / par.b);                                   // :209
+    const double awet = w - y;                                                // :212
+    const double c_awet = par.c * awet;                                       // :213
+    g = (g + c_awet) / par.d1;                                                // :216-219
+    double aet = y - swt;                                                     // :222
+    aet = np_maximum(0.0, aet);                                               // :223
+    aet = np_minimum(e, aet);                                                 // :224
+    sw = y - aet;                                                             // :225
+    q_out = (awet - c_awet) + par.d * g;                                      // :226
+    aet_out = aet;
+}
+
+constexpr int ABCD_U = 4;   // months of forcing in flight per thread (software prefetch)
+
+template <bool SNOW>
+__global__ void __launch_bounds__(128)
+    abcd_spinup_kernel(const double *__restrict__ pet, const double *__restrict__ precip,
+                       const double *__restrict__ tmin, const int *__restrict__ basin_idx,
+                       const double *__restrict__ pars, int ncell, int spinup, int ld,
+                       double *__restrict__ snap /* [6][ncell]: SW x3, G x3 */) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const int row = basin_idx[c];
+    if (row < 0) return;
+    const AbcdPar par = load_par(pars, row, SNOW);
+    double snowpack = 0.0, sw = SW_INIT, g = GW_INIT;
+    const int s1 = spinup - 25, s2 = spinup - 13, s3 = spinup - 1;   // Decembers -25, -13, -1 (:255)
+    int i = 0;
+    for (; i + ABCD_U <= spinup; i += ABCD_U) {
+        double p[ABCD_U], e[ABCD_U], t[ABCD_U];
+#pragma unroll
+        for (int u = 0; u < ABCD_U; ++u) {
+            const size_t off = (size_t)(i + u) * ld + c;
+            p[u] = ldg_stream(precip + off);
+            e[u] = ldg_stream(pet + off);
+            t[u] = SNOW ? ldg_stream(tmin + off) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < ABCD_U; ++u) {
+            double aet, q;
+            abcd_step<SNOW>(i + u == 0, p[u], e[u], t[u], par, snowpack, sw, g, aet, q);
+            const int k = i + u;
+            if (k == s1) { snap[2 * (size_t)ncell + c] = sw; snap[5 * (size_t)ncell + c] = g; }
+            if (k == s2) { snap[1 * (size_t)ncell + c] = sw; snap[4 * (size_t)ncell + c] = g; }
+            if (k == s3) { snap[0 * (size_t)ncell + c] = sw; snap[3 * (size_t)ncell + c] = g; }
+        }
+    }
+    for (; i < spinup; ++i) {
+        const size_t off = (size_t)i * ld + c;
+        double aet, q;
+        abcd_step<SNOW>(i == 0, precip[off], pet[off], SNOW ? tmin[off] : 0.0, par, snowpack, sw, g, aet, q);
+        if (i == s1) { snap[2 * (size_t)ncell + c] = sw; snap[5 * (size_t)ncell + c] = g; }
+        if (i == s2) { snap[1 * (size_t)ncell + c] = sw; snap[4 * (size_t)ncell + c] = g; }
+        if (i == s3) { snap[0 * (size_t)ncell + c] = sw; snap[3 * (size_t)ncell + c] = g; }
+    }
+}
+
+// Deterministic block reduction of (sum, count) pairs; result valid in thread 0.
+template <int NT>
+__device__ __forceinline__ void block_reduce2(double &s, double &n, double *scratch /* [2 * NT/32] */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        n += __shfl_down_sync(0xffffffffu, n, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) {
+        scratch[2 * w] = s;
+        scratch[2 * w + 1] = n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tn = 0.0;
+        for (int k = 0; k < NT / 32; ++k) {
+            ts += scratch[2 * k];
+            tn += scratch[2 * k + 1];
+        }
+        s = ts;
+        n = tn;
+    }
+}
+
+// set_vals (abcd.py:246-282): per basin, mean over the 3 Decembers of nanmean over cells.
+__global__ void __launch_bounds__(256)
+    abcd_reinit_kernel(const double *__restrict__ snap, const int *__restrict__ order,
+                       const int *__restrict__ offsets, int ncell, double *__restrict__ init /* [nb][2] */) {
+    __shared__ double scratch[16];
+    const int b = blockIdx.x;
+    const int beg = offsets[b], end = offsets[b + 1];
+    double mean3[2];
+    for (int v = 0; v < 2; ++v) {
+        double acc = 0.0;   // only meaningful in thread 0
+        for (int k = 0; k < 3; ++k) {
+            double s = 0.0, n = 0.0;
+            const double *src = snap + (size_t)(v * 3 + k) * ncell;
+            for (int j = beg + threadIdx.x; j < end; j += blockDim.x) {
+                const double x = src[order[j]];
+                if (!isnan(x)) {
+                    s += x;
+                    n += 1.0;
+                }
+            }
+            block_reduce2<256>(s, n, scratch);
+            acc = acc + s / n;   // nanmean; 0/0 -> NaN like numpy
+        }
+        mean3[v] = acc / 3.0;
+    }
+    if (threadIdx.x == 0) {
+        init[2 * b] = mean3[0];
+        init[2 * b + 1] = mean3[1];
+    }
+}
+
+template <bool SNOW>
+__global__ void __launch_bounds__(128)
+    abcd_sim_kernel(const double *__restrict__ pet, const double *__restrict__ precip,
+                    const double *__restrict__ tmin, const int *__restrict__ basin_idx,
+                    const double *__restrict__ pars, const double *__restrict__ init, int ncell, int nmonths,
+                    int ld, double *__restrict__ aet_o, double *__restrict__ q_o, double *__restrict__ sav_o) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const int row = basin_idx[c];
+    if (row < 0) {
+        // not simulated: the reference leaves these rows uninitialised (abcd.py:384-389)
+        const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+        for (int i = 0; i < nmonths; ++i) {
+            const size_t off = (size_t)i * ld + c;
+            if (aet_o) aet_o[off] = nanv;
+            if (q_o) q_o[off] = nanv;
+            if (sav_o) sav_o[off] = nanv;
+        }
+        return;
+    }
+    const AbcdPar par = load_par(pars, row, SNOW);
+    double snowpack = 0.0, sw = init[2 * row], g = init[2 * row + 1];
+    int i = 0;
+    for (; i + ABCD_U <= nmonths; i += ABCD_U) {
+        double p[ABCD_U], e[ABCD_U], t[ABCD_U];
+#pragma unroll
+        for (int u = 0; u < ABCD_U; ++u) {
+            const size_t off = (size_t)(i + u) * ld + c;
+            p[u] = ldg_stream(precip + off);
+            e[u] = ldg_stream(pet + off);
+            t[u] = SNOW ? ldg_stream(tmin + off) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < ABCD_U; ++u) {
+            double aet, q;
+            abcd_step<SNOW>(i + u == 0, p[u], e[u], t[u], par, snowpack, sw, g, aet, q);
+            const size_t off = (size_t)(i + u) * ld + c;
+            if (aet_o) stg_stream(aet_o + off, aet);
+            if (q_o) stg_stream(q_o + off, q);
+            if (sav_o) stg_stream(sav_o + off, sw);
+        }
+    }
+    for (; i < nmonths; ++i) {
+        const size_t off = (size_t)i * ld + c;
+        double aet, q;
+        abcd_step<SNOW>(i == 0, precip[off], pet[off], SNOW ? tmin[off] : 0.0, par, snowpack, sw, g, aet, q);
+        if (aet_o) stg_stream(aet_o + off, aet);
+        if (q_o) stg_stream(q_o + off, q);
+        if (sav_o) stg_stream(sav_o + off, sw);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Calibration objective, batched over parameter sets (calibrate_abcd.py:134-162, 176-213).
+// block = (parameter set p, basin slot i).  Every thread owns the cells j = tid, tid + NT, ... of
+// the basin; their (snowpack, SW, G) live in shared memory; months are the outer loop, so the
+// forcing of the basin is streamed once per block and re-used from L2 by the other parameter
+// sets of the same basin (blockIdx.x = p is the fastest index).
+// ---------------------------------------------------------------------------------------------
+constexpr int KGE_NT = 128;
+
+template <bool SNOW>
+__global__ void __launch_bounds__(KGE_NT)
+    abcd_kge_kernel(const double *__restrict__ pet, const double *__restrict__ precip,
+                    const double *__restrict__ tmin, const double *__restrict__ area,
+                    const int *__restrict__ order, const int *__restrict__ offsets,
+                    const int *__restrict__ slot_basin /* [nb] plan row, sorted by size desc */,
+                    const int *__restrict__ slot_out /* [nb] caller slot */, const double *__restrict__ pars,
+                    const double *__restrict__ obs, int npar, int nmonths, int spinup, int ld, int unit_km3,
+                    double *__restrict__ ed_out, double *__restrict__ series_out) {
+    extern __shared__ double smem[];
+    const int p = blockIdx.x;
+    const int b = slot_basin[blockIdx.y];
+    const int slot = slot_out[blockIdx.y];
+    const int beg = offsets[b], nb = offsets[b + 1] - beg;
+    constexpr int NW = KGE_NT / 32;
+    double *st_sw = smem;                 // [nb]
+    double *st_g = st_sw + nb;            // [nb]
+    double *st_sn = st_g + nb;            // [nb]
+    double *part = st_sn + nb;            // [NW][nmonths] per-warp partial basin sums
+    double *scratch = part + (size_t)NW * nmonths;   // [16]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const AbcdPar par = load_par(pars, slot * npar + p, SNOW);
+
+    // ---- spin-up ------------------------------------------------------------------------------
+    for (int j = threadIdx.x; j < nb; j += KGE_NT) {
+        st_sw[j] = SW_INIT;
+        st_g[j] = GW_INIT;
+        st_sn[j] = 0.0;
+    }
+    const int s1 = spinup - 25, s2 = spinup - 13, s3 = spinup - 1;
+    double dsum[6] = {0, 0, 0, 0, 0, 0}, dcnt[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < spinup; ++i) {
+        const size_t off = (size_t)i * ld;
+        const int which = (i == s3) ? 0 : (i == s2) ? 1 : (i == s1) ? 2 : -1;
+        for (int j = threadIdx.x; j < nb; j += KGE_NT) {
+            const int c = order[beg + j];
+            double sn = st_sn[j], sw = st_sw[j], g = st_g[j], aet, q;
+            abcd_step<SNOW>(i == 0, __ldg(precip + off + c), __ldg(pet + off + c),
+                            SNOW ? __ldg(tmin + off + c) : 0.0, par, sn, sw, g, aet, q);
+            st_sn[j] = sn;
+            st_sw[j] = sw;
+            st_g[j] = g;
+            if (which >= 0) {
+                if (!isnan(sw)) { dsum[which] += sw; dcnt[which] += 1.0; }
+                if (!isnan(g)) { dsum[3 + which] += g; dcnt[3 + which] += 1.0; }
+            }
+        }
+    }
+    // ---- basin re-initialisation (set_vals with all cells in one basin, :143) --------------------
+    __shared__ double init_sw, init_g;
+    {
+        double m_sw = 0.0, m_g = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            double s = dsum[k], n = dcnt[k];
+            block_reduce2<KGE_NT>(s, n, scratch);
+            m_sw = m_sw + s / n;
+            s = dsum[3 + k];
+            n = dcnt[3 + k];
+            block_reduce2<KGE_NT>(s, n, scratch);
+            m_g = m_g + s / n;
+        }
+        if (threadIdx.x == 0) {
+            init_sw = m_sw / 3.0;
+            init_g = m_g / 3.0;
+        }
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < nb; j += KGE_NT) {
+        st_sw[j] = init_sw;
+        st_g[j] = init_g;
+        st_sn[j] = 0.0;
+    }
+    // ---- simulation + basin aggregation (nansum over cells, :159 / :162) -------------------------
+    for (int i = 0; i < nmonths; ++i) {
+        const size_t off = (size_t)i * ld;
+        double acc = 0.0;
+        for (int j = threadIdx.x; j < nb; j += KGE_NT) {
+            const int c = order[beg + j];
+            double sn = st_sn[j], sw = st_sw[j], g = st_g[j], aet, q;
+            abcd_step<SNOW>(i == 0, __ldg(precip + off + c), __ldg(pet + off + c),
+                            SNOW ? __ldg(tmin + off + c) : 0.0, par, sn, sw, g, aet, q);
+            st_sn[j] = sn;
+            st_sw[j] = sw;
+            st_g[j] = g;
+            const double v = unit_km3 ? (q * __ldg(area + c) * 1e-6) : q;
+            if (!isnan(v)) acc += v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) part[(size_t)warp * nmonths + i] = acc;
+    }
+    __syncthreads();
+    // ---- KGE distance (:197-211) --------------------------------------------------------------
+    const double *ob = obs + (size_t)slot * nmonths;
+    double sm = 0.0, so = 0.0;
+    for (int i = threadIdx.x; i < nmonths; i += KGE_NT) {
+        double m = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) m += part[(size_t)w * nmonths + i];
+        part[i] = m;   // warp 0's row now holds the basin series
+        if (series_out) series_out[((size_t)slot * npar + p) * nmonths + i] = m;
+        sm += m;
+        so += ob[i];
+    }
+    block_reduce2<KGE_NT>(sm, so, scratch);
+    __shared__ double mean_m, mean_o;
+    if (threadIdx.x == 0) {
+        mean_m = sm / nmonths;
+        mean_o = so / nmonths;
+    }
+    __syncthreads();
+    double vm = 0.0, vo = 0.0, cov = 0.0;
+    for (int i = threadIdx.x; i < nmonths; i += KGE_NT) {
+        const double dm = part[i] - mean_m, dob = ob[i] - mean_o;
+        vm += dm * dm;
+        vo += dob * dob;
+        cov += dm * dob;
+    }
+    double dummy = 0.0;
+    block_reduce2<KGE_NT>(vm, vo, scratch);
+    block_reduce2<KGE_NT>(cov, dummy, scratch);
+    if (threadIdx.x == 0) {
+        const double sd_m = sqrt(vm / nmonths), sd_o = sqrt(vo / nmonths);
+        const double relvar = sd_m / sd_o;
+        const double bias = mean_m / mean_o;
+        double r = cov / sqrt(vm * vo);
+        r = fmin(fmax(r, -1.0), 1.0);   // np.corrcoef clips to [-1, 1]
+        ed_out[(size_t)slot * npar + p] =
+            sqrt(((r - 1) * (r - 1)) + ((relvar - 1) * (relvar - 1)) + ((bias - 1) * (bias - 1)));
+    }
+}
+
+// out[m][b] = nansum over the cells of basin b of src[m][c] * w[c]; one warp per (basin, month).
+__global__ void __launch_bounds__(256)
+    basin_sum_kernel(const double *__restrict__ src, const double *__restrict__ w, const int *__restrict__ order,
+                     const int *__restrict__ offsets, int n_basins, int nmonths, int ld,
+                     double *__restrict__ out) {
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.y * (blockDim.x >> 5) + warp;
+    if (m >= nmonths) return;
+    const int beg = offsets[b], end = offsets[b + 1];
+    double acc = 0.0;
+    for (int j = beg + lane; j < end; j += 32) {
+        const int c = order[j];
+        double v = src[(size_t)m * ld + c];
+        if (w) v = v * w[c];
+        if (!isnan(v)) acc += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[(size_t)m * n_basins + b] = acc;
+}
+
+}  // namespace xan
+
+using namespace xan;
+
+extern "C" {
+
+xan_abcd_plan *xan_abcd_plan_create(const int *h_basin_idx, int ncell, int n_basins) {
+    if (!h_basin_idx || ncell <= 0 || n_basins <= 0) {
+        set_error("xan_abcd_plan_create: bad arguments (ncell=%d, n_basins=%d)", ncell, n_basins);
+        return nullptr;
+    }
+    auto *pl = new xan_abcd_plan();
+    pl->ncell = ncell;
+    pl->n_basins = n_basins;
+    pl->h_offsets.assign(n_basins + 1, 0);
+    for (int c = 0; c < ncell; ++c) {
+        const int b = h_basin_idx[c];
+        if (b >= n_basins) {
+            set_error("xan_abcd_plan_create: basin index %d of cell %d >= n_basins %d", b, c, n_basins);
+            delete pl;
+            return nullptr;
+        }
+        if (b >= 0) pl->h_offsets[b + 1]++;
+    }
+    for (int b = 0; b < n_basins; ++b) {
+        pl->max_basin_cells = std::max(pl->max_basin_cells, pl->h_offsets[b + 1]);
+        pl->h_offsets[b + 1] += pl->h_offsets[b];
+    }
+    const int n_live = pl->h_offsets[n_basins];
+    pl->h_order.assign(std::max(n_live, 1), 0);
+    std::vector<int> cur(pl->h_offsets.begin(), pl->h_offsets.end() - 1);
+    for (int c = 0; c < ncell; ++c) {
+        const int b = h_basin_idx[c];
+        if (b >= 0) pl->h_order[cur[b]++] = c;
+    }
+    bool ok = cudaMalloc(&pl->d_basin_idx, sizeof(int) * ncell) == cudaSuccess &&
+              cudaMalloc(&pl->d_order, sizeof(int) * std::max(n_live, 1)) == cudaSuccess &&
+              cudaMalloc(&pl->d_offsets, sizeof(int) * (n_basins + 1)) == cudaSuccess &&
+              cudaMemcpy(pl->d_basin_idx, h_basin_idx, sizeof(int) * ncell, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(pl->d_order, pl->h_order.data(), sizeof(int) * std::max(n_live, 1),
+                         cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(pl->d_offsets, pl->h_offsets.data(), sizeof(int) * (n_basins + 1),
+                         cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        set_error("xan_abcd_plan_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        xan_abcd_plan_destroy(pl);
+        return nullptr;
+    }
+    return pl;
+}
+
+void xan_abcd_plan_destroy(xan_abcd_plan *pl) {
+    if (!pl) return;
+    cudaFree(pl->d_basin_idx);
+    cudaFree(pl->d_order);
+    cudaFree(pl->d_offsets);
+    delete pl;
+}
+
+int xan_abcd_run(const xan_abcd_plan *pl, const double *d_pet, const double *d_precip, const double *d_tmin,
+                 const double *d_pars, int nmonths, int spinup, int ld, double *d_aet, double *d_q,
+                 double *d_sav, void *stream) {
+    XAN_REQUIRE(pl && d_pet && d_precip && d_pars, "xan_abcd_run: null pointer");
+    XAN_REQUIRE(nmonths > 0 && ld >= pl->ncell, "xan_abcd_run: bad shape nmonths=%d ld=%d", nmonths, ld);
+    if (spinup < 25) {
+        // ABCD.set_vals indexes month -25 of the spin-up arrays (abcd.py:255-266)
+        set_error("Spin-up steps must produce at least 10 years spin-up. Your spin-up only consist of %d months. "
+                  "Please reconfigure and try again.", spinup);
+        return XAN_E_SPINUP;
+    }
+    XAN_REQUIRE(spinup <= nmonths, "xan_abcd_run: spinup (%d) exceeds the %d months of forcing", spinup, nmonths);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int ncell = pl->ncell;
+    double *snap = nullptr, *init = nullptr;
+    XAN_CUDA_CHECK(cudaMallocAsync(&snap, sizeof(double) * 6 * (size_t)ncell, s));
+    XAN_CUDA_CHECK(cudaMallocAsync(&init, sizeof(double) * 2 * (size_t)pl->n_basins, s));
+    const int grid = ceil_div(ncell, 128);
+    if (d_tmin)
+        abcd_spinup_kernel<true><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, pl->d_basin_idx, d_pars, ncell,
+                                                      spinup, ld, snap);
+    else
+        abcd_spinup_kernel<false><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, pl->d_basin_idx, d_pars, ncell,
+                                                       spinup, ld, snap);
+    abcd_reinit_kernel<<<pl->n_basins, 256, 0, s>>>(snap, pl->d_order, pl->d_offsets, ncell, init);
+    if (d_tmin)
+        abcd_sim_kernel<true><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, pl->d_basin_idx, d_pars, init, ncell,
+                                                   nmonths, ld, d_aet, d_q, d_sav);
+    else
+        abcd_sim_kernel<false><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, pl->d_basin_idx, d_pars, init, ncell,
+                                                    nmonths, ld, d_aet, d_q, d_sav);
+    XAN_CUDA_CHECK(cudaGetLastError());
+    XAN_CUDA_CHECK(cudaFreeAsync(snap, s));
+    XAN_CUDA_CHECK(cudaFreeAsync(init, s));
+    return XAN_OK;
+}
+
+int xan_abcd_kge_batch(const xan_abcd_plan *pl, const int *h_basins, int nb, int npar, const double *d_pet,
+                       const double *d_precip, const double *d_tmin, const double *d_area, const double *d_pars,
+                       const double *d_obs, int nmonths, int spinup, int ld, int unit_km3, double *d_ed,
+                       double *d_series, void *stream) {
+    XAN_REQUIRE(pl && h_basins && d_pet && d_precip && d_pars && d_obs && d_ed, "xan_abcd_kge_batch: null pointer");
+    XAN_REQUIRE(!unit_km3 || d_area, "xan_abcd_kge_batch: km3_per_mth needs the cell areas");
+    XAN_REQUIRE(nb > 0 && npar > 0 && nmonths > 0 && ld >= pl->ncell, "xan_abcd_kge_batch: bad shape");
+    if (spinup < 25) {
+        set_error("Spin-up steps must produce at least 10 years spin-up. Your spin-up only consist of %d months. "
+                  "Please reconfigure and try again.", spinup);
+        return XAN_E_SPINUP;
+    }
+    XAN_REQUIRE(spinup <= nmonths, "xan_abcd_kge_batch: spinup (%d) exceeds the %d months of forcing", spinup,
+                nmonths);
+    cudaStream_t s = (cudaStream_t)stream;
+    // schedule big basins first (longest-processing-time order)
+    std::vector<int> slots(nb);
+    std::iota(slots.begin(), slots.end(), 0);
+    int max_cells = 0;
+    for (int i = 0; i < nb; ++i) {
+        XAN_REQUIRE(h_basins[i] >= 0 && h_basins[i] < pl->n_basins, "xan_abcd_kge_batch: basin row %d out of range",
+                    h_basins[i]);
+        const int n = pl->h_offsets[h_basins[i] + 1] - pl->h_offsets[h_basins[i]];
+        XAN_REQUIRE(n > 0, "xan_abcd_kge_batch: basin row %d has no cells", h_basins[i]);
+        max_cells = std::max(max_cells, n);
+    }
+    std::stable_sort(slots.begin(), slots.end(), [&](int x, int y) {
+        const int nx = pl->h_offsets[h_basins[x] + 1] - pl->h_offsets[h_basins[x]];
+        const int ny = pl->h_offsets[h_basins[y] + 1] - pl->h_offsets[h_basins[y]];
+        return nx > ny;
+    });
+    std::vector<int> h_meta(2 * nb);
+    for (int i = 0; i < nb; ++i) {
+        h_meta[i] = h_basins[slots[i]];
+        h_meta[nb + i] = slots[i];
+    }
+    const size_t smem = sizeof(double) * (3 * (size_t)max_cells + (KGE_NT / 32) * (size_t)nmonths + 16);
+    XAN_REQUIRE(smem <= 227 * 1024, "xan_abcd_kge_batch: basin with %d cells x %d months needs %zu B of shared memory",
+                max_cells, nmonths, smem);
+    int *d_meta = nullptr;
+    XAN_CUDA_CHECK(cudaMallocAsync(&d_meta, sizeof(int) * 2 * nb, s));
+    XAN_CUDA_CHECK(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(int) * 2 * nb, cudaMemcpyHostToDevice, s));
+    dim3 grid(npar, nb);
+    if (d_tmin) {
+        XAN_CUDA_CHECK(cudaFuncSetAttribute(abcd_kge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        abcd_kge_kernel<true><<<grid, KGE_NT, smem, s>>>(d_pet, d_precip, d_tmin, d_area, pl->d_order, pl->d_offsets,
+                                                         d_meta, d_meta + nb, d_pars, d_obs, npar, nmonths, spinup, ld,
+                                                         unit_km3, d_ed, d_series);
+    } else {
+        XAN_CUDA_CHECK(cudaFuncSetAttribute(abcd_kge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        abcd_kge_kernel<false><<<grid, KGE_NT, smem, s>>>(d_pet, d_precip, d_tmin, d_area, pl->d_order, pl->d_offsets,
+                                                          d_meta, d_meta + nb, d_pars, d_obs, npar, nmonths, spinup, ld,
+                                                          unit_km3, d_ed, d_series);
+    }
+    XAN_CUDA_CHECK(cudaGetLastError());
+    XAN_CUDA_CHECK(cudaFreeAsync(d_meta, s));
+    return XAN_OK;
+}
+
+int xan_basin_sum(const xan_abcd_plan *pl, const double *d_src, const double *d_w, int nmonths, int ld,
+                  double *d_out, void *stream) {
+    XAN_REQUIRE(pl && d_src && d_out, "xan_basin_sum: null pointer");
+    XAN_REQUIRE(nmonths > 0 && ld >= pl->ncell, "xan_basin_sum: bad shape");
+    dim3 grid(pl->n_basins, ceil_div(nmonths, 8));
+    basin_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_src, d_w, pl->d_order, pl->d_offsets, pl->n_basins,
+                                                            nmonths, ld, d_out);
+    XAN_CUDA_CHECK(cudaGetLastError());
+    return XAN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// Shared helpers of libxanthos_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cmath>
+#include <cfloat>
+
+#include "../../include/xanthos_b200.h"
+
+namespace xan {
+
+void set_error(const char *fmt, ...);
+
+#define XAN_CUDA_CHECK(expr)                                                                  \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            xan::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,               \
+                           cudaGetErrorString(_e));                                           \
+            return XAN_E_CUDA;                                                                \
+        }                                                                                     \
+    } while (0)
+
+#define XAN_REQUIRE(cond, ...)                                                                \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            xan::set_error(__VA_ARGS__);                                                      \
+            return XAN_E_INVALID;                                                             \
+        }                                                                                     \
+    } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Gregorian month length (calendar.monthrange; penman_monteith.py:57, hargreaves_samani.py:26,
+// thornthwaite.py:113).  moy in 0..11.
+__host__ __device__ inline bool is_leap_gregorian(int y) {
+    return (y % 4 == 0) && ((y % 100 != 0) || (y % 400 == 0));
+}
+__host__ __device__ inline int month_days(int moy, bool leap) {
+    const int d = (moy == 1) ? 28 : ((moy == 3 || moy == 5 || moy == 8 || moy == 10) ? 30 : 31);
+    return (moy == 1 && leap) ? 29 : d;
+}
+
+// numpy.nan_to_num for float64
+__device__ __forceinline__ double nan_to_num(double v) {
+    if (isnan(v)) return 0.0;
+    if (isinf(v)) return v > 0 ? DBL_MAX : -DBL_MAX;
+    return v;
+}
+
+// Streaming (read-once) global load that does not allocate in L1.
+__device__ __forceinline__ double ldg_stream(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+// Streaming store (evict-first): outputs are written once and not re-read by the same kernel.
+__device__ __forceinline__ void stg_stream(double *p, double v) {
+    asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+}  // namespace xan
