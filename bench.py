@@ -1,0 +1,464 @@
+#!/usr/bin/env python
+"""
+Benchmark of the Xanthos hot path (BASELINE.json: cell-months/s for PM + ABCD + MRTM).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload = "pm_abcd_mrtm_360"): BASELINE.json configs[0]/[1] shape - Penman-Monteith
+PET -> ABCD runoff -> MRTM routing, 67,420 cells x 360 months (1971-2000), synthetic forcing,
+runoff spin-up 360 months, routing spin-up 360 months, 3-hour routing sub-steps, nlcs = 8.
+A "step" is one pass of that pipeline over one member.  At N > 1 every rank runs one member
+(ensemble sharding, weak scaling, no collective in the data path; the basin-aggregated runoff and
+streamflow [360 x 235] of every member are all-gathered over NCCL at the end of the step).
+
+  value : cell-months/s with the forcing already resident in HBM (month-major fields), device time
+  e2e   : same metric through the reference-facing plug-in calls (run_pmpet / abcd_execute /
+          route) with pinned HOST buffers in and host ndarrays out; H2D and D2H inside the timing
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from types import SimpleNamespace
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NCELL, NMONTHS, START_YR, END_YR = 67420, 360, 1971, 2000
+NLCS, N_BASINS = 8, 235
+RUNOFF_SPINUP, ROUTING_SPINUP, DT = 360, 360, 3 * 3600
+WORKLOAD = "pm_abcd_mrtm_360"
+
+# algorithmic bytes per cell-month (fp64, every array touched once; SURVEY.md section 8d / DESIGN.md)
+BYTES_PM = 6 * 8 + NLCS * 8 / 12.0 + 8          # 6 forcings + land cover (once per year) + PET out = 61.3
+BYTES_ABCD = 24 + 24 + 24 * RUNOFF_SPINUP / NMONTHS   # sim reads + writes + spin-up reads = 72
+BYTES_MRTM = 8 + 16 + 8 * ROUTING_SPINUP / NMONTHS    # q + (ChStorage, Avg_ChFlow) + spin-up reads = 32
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return json.load(f), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(',')]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    smax.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), p[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out['sm_mhz'] = float(np.median(sm))
+            out['sm_max_mhz'] = float(max(smax))
+        out['reasons'] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs
+# ------------------------------------------------------------------------------------------------
+def build_inputs(member_seed=1, ncell=NCELL, nmonths=NMONTHS):
+    from xanthos_b200 import synthetic
+    if ncell == NCELL:
+        world = synthetic.make_world(seed=0)
+    else:
+        world = synthetic.make_world(36, 72, ncell, 12, seed=0)
+    end_yr = START_YR + nmonths // 12 - 1
+    pm = synthetic.pm_inputs(world, START_YR, end_yr, nlcs=NLCS, seed=member_seed)
+    ab = synthetic.abcd_inputs(world, nmonths, seed=member_seed, with_pet=False)
+    for k in ('tair_load', 'TMIN_load', 'rhs_load', 'wind_load', 'rsds_load', 'rlds_load'):
+        pm[k] = np.nan_to_num(pm[k])
+    ab['tmin'] = np.nan_to_num(ab['tmin'])
+    return world, pm, ab, end_yr
+
+
+def month_days_mod4(nmonths, start_yr):
+    d = []
+    for y in range(start_yr, start_yr + nmonths // 12):
+        d += [31, 29 if y % 4 == 0 else 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31]
+    return np.array(d, dtype=np.int32)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world_size, local_rank):
+    import torch
+    import torch.distributed as dist
+    from xanthos_b200 import _cuda as C
+    from xanthos_b200.pet import penman_monteith as pm_mod
+    from xanthos_b200.runoff import abcd as abcd_mod
+    from xanthos_b200.routing import mrtm as mrtm_mod
+
+    torch.cuda.set_device(local_rank)
+    C.lib()
+    ncell, nmonths = args.ncell, args.nmonths
+    world, pm, ab, end_yr = build_inputs(member_seed=1 + rank, ncell=ncell, nmonths=nmonths)
+    settings = world.settings()
+    ndays = month_days_mod4(nmonths, START_YR)
+    spin_ro, spin_rt = min(RUNOFF_SPINUP, nmonths), min(ROUTING_SPINUP, nmonths)
+    lc_years = pm['lc_years']
+
+    # ---- static, device-resident -------------------------------------------------------------------
+    dsid = mrtm_mod.downstream(world.coords, world.flow_dir, settings)
+    upid = mrtm_mod.upstream(world.coords, dsid, settings)
+    um = mrtm_mod.upstream_genmatrix(upid)
+    rows = abcd_mod._basin_rows(world.n_basins, world.basin_ids, world.n_basins)
+    plan = abcd_mod.basin_plan(rows, world.n_basins)
+    d_L, d_V, d_A = C.dev_vector(world.flow_dist), C.dev_vector(world.velocity), C.dev_vector(world.area)
+    d_Akm3 = d_A * 1e-6
+    d_pars = torch.from_numpy(ab['pars']).cuda()
+
+    # ---- host inputs in pinned memory (what a DataLoader would hold) --------------------------------
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).pin_memory()
+        return t.numpy()
+    forc_names = ('tair_load', 'TMIN_load', 'rhs_load', 'wind_load', 'rsds_load', 'rlds_load')
+    host = {k: pinned(pm[k]) for k in forc_names}
+    host['precip'] = pinned(ab['precip'])
+    host['tmin'] = pinned(ab['tmin'])
+    host['lct_load'] = pinned(pm['lct_load'])
+    tables = {k: pm[k] for k in pm if k not in forc_names + ('lct_load', 'tairprev_load')}
+    h2d_bytes = sum(v.nbytes for v in host.values())
+
+    # ---- device-resident copies for the `value` leg ---------------------------------------------------
+    dev = {k: C.Field.from_host(host[k]) for k in forc_names + ('precip', 'tmin')}
+    d_lct = pm_mod.stage_land_cover(host['lct_load'], dev['tair_load'].ld)
+    d_elev = C.dev_vector(pm['elev'])
+    torch.cuda.synchronize()
+
+    def data_ns(src, lct):
+        d = dict(tables)
+        d.update({k: src[k] for k in forc_names})
+        d['lct_load'] = lct
+        d['elev'] = d_elev
+        return SimpleNamespace(**d)
+
+    stage_ms = {'pm': [], 'abcd': [], 'mrtm': [], 'agg': []}
+
+    def device_step(record=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        pet = pm_mod.run_pmpet_device(data_ns(dev, d_lct), ncell, NLCS, START_YR, end_yr, pm['water_idx'],
+                                      pm['snow_idx'], lc_years)
+        ev[1].record()
+        res = abcd_mod.run_device(plan, d_pars, pet, dev['precip'], dev['tmin'], nmonths, spin_ro)
+        ev[2].record()
+        chs, avg, inst = mrtm_mod.route_device(um, res['q'], d_L, d_V, d_A, ndays, DT, spin_rt)
+        ev[3].record()
+        # basin aggregates: runoff in km3/month and mean streamflow, [nmonths, n_basins]
+        agg = torch.empty((2, nmonths, world.n_basins), dtype=torch.float64, device='cuda')
+        C.check(C.lib().xan_basin_sum(plan._plan, C.ptr(res['q'].t), C.ptr(d_Akm3), nmonths, res['q'].ld,
+                                      C.ptr(agg[0]), C.stream_ptr()))
+        C.check(C.lib().xan_basin_sum(plan._plan, C.ptr(avg.t), None, nmonths, avg.ld, C.ptr(agg[1]), C.stream_ptr()))
+        if world_size > 1:
+            gathered = [torch.empty_like(agg) for _ in range(world_size)]
+            dist.all_gather(gathered, agg)
+        ev[4].record()
+        if record:
+            torch.cuda.synchronize()
+            for k, i in (('pm', 0), ('abcd', 1), ('mrtm', 2), ('agg', 3)):
+                stage_ms[k].append(ev[i].elapsed_time(ev[i + 1]))
+        return pet, res, chs, avg, agg
+
+    d2h_bytes_holder = [0]
+
+    def e2e_step():
+        """Reference-facing plug-in calls on host buffers (the Components.simulation sequence)."""
+        C.forget_all()
+        pet = pm_mod.run_pmpet(data_ns(host, host['lct_load']), ncell, NLCS, START_YR, end_yr, pm['water_idx'],
+                               pm['snow_idx'], lc_years)
+        pet, aet, q, sav = abcd_mod.abcd_execute(n_basins=world.n_basins, basin_ids=world.basin_ids, pet=pet,
+                                                 precip=host['precip'], tmin=host['tmin'], calib_file=ab['pars'],
+                                                 n_months=nmonths, spinup_steps=spin_ro, jobs=-1)
+        chs, avg, inst = mrtm_mod.route(um, q, world.flow_dist, world.velocity, world.area, ndays, DT, spin_rt)
+        d2h_bytes_holder[0] = sum(a.nbytes for a in (pet, aet, q, sav, chs, avg, inst))
+        return float(avg[0, -1])
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, wall], dtype=torch.float64, device='cuda')
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    # ---- measure ----------------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    launches0 = None
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler.start()
+    launches0 = C.launch_count
+    dev_ms, _ = timed(device_step, args.steps, 0)
+    launches = (C.launch_count - launches0) // max(args.steps, 1)
+    clocks = sampler.stop()
+    for _ in range(3):
+        device_step(record=True)
+    e2e_ms, e2e_wall = timed(e2e_step, max(1, min(args.steps, 5)), 2)
+    e2e_steps = max(1, min(args.steps, 5))
+
+    cm = float(ncell) * nmonths
+    ms_step = dev_ms / args.steps
+    value = world_size * cm / (ms_step * 1e-3)
+    e2e_val = world_size * cm / (max(e2e_ms, e2e_wall) / e2e_steps * 1e-3)
+
+    if rank != 0:
+        return
+    peaks, peak_src = _peaks()
+    med = {k: float(np.median(v)) for k, v in stage_ms.items()}
+    per_kernel = {
+        'pm_pet_kernel': dict(ms=med['pm'], alg_bytes=BYTES_PM * cm),
+        'abcd_spinup+reinit+sim': dict(ms=med['abcd'], alg_bytes=BYTES_ABCD * cm),
+        'mrtm_tree_kernel': dict(ms=med['mrtm'], alg_bytes=BYTES_MRTM * cm),
+    }
+    for v in per_kernel.values():
+        v['gbs'] = v['alg_bytes'] / (v['ms'] * 1e-3) / 1e9
+        v['frac_hbm'] = v['gbs'] / peaks['hbm_gbs']
+    dom = max(per_kernel, key=lambda k: per_kernel[k]['ms'])
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': per_kernel[dom]['gbs'], 'peak': peaks['hbm_gbs'],
+                'unit': 'GB/s', 'frac': per_kernel[dom]['frac_hbm'], 'traffic': None, 'peak_source': peak_src,
+                'share_of_step': per_kernel[dom]['ms'] / sum(v['ms'] for v in per_kernel.values()),
+                'note': 'dominant kernel is latency/FP64 bound, not HBM bound; see DESIGN.md',
+                'kernels': {k: {'ms': round(v['ms'], 4), 'achieved_gbs': round(v['gbs'], 2),
+                                'frac_hbm': round(v['frac_hbm'], 5)} for k, v in per_kernel.items()}}
+    line = {
+        'metric': 'cell-months/s (PM+ABCD+MRTM)', 'value': value, 'unit': 'cell-months/s', 'n_gpus': world_size,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD if (ncell, nmonths) == (NCELL, NMONTHS) else 'reduced_%dx%d' % (ncell, nmonths),
+                   'ncell': ncell, 'nmonths': nmonths, 'nlcs': NLCS, 'runoff_spinup': spin_ro,
+                   'routing_spinup': spin_rt, 'dt_s': DT, 'members_per_gpu': 1,
+                   'parallelism': 'member-per-gpu x%d' % world_size,
+                   'l2': 'inputs (8 x %.0f MB per member) exceed the 126 MB L2; no flush needed' % (cm * 8 / 1e6),
+                   'mrtm_plan': um.info},
+        'e2e': {'value': e2e_val, 'unit': 'cell-months/s', 'h2d_bytes_per_step': int(h2d_bytes),
+                'd2h_bytes_per_step': int(d2h_bytes_holder[0]), 'ms_per_step': max(e2e_ms, e2e_wall) / e2e_steps,
+                'steps': e2e_steps},
+        'gpu_launches': int(launches) * args.steps,
+        'gpu_launches_per_step': int(launches),
+        'clocks': clocks,
+        'roofline': roofline,
+    }
+    if world_size == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline(world, pm, ab, end_yr, budget_s=args.cpu_budget)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference's numpy path) - also the `--impl reference` arm
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(world, pm, ab, end_yr, budget_s=20.0, threads=None):
+    """
+    Time the numpy oracle (a restatement of the reference's own numpy algorithm, pinned bitwise to
+    it) on a bounded sample of the same workload and extrapolate linearly in cell-months.
+    Per-stage samples: PM - 1 year, all cells; ABCD - 48 months spin-up + 48 months simulation,
+    all cells, basin chunks over threads like the reference (abcd.py:368-382); MRTM - 4 months.
+    """
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pet as opet, abcd as oabcd, mrtm as omrtm
+    from oracle.calendar_utils import set_month_arrays
+    ncell = world.ncell
+    threads = threads or os.cpu_count() or 1
+
+    t0 = time.perf_counter()
+    pm1 = {k: (v[:, :12] if isinstance(v, np.ndarray) and v.ndim == 2 and v.shape[0] == ncell and v.shape[1] >= 12
+               and k.endswith('_load') and k != 'lct_load' else v) for k, v in pm.items()}
+    pet = opet.pm_pet(pm1, ncell, NLCS, START_YR, START_YR, pm['water_idx'], pm['snow_idx'], pm['lc_years'])
+    t_pm = (time.perf_counter() - t0) / (ncell * 12)                       # s per cell-month, 1 thread
+
+    ms = 48
+    pet_s = np.tile(pet, (1, ms // 12))
+    rows = np.asarray(world.basin_ids) - 1
+    chunks = np.array_split(np.arange(world.n_basins), max(1, min(threads, 8)))
+
+    def run_chunk(ch):
+        idx = np.nonzero(np.isin(rows, ch))[0]
+        if len(idx) == 0:
+            return
+        oabcd.abcd_emulate(ab['pars'][rows[idx]], pet_s[idx], ab['precip'][idx, :ms], ab['tmin'][idx, :ms],
+                           world.basin_ids[idx], ms, ms)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=len(chunks)) as ex:
+        list(ex.map(run_chunk, chunks))
+    t_abcd = (time.perf_counter() - t0) / (ncell * 2 * ms)                 # s per cell-month-step
+
+    dsid = omrtm.downstream(world.coords, world.flow_dir, world.nrow, world.ncol)
+    upid = omrtm.upstream_fast(world.coords, dsid, world.nrow, world.ncol)
+    cols, sign, cnt = omrtm.gather_rows(upid)
+    import scipy.sparse as sparse
+    indptr = np.concatenate([[0], np.cumsum(cnt)])
+    mask = np.arange(9)[None, :] < cnt[:, None]
+    indices, data = cols[mask], sign[mask]
+    um = sparse.csr_matrix((data, indices, indptr), shape=(ncell, ncell))   # same operator the reference builds
+    ndays = set_month_arrays(12, START_YR, START_YR)[:, 2]
+    q = np.abs(np.random.default_rng(0).normal(50, 30, (ncell, 4)))
+    S = np.zeros(ncell)
+    t0 = time.perf_counter()
+    nmr = 3
+    for m in range(nmr):
+        S = _mrtm_month_scipy(world.flow_dist, S, world.velocity, q[:, m], world.area, int(ndays[m]), DT, um)
+    t_mrtm = (time.perf_counter() - t0) / (ncell * nmr)
+
+    per_cm = t_pm + t_abcd * (1 + RUNOFF_SPINUP / NMONTHS) + t_mrtm * (1 + ROUTING_SPINUP / NMONTHS)
+    return {'value': 1.0 / per_cm, 'unit': 'cell-months/s', 'cores': int(len(chunks)), 'kind': 'port',
+            'sample': 'PM 1 year x %d cells (1 thread); ABCD %d+%d months x %d cells (%d threads over basin chunks, '
+                      'as the reference); MRTM %d months x %d cells with scipy CSR (1 thread); extrapolated linearly '
+                      'to 360 months with both spin-ups' % (ncell, ms, ms, ncell, len(chunks), nmr, ncell),
+            'stage_cell_months_per_s': {'pm': 1.0 / t_pm, 'abcd_per_pass': 1.0 / t_abcd, 'mrtm_per_pass': 1.0 / t_mrtm},
+            'host_cpus': os.cpu_count()}
+
+
+def _mrtm_month_scipy(L, S0, ChV, q, area, nday, dt, UM):
+    """Oracle month step with the scipy CSR operator, as the reference evaluates it (mrtm.py:16-82)."""
+    nt = int(nday * 24 * 3600 / dt)
+    S = np.copy(S0)
+    tauinv = ChV / L
+    dtinv = 1. / dt
+    erl = (q * area) * (1e6 / 1e3) / (nday * 24 * 3600)
+    for _ in range(nt):
+        F = S * tauinv
+        dSdt = UM.dot(F) + erl
+        Sx = (dSdt * dt) < (-S)
+        if Sx.any():
+            F[Sx] = dSdt[Sx] + F[Sx] + S[Sx] * dtinv
+            S[Sx] = 0
+            Sxn = np.logical_not(Sx)
+            dSdt[Sxn] = (UM.dot(F))[Sxn] + erl[Sxn]
+            S[Sxn] += dSdt[Sxn] * dt
+        else:
+            S += (dSdt * dt)
+    return S
+
+
+def run_reference(args, rank, world_size):
+    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    world, pm, ab, end_yr = build_inputs(member_seed=1, ncell=args.ncell, nmonths=max(12, min(args.nmonths, 48)))
+    ab48 = dict(ab)
+    vals = []
+    t_all = time.perf_counter()
+    for _ in range(args.warmup + args.steps):
+        vals.append(cpu_baseline(world, pm, ab48, end_yr, budget_s=args.cpu_budget))
+        if time.perf_counter() - t_all > 240:
+            break
+    timed_vals = vals[min(args.warmup, len(vals) - 1):]
+    v = float(np.mean([x['value'] for x in timed_vals]))
+    cb = dict(timed_vals[-1])
+    cb['value'] = v
+    cm = float(args.ncell) * args.nmonths
+    line = {'impl': 'reference', 'metric': 'cell-months/s (PM+ABCD+MRTM)', 'value': v, 'unit': 'cell-months/s',
+            'n_gpus': world_size, 'steps': len(timed_vals), 'warmup': args.warmup, 'ms_per_step': cm / v * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'ncell': args.ncell, 'nmonths': args.nmonths, 'nlcs': NLCS,
+                       'runoff_spinup': RUNOFF_SPINUP, 'routing_spinup': ROUTING_SPINUP, 'dt_s': DT,
+                       'note': 'each step times a bounded sample and extrapolates linearly in cell-months'},
+            'cpu_baseline': cb,
+            'e2e': {'value': v, 'unit': 'cell-months/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--ncell', type=int, default=NCELL)
+    ap.add_argument('--nmonths', type=int, default=NMONTHS)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-budget', type=float, default=20.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    world_size = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world_size)
+        return
+    if world_size > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    try:
+        run_ours(args, rank, world_size, local_rank)
+    finally:
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -159,10 +159,14 @@ def test_mrtm_streamrouting_single_month():
         assert bitwise_equal(a, b)
 
 
-@pytest.mark.parametrize("kw", [dict(block_threads=32, cells_per_thread=1), dict(block_threads=64, cells_per_thread=2),
-                                dict(block_threads=32, cells_per_thread=4), dict(block_threads=128, cells_per_thread=3)])
-def test_mrtm_cut_trees_match_oracle(kw):
+@pytest.mark.parametrize("kw,fill", [(dict(block_threads=32, cells_per_thread=1), 0),
+                                     (dict(block_threads=64, cells_per_thread=2), 12),
+                                     (dict(block_threads=32, cells_per_thread=4), 20),
+                                     (dict(block_threads=128, cells_per_thread=3), 7)])
+def test_mrtm_cut_trees_match_oracle(kw, fill, monkeypatch):
     """River trees much larger than a block: exercises the cut-edge pipeline between blocks."""
+    if fill:
+        monkeypatch.setenv('XANTHOS_MRTM_BLOCK_CELLS', str(fill))
     from xanthos_b200 import synthetic
     from xanthos_b200.routing import mrtm
     from xanthos_b200 import _cuda as C
@@ -176,7 +180,7 @@ def test_mrtm_cut_trees_match_oracle(kw):
     upid = mrtm.upstream(w.coords, dsid, s)
     um = mrtm.upstream_genmatrix(upid, **kw)
     info = um.info
-    assert info['is_forest'] == 1 and info['n_cut_edges'] > 0 and info['max_component'] > kw['block_threads']
+    assert info['is_forest'] == 1 and info['n_cut_edges'] > 0 and info['n_levels'] > 1
     ndays = set_month_arrays(24, 2003, 2004)[:m, 2]
     rows = omrtm.gather_rows(omrtm.upstream_fast(w.coords, omrtm.downstream(w.coords, w.flow_dir, w.nrow, w.ncol),
                                                  w.nrow, w.ncol))

@@ -70,6 +70,33 @@ SIGNATURES = {
 
 _lib = None
 
+# kernels launched by each entry point (the claim behind bench.py's "gpu_launches")
+KERNELS_PER_CALL = {
+    'xan_to_month_major': 1, 'xan_to_cell_major': 1, 'xan_hs_pet': 2, 'xan_thornthwaite_pet': 2,
+    'xan_thornthwaite_daylight': 1, 'xan_pm_pet': 1, 'xan_abcd_run': 3, 'xan_abcd_kge_batch': 1,
+    'xan_mrtm_route': 1, 'xan_agg_to_year': 1, 'xan_basin_sum': 1,
+}
+launch_count = 0
+
+
+class _CountingLib:
+    """Thin proxy over the CDLL that counts kernel launches per entry point."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+        n = KERNELS_PER_CALL.get(name, 0)
+        if n == 0:
+            return fn
+
+        def counted(*args):
+            global launch_count
+            launch_count += n
+            return fn(*args)
+        return counted
+
 
 def lib():
     """The loaded shared library (raises LibraryMissing when it has not been built)."""
@@ -83,7 +110,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        _lib = L
+        _lib = _CountingLib(L)
     return _lib
 
 

@@ -46,8 +46,9 @@ struct xan_mrtm_plan {
     int T = 0, K = 0, C = 0;            // threads per block, cells per thread, slots per block
     int n_blocks = 0, n_edges = 0, n_levels = 0, G = 0;   // G = max ghosts per block
     int *d_slot_cell = nullptr;         // [n_blocks * C] cell index or -1
-    uint4 *d_slot_nbr = nullptr;        // [n_blocks * C] gather entries 0..7 (16 bit each)
-    unsigned *d_slot_nbr8 = nullptr;    // [n_blocks * C] entry 8 | cnt << 16 | flags << 20
+    uint4 *d_slot_nbr = nullptr;        // [n_blocks * C] local F index of upstream cell 0..7 (16 bit each, column order)
+    unsigned *d_slot_meta = nullptr;    // [n_blocks * C] nup | ps << 4 | local index of the receiver << 16 (0xffff none)
+    int *d_ghost_down = nullptr;        // [n_ghosts] local index of the cell fed by ghost k
     int *d_slot_out = nullptr;          // [n_blocks * C] cut edge fed by this cell or -1
     int *d_ghost_ptr = nullptr;         // [n_blocks + 1]
     int *d_ghost_edge = nullptr;        // [n_ghosts] cut edge read by ghost k
@@ -62,7 +63,6 @@ struct xan_mrtm_plan {
 namespace xan {
 
 constexpr int RING = 4;                 // months of cut-edge series kept in flight
-constexpr unsigned FLAG_DOWN_LOCAL = 1; // the cell's receiver is in the same block
 
 // =============================================================================================
 // host: topology
@@ -177,9 +177,9 @@ static int build_rows(xan_mrtm_plan *pl, const int64_t *upid) {
 // host: tree partition and block packing
 // =============================================================================================
 struct Packing {
-    std::vector<int> slot_cell, slot_out, ghost_ptr, ghost_edge, edge_prod, edge_cons;
+    std::vector<int> slot_cell, slot_out, ghost_ptr, ghost_edge, ghost_down, edge_prod, edge_cons;
     std::vector<uint4> slot_nbr;
-    std::vector<unsigned> slot_nbr8;
+    std::vector<unsigned> slot_meta;
     int n_blocks = 0, n_edges = 0, n_levels = 0, G = 0;
 };
 
@@ -334,7 +334,7 @@ static bool build_packing(xan_mrtm_plan *pl, int C, int T, int fill, Packing &pk
     pk.slot_cell.assign((size_t)nbk * C, -1);
     pk.slot_out.assign((size_t)nbk * C, -1);
     pk.slot_nbr.assign((size_t)nbk * C, make_uint4(0, 0, 0, 0));
-    pk.slot_nbr8.assign((size_t)nbk * C, 0);
+    pk.slot_meta.assign((size_t)nbk * C, 0xffff0000u);
     std::vector<std::vector<int>> ghosts(nbk);   // producing cells seen by block b
     std::vector<int> edge_of_cell(n, -1);
     for (int v = 0; v < n; ++v) {
@@ -355,10 +355,12 @@ static bool build_packing(xan_mrtm_plan *pl, int C, int T, int fill, Packing &pk
     }
     if (C + pk.G > 32767 || pk.G > T) return false;
     pk.ghost_edge.assign(std::max(pk.ghost_ptr[nbk], 1), -1);
+    pk.ghost_down.assign(std::max(pk.ghost_ptr[nbk], 1), 0);
     std::vector<int> ghost_local(n, -1);   // local F index of producing cell v inside its consumer
     for (int b = 0; b < nbk; ++b)
         for (size_t k = 0; k < ghosts[b].size(); ++k) {
             pk.ghost_edge[pk.ghost_ptr[b] + k] = edge_of_cell[ghosts[b][k]];
+            pk.ghost_down[pk.ghost_ptr[b] + k] = cell_slot[pl->down[ghosts[b][k]]];
             ghost_local[ghosts[b][k]] = C + (int)k;
         }
     for (int v = 0; v < n; ++v) {
@@ -366,17 +368,21 @@ static bool build_packing(xan_mrtm_plan *pl, int C, int T, int fill, Packing &pk
         const size_t g = (size_t)b * C + cell_slot[v];
         pk.slot_cell[g] = v;
         pk.slot_out[g] = edge_of_cell[v];
-        unsigned short e[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned short e[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const int beg = pl->row_ptr[v], cnt = pl->row_ptr[v + 1] - beg;
+        int nup = 0, ps = 0;
         for (int s = 0; s < cnt; ++s) {
             const int j = pl->col[beg + s];
-            const int loc = (cell_block[j] == b) ? cell_slot[j] : ghost_local[j];
-            e[s] = (unsigned short)(loc | (pl->sgn[beg + s] < 0 ? 0x8000 : 0));
+            if (j == v) {
+                ps = nup;   // the -F(self) term sits after `ps` upstream terms
+                continue;
+            }
+            e[nup++] = (unsigned short)((cell_block[j] == b) ? cell_slot[j] : ghost_local[j]);
         }
         pk.slot_nbr[g] = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
         const int r = pl->down[v];
-        const unsigned flags = (r >= 0 && cell_block[r] == b) ? FLAG_DOWN_LOCAL : 0;
-        pk.slot_nbr8[g] = e[8] | ((unsigned)cnt << 16) | (flags << 20);
+        const unsigned dl = (r >= 0 && cell_block[r] == b) ? (unsigned)cell_slot[r] : 0xffffu;
+        pk.slot_meta[g] = (unsigned)nup | ((unsigned)ps << 4) | (dl << 16);
     }
     return true;
 }
@@ -393,27 +399,42 @@ __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Row of UM times F, accumulated from 0.0 in ascending column order (scipy csr_matvec order).
-__device__ __forceinline__ double gather_row(const double *__restrict__ F, uint4 nb, unsigned nb8) {
-    const int cnt = (nb8 >> 16) & 0xf;
+// Row i of UM times F, accumulated from 0.0 in ascending column order (scipy csr_matvec order):
+// `nup` upstream terms (+F_j, read from shared memory) with the -F_i term after the first `ps`.
+// Cells are sorted by nup inside a block, so the nested branches are (nearly) warp-uniform and a
+// headwater cell (nup == 0, about half of all cells) touches no shared memory at all.
+__device__ __forceinline__ double um_row(const double *__restrict__ Fb, uint4 nb, unsigned meta, double Fself) {
+    const int nup = meta & 0xf, ps = (meta >> 4) & 0xf;
     double d = 0.0;
-    unsigned e;
-#define XAN_TERM(s, word, shift)                         \
-    if (cnt > (s)) {                                     \
-        e = ((word) >> (shift)) & 0xffffu;               \
-        const double v = F[e & 0x7fffu];                 \
-        d = d + ((e & 0x8000u) ? -v : v);                \
+#define XAN_TERM(s, word, shift)                    \
+    if (ps == (s)) d = d - Fself;                   \
+    d = d + Fb[((word) >> (shift)) & 0xffffu];
+    if (nup > 0) {
+        XAN_TERM(0, nb.x, 0)
+        if (nup > 1) {
+            XAN_TERM(1, nb.x, 16)
+            if (nup > 2) {
+                XAN_TERM(2, nb.y, 0)
+                if (nup > 3) {
+                    XAN_TERM(3, nb.y, 16)
+                    if (nup > 4) {
+                        XAN_TERM(4, nb.z, 0)
+                        if (nup > 5) {
+                            XAN_TERM(5, nb.z, 16)
+                            if (nup > 6) {
+                                XAN_TERM(6, nb.w, 0)
+                                if (nup > 7) {
+                                    XAN_TERM(7, nb.w, 16)
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
     }
-    XAN_TERM(0, nb.x, 0)
-    XAN_TERM(1, nb.x, 16)
-    XAN_TERM(2, nb.y, 0)
-    XAN_TERM(3, nb.y, 16)
-    XAN_TERM(4, nb.z, 0)
-    XAN_TERM(5, nb.z, 16)
-    XAN_TERM(6, nb.w, 0)
-    XAN_TERM(7, nb.w, 16)
-    XAN_TERM(8, nb8, 0)
 #undef XAN_TERM
+    if (ps == nup) d = d - Fself;
     return d;
 }
 
@@ -423,10 +444,11 @@ __device__ __forceinline__ double gather_row(const double *__restrict__ F, uint4
 struct TreeArgs {
     const int *slot_cell;
     const uint4 *slot_nbr;
-    const unsigned *slot_nbr8;
+    const unsigned *slot_meta;
     const int *slot_out;
     const int *ghost_ptr;
     const int *ghost_edge;
+    const int *ghost_down;
     const int *edge_prod;
     const int *edge_cons;
     int *progress;
@@ -446,24 +468,25 @@ __global__ void __launch_bounds__(K >= 3 ? 256 : 512, 1) mrtm_tree_kernel(const 
     const int C = a.C, W = a.C + a.G;
     double *X = smem, *Y = smem + W, *Z = smem + 2 * W;   // F, F', next F (X and Z swap)
     double *gs = smem + 3 * W;                            // [G][ntmax][2] staged ghost series
+    unsigned char *dirty = reinterpret_cast<unsigned char *>(gs + (size_t)a.G * a.ntmax * 2);   // [C]
     const int g0 = a.ghost_ptr[b], ng = a.ghost_ptr[b + 1] - g0;
 
     int cell[K], oedge[K];
     uint4 nb[K];
-    unsigned nb8[K];
+    unsigned meta[K];
     double S[K], tauinv[K], area[K], Favg[K], erl[K], qn[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) {
         const size_t g = (size_t)b * C + tid + j * T;
-        const bool live = (tid + j * T) < C;
-        cell[j] = live ? a.slot_cell[g] : -1;
+        cell[j] = a.slot_cell[g];
         oedge[j] = -1;
         S[j] = 0.0; tauinv[j] = 0.0; area[j] = 0.0; Favg[j] = 0.0; erl[j] = 0.0; qn[j] = 0.0;
         nb[j] = make_uint4(0, 0, 0, 0);
-        nb8[j] = 0;
+        meta[j] = 0xffff0000u;
+        dirty[tid + j * T] = 0;
         if (cell[j] >= 0) {
             nb[j] = a.slot_nbr[g];
-            nb8[j] = a.slot_nbr8[g];
+            meta[j] = a.slot_meta[g];
             oedge[j] = a.slot_out[g];
             tauinv[j] = a.velocity[cell[j]] / a.flow_dist[cell[j]];                 // mrtm.py:42
             area[j] = a.area[cell[j]];
@@ -473,6 +496,7 @@ __global__ void __launch_bounds__(K >= 3 ? 256 : 512, 1) mrtm_tree_kernel(const 
     }
     const int my_edge = (tid < ng) ? a.ghost_edge[g0 + tid] : -1;
     const int my_prod = (my_edge >= 0) ? a.edge_prod[my_edge] : -1;
+    const int my_gdown = (my_edge >= 0) ? a.ghost_down[g0 + tid] : 0;
     const double dt = a.dt, dtinv = 1. / a.dt;                                      // mrtm.py:43
     const int nsteps = a.spinup + a.nmonths;
 
@@ -515,37 +539,54 @@ __global__ void __launch_bounds__(K >= 3 ? 256 : 512, 1) mrtm_tree_kernel(const 
         __syncthreads();
 
         for (int t = 0; t < nt; ++t) {
-            double F[K], Fp[K], d[K], Sn[K];
+            double F[K], Fp[K], Sn[K];
             bool clamp[K];
             int flag = 0;
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 F[j] = S[j] * tauinv[j];
-                d[j] = gather_row(X, nb[j], nb8[j]) + erl[j];                       // mrtm.py:51
-                clamp[j] = (d[j] * dt) < (-S[j]);                                   // mrtm.py:54
-                Fp[j] = clamp[j] ? (d[j] + F[j] + S[j] * dtinv) : F[j];             // mrtm.py:60
-                Sn[j] = clamp[j] ? 0.0 : (S[j] + d[j] * dt);                        // mrtm.py:63, :76
+                Fp[j] = F[j];
+                Sn[j] = S[j];
+                clamp[j] = false;
                 if (cell[j] >= 0) {
+                    const double d = um_row(X, nb[j], meta[j], F[j]) + erl[j];      // mrtm.py:51
+                    clamp[j] = (d * dt) < (-S[j]);                                  // mrtm.py:54
+                    if (clamp[j]) {
+                        Fp[j] = d + F[j] + S[j] * dtinv;                            // mrtm.py:60
+                        Sn[j] = 0.0;                                                // mrtm.py:63
+                        const unsigned dl = meta[j] >> 16;
+                        if (dl != 0xffffu) {   // the receiver must redo its balance with F'
+                            dirty[dl] = 1;
+                            flag = 1;
+                        }
+                    } else {
+                        Sn[j] = S[j] + d * dt;                                      // mrtm.py:76
+                    }
                     Y[tid + j * T] = Fp[j];
                     Z[tid + j * T] = Sn[j] * tauinv[j];   // speculative flow of the next sub-step
-                    flag |= (clamp[j] && ((nb8[j] >> 20) & FLAG_DOWN_LOCAL)) ? 1 : 0;
                 }
             }
             if (tid < ng) {
                 const double *g = gs + ((size_t)tid * a.ntmax + t) * 2;
                 Y[C + tid] = g[1];
                 if (t + 1 < nt) Z[C + tid] = g[2];
-                flag |= (__double_as_longlong(g[0]) != __double_as_longlong(g[1])) ? 1 : 0;
+                if (__double_as_longlong(g[0]) != __double_as_longlong(g[1])) {
+                    dirty[my_gdown] = 1;
+                    flag = 1;
+                }
             }
             if (__syncthreads_or(flag)) {
-                // some inflow changed in the clamp pass: redo the balance with F' (mrtm.py:66-69)
+                // an inflow changed in the clamp pass: the receivers redo the balance with F' (mrtm.py:66-69)
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    if (!clamp[j]) {
-                        const double d2 = gather_row(Y, nb[j], nb8[j]) + erl[j];
-                        Sn[j] = S[j] + d2 * dt;
+                    if (cell[j] >= 0 && dirty[tid + j * T]) {
+                        dirty[tid + j * T] = 0;
+                        if (!clamp[j]) {
+                            const double d2 = um_row(Y, nb[j], meta[j], F[j]) + erl[j];
+                            Sn[j] = S[j] + d2 * dt;
+                            Z[tid + j * T] = Sn[j] * tauinv[j];
+                        }
                     }
-                    if (cell[j] >= 0) Z[tid + j * T] = Sn[j] * tauinv[j];
                 }
                 __syncthreads();
             }
@@ -558,18 +599,19 @@ __global__ void __launch_bounds__(K >= 3 ? 256 : 512, 1) mrtm_tree_kernel(const 
                     __stcg(r, F[j]);
                     __stcg(r + 1, Fp[j]);
                 }
-                if (t == nt - 1 && step == nsteps - 1 && a.instream && cell[j] >= 0) a.instream[cell[j]] = Fp[j];
             }
             double *tmp = X; X = Z; Z = tmp;
         }
-        if (store) {
 #pragma unroll
-            for (int j = 0; j < K; ++j)
-                if (cell[j] >= 0) {
+        for (int j = 0; j < K; ++j)
+            if (cell[j] >= 0) {
+                if (store) {
                     if (a.chs) stg_stream(a.chs + (size_t)m * a.ld + cell[j], S[j]);
                     if (a.avg) stg_stream(a.avg + (size_t)m * a.ld + cell[j], Favg[j] / nt);   // mrtm.py:80
                 }
-        }
+                // instantaneous flow after the last sub-step = last published F' (still in Y)
+                if (step == nsteps - 1 && a.instream) a.instream[cell[j]] = Y[tid + j * T];
+            }
         // ---- publish: this block has finished month `step` ------------------------------------------
         __threadfence();
         __syncthreads();
@@ -677,7 +719,8 @@ static void free_device(xan_mrtm_plan *pl) {
     cudaFree(pl->d_gcol);
     cudaFree(pl->d_slot_cell);
     cudaFree(pl->d_slot_nbr);
-    cudaFree(pl->d_slot_nbr8);
+    cudaFree(pl->d_slot_meta);
+    cudaFree(pl->d_ghost_down);
     cudaFree(pl->d_slot_out);
     cudaFree(pl->d_ghost_ptr);
     cudaFree(pl->d_ghost_edge);
@@ -730,8 +773,9 @@ xan_mrtm_plan *xan_mrtm_plan_create(const int64_t *h_upid, int ncell, int block_
         cudaGetLastError();
         sms = 148;
     }
-    pl->T = (block_threads > 0) ? block_threads : 256;
-    pl->K = (cells_per_thread > 0) ? cells_per_thread : 2;
+    const char *env_t = getenv("XANTHOS_MRTM_THREADS"), *env_k = getenv("XANTHOS_MRTM_CELLS_PER_THREAD");
+    pl->T = (block_threads > 0) ? block_threads : (env_t ? atoi(env_t) : 256);
+    pl->K = (cells_per_thread > 0) ? cells_per_thread : (env_k ? atoi(env_k) : 2);
     if (pl->T % 32 != 0 || pl->T > 512 || pl->K > 4 || (pl->K >= 3 && pl->T > 256)) {
         set_error("xan_mrtm_plan_create: block_threads must be a multiple of 32, <= 512 (<= 256 when "
                   "cells_per_thread >= 3), and cells_per_thread <= 4");
@@ -774,7 +818,8 @@ static int ensure_device(xan_mrtm_plan *pl) {
     if (ok && pl->n_blocks > 0) {
         std::vector<int> zeros(pk.n_blocks, 0);
         ok = upload(pk.slot_cell, &pl->d_slot_cell) && upload(pk.slot_nbr, &pl->d_slot_nbr) &&
-             upload(pk.slot_nbr8, &pl->d_slot_nbr8) && upload(pk.slot_out, &pl->d_slot_out) &&
+             upload(pk.slot_meta, &pl->d_slot_meta) && upload(pk.slot_out, &pl->d_slot_out) &&
+             upload(pk.ghost_down, &pl->d_ghost_down) &&
              upload(pk.ghost_ptr, &pl->d_ghost_ptr) && upload(pk.ghost_edge, &pl->d_ghost_edge) &&
              upload(pk.edge_prod, &pl->d_edge_prod) && upload(pk.edge_cons, &pl->d_edge_cons) &&
              upload(zeros, &pl->d_progress);
@@ -859,7 +904,8 @@ int xan_mrtm_route(xan_mrtm_plan *pl, const double *d_runoff, const double *d_fl
         TreeArgs a;
         a.slot_cell = pl->d_slot_cell;
         a.slot_nbr = pl->d_slot_nbr;
-        a.slot_nbr8 = pl->d_slot_nbr8;
+        a.slot_meta = pl->d_slot_meta;
+        a.ghost_down = pl->d_ghost_down;
         a.slot_out = pl->d_slot_out;
         a.ghost_ptr = pl->d_ghost_ptr;
         a.ghost_edge = pl->d_ghost_edge;
@@ -887,7 +933,7 @@ int xan_mrtm_route(xan_mrtm_plan *pl, const double *d_runoff, const double *d_fl
         XAN_CUDA_CHECK(cudaMallocAsync(&ring, sizeof(double) * ring_elems, s));
         XAN_CUDA_CHECK(cudaMemsetAsync(pl->d_progress, 0, sizeof(int) * pl->n_blocks, s));
         a.ring = ring;
-        const size_t smem = sizeof(double) * (3 * (size_t)(pl->C + pl->G) + (size_t)pl->G * ntmax * 2);
+        const size_t smem = sizeof(double) * (3 * (size_t)(pl->C + pl->G) + (size_t)pl->G * ntmax * 2) + (size_t)pl->C + 16;
         if (smem > 227 * 1024) {
             set_error("xan_mrtm_route: tree kernel needs %zu B of shared memory (G=%d, ntmax=%d)", smem, pl->G, ntmax);
             rc = XAN_E_INVALID;
