@@ -135,29 +135,29 @@ int xan_mrtm_upstream(const double *h_coords, const int64_t *h_dsid, int ncell, 
 
 /* Execution plan; replaces upstream_genmatrix (mrtm.py:194-230): from h_upid [ncell][9] it
  * builds the rows of UM = UP - I, checks that the flow graph is a forest, cuts large river trees
- * into sub-trees and packs them into thread blocks.  block_threads / cells_per_thread <= 0 pick
- * defaults.  Plan creation is host-side integer work and needs no device; the device tables are
- * uploaded by the first xan_mrtm_route call. */
+ * into pieces of at most 32 lanes and packs them into warps.  block_threads (multiple of 32,
+ * <= 256) / chunk_substeps (sub-steps per hand-over between warps) <= 0 pick defaults.  Plan
+ * creation is host-side integer work and needs no device; the device tables are uploaded by the
+ * first xan_mrtm_route call. */
 typedef struct xan_mrtm_plan xan_mrtm_plan;
 xan_mrtm_plan *xan_mrtm_plan_create(const int64_t *h_upid, int ncell, int block_threads,
-                                    int cells_per_thread);
+                                    int chunk_substeps);
 void xan_mrtm_plan_destroy(xan_mrtm_plan *plan);
 /* rows of UM = UP - I in CSR form (mrtm.py:194-230): indptr [ncell+1], indices/data [nnz] */
 int xan_mrtm_plan_um_nnz(const xan_mrtm_plan *plan);
 int xan_mrtm_plan_um(const xan_mrtm_plan *plan, int64_t *h_indptr, int64_t *h_indices,
                      int64_t *h_data);
-/* info[0]=is_forest info[1]=n_components info[2]=max_component info[3]=n_blocks
- * info[4]=n_cut_edges info[5]=n_levels info[6]=block_threads info[7]=cells_per_thread */
+/* info[0]=is_forest info[1]=n_components info[2]=max_component info[3]=n_warps
+ * info[4]=n_cut_edges info[5]=n_levels info[6]=block_threads info[7]=chunk_substeps */
 int xan_mrtm_plan_info(const xan_mrtm_plan *plan, int *info8);
-/* diagnostic export of the tree-kernel packing: slot_cell [n_blocks * block_threads *
- * cells_per_thread] (cell index or -1), edge_prod / edge_cons [n_cut_edges] (block indices).
- * Any pointer may be NULL. */
-int xan_mrtm_plan_packing(const xan_mrtm_plan *plan, int *h_slot_cell, int *h_edge_prod,
+/* diagnostic export of the warp-kernel packing: lane_cell [n_warps * 32] (cell index or -1),
+ * edge_prod / edge_cons [n_cut_edges] (warp indices).  Any pointer may be NULL. */
+int xan_mrtm_plan_packing(const xan_mrtm_plan *plan, int *h_lane_cell, int *h_edge_prod,
                           int *h_edge_cons);
 
-#define XAN_MRTM_AUTO 0  /* tree-pipelined block kernel if the flow graph is a forest */
-#define XAN_MRTM_GRID 1  /* cooperative grid-sync kernel (any graph)                   */
-#define XAN_MRTM_TREE 2  /* force the block kernel (fails if not a forest)             */
+#define XAN_MRTM_AUTO 0  /* warp-dataflow kernel if the flow graph is a forest  */
+#define XAN_MRTM_GRID 1  /* cooperative grid-sync kernel (any graph)            */
+#define XAN_MRTM_TREE 2  /* force the warp kernel (fails if not a forest)       */
 
 /* Replaces the routing loops of Components.calculate_routing (xanthos/components.py:262-296)
  * around streamrouting (mrtm.py:16-82): `spinup_months` months of spin-up over the first months

@@ -135,7 +135,7 @@ def test_mrtm_golden_bitwise(name, method):
     dsid = mrtm.downstream(case['coords'], case['flow_dir'], s)
     upid = mrtm.upstream(case['coords'], dsid, s)
     assert np.array_equal(dsid, ref['dsid']) and np.array_equal(upid, ref['upid'])
-    um = mrtm.upstream_genmatrix(upid, 64, 1)
+    um = mrtm.upstream_genmatrix(upid, 64, 16)
     chs, avg, F = mrtm.route(um, case['runoff'], case['flow_dist'], case['velocity'], case['area'], ref['ndays'],
                              case['dt'], case['routing_spinup'],
                              method=C.MRTM_TREE if method == 'tree' else C.MRTM_GRID)
@@ -159,14 +159,14 @@ def test_mrtm_streamrouting_single_month():
         assert bitwise_equal(a, b)
 
 
-@pytest.mark.parametrize("kw,fill", [(dict(block_threads=32, cells_per_thread=1), 0),
-                                     (dict(block_threads=64, cells_per_thread=2), 12),
-                                     (dict(block_threads=32, cells_per_thread=4), 20),
-                                     (dict(block_threads=128, cells_per_thread=3), 7)])
-def test_mrtm_cut_trees_match_oracle(kw, fill, monkeypatch):
-    """River trees much larger than a block: exercises the cut-edge pipeline between blocks."""
-    if fill:
-        monkeypatch.setenv('XANTHOS_MRTM_BLOCK_CELLS', str(fill))
+@pytest.mark.parametrize("kw,lanes", [(dict(block_threads=32, chunk_substeps=64), 0),
+                                      (dict(block_threads=64, chunk_substeps=7), 12),
+                                      (dict(block_threads=256, chunk_substeps=1), 20),
+                                      (dict(block_threads=128, chunk_substeps=300), 9)])
+def test_mrtm_cut_trees_match_oracle(kw, lanes, monkeypatch):
+    """River trees much larger than a warp: exercises the cut-edge pipeline between warps."""
+    if lanes:
+        monkeypatch.setenv('XANTHOS_MRTM_LANES', str(lanes))
     from xanthos_b200 import synthetic
     from xanthos_b200.routing import mrtm
     from xanthos_b200 import _cuda as C

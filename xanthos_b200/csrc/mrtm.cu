@@ -1,17 +1,19 @@
 // MRTM river routing (xanthos/routing/mrtm.py, xanthos/components.py:262-296), fp64, compiled with
 // -fmad=false: the routing results are BIT-IDENTICAL to the reference's scipy-CSR formulation.
 //
-// Host side  : integer topology (downstream / upstream / UM = UP - I), forest check, tree
-//              partition into pieces of bounded size, levels, packing of pieces into thread blocks.
+// Host side  : integer topology (downstream / upstream / UM = UP - I), forest check, partition of
+//              every river tree into "pieces" of at most 32 lanes, levels, packing of pieces into warps.
 // Device side:
-//   * mrtm_tree_kernel - one persistent thread block per group of river (sub)trees.  Channel
-//     storage S lives in registers for the whole run; the flows F of the block's cells live in
-//     shared memory, and the reference's sparse "UM.dot(F)" is a <= 9-entry gather from that
-//     buffer in ascending column order.  A sub-step needs ONE __syncthreads_or (two only when a
-//     cell of the block was clamped).  River trees larger than a block are cut into sub-trees;
-//     the flow over a cut edge travels downstream-only, so the upstream block simply runs ahead
-//     and hands the per-sub-step flow series of the cut cell to the downstream block one month at
-//     a time through a small ring buffer in global memory (acquire/release progress counters).
+//   * mrtm_warp_kernel - warp-level dataflow, NO block- or grid-wide barrier anywhere in the time
+//     loop.  One warp owns one or more pieces (<= 32 cells + ghost lanes).  Channel storage S lives
+//     in a register of the owning lane for the whole run; the flows F of the warp's cells are
+//     exchanged through 512 B of shared memory with __syncwarp, and the reference's sparse
+//     "UM.dot(F)" is a <= 9-term gather from that buffer in ascending column order.  Water only
+//     moves downstream, so a cut edge between two pieces is a one-way dependency: the upstream
+//     warp runs ahead and streams the (F, F') series of its outlet cell into a small ring buffer
+//     in global memory (L2 resident), chunk by chunk; the downstream warp follows one chunk behind
+//     (acquire/release progress counters, back-pressure through the same counters).  The depth of
+//     the piece tree only adds a start-up lag of one chunk per level.
 //   * mrtm_grid_kernel - general fallback for graphs that are not forests: cooperative launch,
 //     two grid-wide syncs per sub-step, state in global memory.
 #include "common.cuh"
@@ -41,28 +43,26 @@ struct xan_mrtm_plan {
     bool is_forest = false;
     int n_components = 0, max_component = 0;
     // ---- grid kernel ------------------------------------------------------------------------
-    int *d_gcol = nullptr;              // [9][ncell] column (bit 31 set = minus sign), -1 = empty
-    // ---- tree kernel ------------------------------------------------------------------------
-    int T = 0, K = 0, C = 0;            // threads per block, cells per thread, slots per block
-    int n_blocks = 0, n_edges = 0, n_levels = 0, G = 0;   // G = max ghosts per block
-    int *d_slot_cell = nullptr;         // [n_blocks * C] cell index or -1
-    uint4 *d_slot_nbr = nullptr;        // [n_blocks * C] local F index of upstream cell 0..7 (16 bit each, column order)
-    unsigned *d_slot_meta = nullptr;    // [n_blocks * C] nup | ps << 4 | local index of the receiver << 16 (0xffff none)
-    int *d_ghost_down = nullptr;        // [n_ghosts] local index of the cell fed by ghost k
-    int *d_slot_out = nullptr;          // [n_blocks * C] cut edge fed by this cell or -1
-    int *d_ghost_ptr = nullptr;         // [n_blocks + 1]
-    int *d_ghost_edge = nullptr;        // [n_ghosts] cut edge read by ghost k
-    int *d_edge_prod = nullptr;         // [n_edges] producing block
-    int *d_edge_cons = nullptr;         // [n_edges] consuming block
-    int *d_progress = nullptr;          // [n_blocks] months completed (reset per run)
-    bool on_device = false;             // device tables are uploaded lazily by the first route()
-    xan::Packing *packing = nullptr;    // host copy of the tree-kernel tables
     std::vector<int> h_gcol;
+    int *d_gcol = nullptr;              // [9][ncell] column (bit 31 set = minus sign), -1 = empty
+    // ---- warp kernel ------------------------------------------------------------------------
+    int block_threads = 256, chunk = 64;
+    int n_warps = 0, n_edges = 0, n_levels = 0, G = 0;   // G = max ghost lanes of a warp
+    xan::Packing *packing = nullptr;    // host copy of the lane tables
+    int *d_lane_cell = nullptr;         // [n_warps * 32] cell index or -1
+    int *d_lane_gedge = nullptr;        // [n_warps * 32] cut edge READ by this (ghost) lane or -1
+    int *d_lane_oedge = nullptr;        // [n_warps * 32] cut edge WRITTEN by this lane or -1
+    uint2 *d_lane_src = nullptr;        // [n_warps * 32] source lane of upstream term 0..7 (8 bit each)
+    unsigned *d_lane_meta = nullptr;    // [n_warps * 32] nup | ps << 4 | ghost slot << 8
+    int *d_edge_prod = nullptr;         // [n_edges] producing warp
+    int *d_edge_cons = nullptr;         // [n_edges] consuming warp
+    int *d_progress = nullptr;          // [n_warps] chunks completed (reset per run)
+    bool on_device = false;
 };
 
 namespace xan {
 
-constexpr int RING = 4;                 // months of cut-edge series kept in flight
+constexpr int RING_DEFAULT = 4;   // months of a cut-edge series kept in flight
 
 // =============================================================================================
 // host: topology
@@ -174,16 +174,16 @@ static int build_rows(xan_mrtm_plan *pl, const int64_t *upid) {
 }
 
 // =============================================================================================
-// host: tree partition and block packing
+// host: partition of the forest into warp-sized pieces
 // =============================================================================================
 struct Packing {
-    std::vector<int> slot_cell, slot_out, ghost_ptr, ghost_edge, ghost_down, edge_prod, edge_cons;
-    std::vector<uint4> slot_nbr;
-    std::vector<unsigned> slot_meta;
-    int n_blocks = 0, n_edges = 0, n_levels = 0, G = 0;
+    std::vector<int> lane_cell, lane_gedge, lane_oedge, edge_prod, edge_cons;
+    std::vector<uint2> lane_src;
+    std::vector<unsigned> lane_meta;
+    int n_warps = 0, n_edges = 0, n_levels = 0, G = 0;
 };
 
-static bool build_packing(xan_mrtm_plan *pl, int C, int T, int fill, Packing &pk) {
+static bool build_packing(xan_mrtm_plan *pl, int lanes, Packing &pk) {
     const int n = pl->ncell;
     // Kahn order, leaves first; a cycle leaves cells unvisited -> not a forest
     std::vector<int> indeg(n), order;
@@ -198,8 +198,7 @@ static bool build_packing(xan_mrtm_plan *pl, int C, int T, int fill, Packing &pk
     pl->is_forest = ((int)order.size() == n) && !pl->multi_receiver;
     if (!pl->is_forest) return false;
 
-    // components (for reporting)
-    {
+    {   // components (for reporting)
         std::vector<int> csize(n, 0), root(n);
         for (int h = n - 1; h >= 0; --h) {
             const int v = order[h];
@@ -215,40 +214,48 @@ static bool build_packing(xan_mrtm_plan *pl, int C, int T, int fill, Packing &pk
             }
     }
 
-    // bottom-up residual sizes; cut the largest children while a sub-tree exceeds `fill`
-    std::vector<int> res(n, 0);
+    // Bottom-up: a piece occupies (cells + ghost lanes) <= `lanes`; every cut child costs its
+    // receiver one ghost lane.  While a sub-tree is too big the heaviest child is cut off.
+    std::vector<int> rs(n, 0), rg(n, 0);
     std::vector<char> cut(n, 0);
     for (int h = 0; h < n; ++h) {
         const int v = order[h];
         const int k = pl->upid[(size_t)v * 9 + 8];
-        int ch[8], sz = 1;
+        int ch[8], sz = 1, gh = 0;
         for (int s = 0; s < k; ++s) {
             ch[s] = pl->upid[(size_t)v * 9 + s] - 1;
-            sz += res[ch[s]];
+            sz += rs[ch[s]];
+            gh += rg[ch[s]];
         }
-        if (sz > fill) {
-            std::sort(ch, ch + k, [&](int a, int b) { return res[a] != res[b] ? res[a] > res[b] : a < b; });
-            for (int s = 0; s < k && sz > fill; ++s) {
+        if (sz + gh > lanes) {
+            std::sort(ch, ch + k, [&](int a, int b) {
+                const int wa = rs[a] + rg[a], wb = rs[b] + rg[b];
+                return wa != wb ? wa > wb : a < b;
+            });
+            for (int s = 0; s < k && sz + gh > lanes; ++s) {
+                if (rs[ch[s]] + rg[ch[s]] <= 1) break;   // cutting a bare leaf gains nothing
                 cut[ch[s]] = 1;
-                sz -= res[ch[s]];
+                sz -= rs[ch[s]];
+                gh -= rg[ch[s]];
+                gh += 1;
             }
+            if (sz + gh > lanes) return false;
         }
-        res[v] = sz;
+        rs[v] = sz;
+        rg[v] = gh;
     }
     // pieces: roots are outlets and cut cells
-    std::vector<int> piece(n, -1), piece_root, piece_size, piece_level;
+    std::vector<int> piece(n, -1), piece_lanes, piece_level;
     for (int h = n - 1; h >= 0; --h) {
         const int v = order[h];
         if (pl->down[v] < 0 || cut[v]) {
-            piece[v] = (int)piece_root.size();
-            piece_root.push_back(v);
-            piece_size.push_back(0);
+            piece[v] = (int)piece_lanes.size();
+            piece_lanes.push_back(rs[v] + rg[v]);
         } else {
             piece[v] = piece[pl->down[v]];
         }
-        piece_size[piece[v]]++;
     }
-    const int np = (int)piece_root.size();
+    const int np = (int)piece_lanes.size();
     piece_level.assign(np, 0);
     std::vector<char> linked(np, 0);
     for (int h = 0; h < n; ++h) {   // leaves first: a piece's incoming edges are final before its own
@@ -262,127 +269,127 @@ static bool build_packing(xan_mrtm_plan *pl, int C, int T, int fill, Packing &pk
     int n_levels = 1;
     for (int p = 0; p < np; ++p) n_levels = std::max(n_levels, piece_level[p] + 1);
 
-    // first-fit decreasing; linked pieces only share a block with pieces of the same level, which
-    // keeps the block dependency graph acyclic.  Free pieces (whole small trees) fill the gaps.
+    // First-fit decreasing into warps.  Linked pieces only share a warp with pieces of the same
+    // level, which keeps the warp dependency graph acyclic; free pieces (whole small trees) fill gaps.
     std::vector<int> ids(np);
     std::iota(ids.begin(), ids.end(), 0);
-    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return piece_size[a] > piece_size[b]; });
-    std::vector<int> blk_fill, blk_level, piece_block(np, -1);
-    for (int lvl = 0; lvl < n_levels; ++lvl) {
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return piece_lanes[a] > piece_lanes[b]; });
+    std::vector<int> w_fill, w_level, piece_warp(np, -1);
+    {
+        // Linked pieces share a warp only when they feed the SAME downstream piece: a warp then has a
+        // single consumer, so back-pressure from a slow consumer can never stall data that another
+        // (faster) consumer is waiting for.  (Mixed consumers create a cycle through the ring
+        // back-pressure that throttles whole river systems to ring_depth / tree_depth.)
+        std::vector<int> piece_down(np, -1);
+        for (int v = 0; v < n; ++v)
+            if (cut[v]) piece_down[piece[v]] = piece[pl->down[v]];
+        std::vector<int> last_open(np + 1, -1);   // per downstream piece (index np = "no consumer"): last warp opened
         for (int p : ids) {
-            if (!linked[p] || piece_level[p] != lvl) continue;
-            int b = -1;
-            for (size_t q = 0; q < blk_fill.size(); ++q)
-                if (blk_level[q] == lvl && blk_fill[q] + piece_size[p] <= fill) {
-                    b = (int)q;
-                    break;
+            if (!linked[p]) continue;
+            const int key = piece_down[p] < 0 ? np : piece_down[p];
+            int w = last_open[key];
+            if (piece_down[p] < 0 || w < 0 || w_fill[w] + piece_lanes[p] > lanes) {
+                w = (int)w_fill.size();
+                w_fill.push_back(0);
+                w_level.push_back(piece_level[p]);
+                if (piece_down[p] >= 0) last_open[key] = w;
+            }
+            w_fill[w] += piece_lanes[p];
+            w_level[w] = std::max(w_level[w], piece_level[p]);   // siblings may sit on different levels
+            piece_warp[p] = w;
+        }
+    }
+    {
+        // free pieces: bucket the open warps by remaining room for an O(1)-ish first fit
+        std::vector<std::vector<int>> by_room(lanes + 1);
+        for (size_t w = 0; w < w_fill.size(); ++w) by_room[lanes - w_fill[w]].push_back((int)w);
+        for (int p : ids) {
+            if (linked[p]) continue;
+            int w = -1;
+            for (int room = piece_lanes[p]; room <= lanes && w < 0; ++room)
+                if (!by_room[room].empty()) {
+                    w = by_room[room].back();
+                    by_room[room].pop_back();
                 }
-            if (b < 0) {
-                b = (int)blk_fill.size();
-                blk_fill.push_back(0);
-                blk_level.push_back(lvl);
+            if (w < 0) {
+                w = (int)w_fill.size();
+                w_fill.push_back(0);
+                w_level.push_back(-1);
             }
-            blk_fill[b] += piece_size[p];
-            piece_block[p] = b;
+            w_fill[w] += piece_lanes[p];
+            piece_warp[p] = w;
+            by_room[lanes - w_fill[w]].push_back(w);
         }
     }
-    size_t first_open = 0;
-    for (int p : ids) {
-        if (linked[p]) continue;
-        int b = -1;
-        while (first_open < blk_fill.size() && blk_fill[first_open] >= fill) ++first_open;
-        for (size_t q = first_open; q < blk_fill.size(); ++q)
-            if (blk_fill[q] + piece_size[p] <= fill) {
-                b = (int)q;
-                break;
-            }
-        if (b < 0) {
-            b = (int)blk_fill.size();
-            blk_fill.push_back(0);
-            blk_level.push_back(-1);
-        }
-        blk_fill[b] += piece_size[p];
-        piece_block[p] = b;
-    }
-    // order blocks by level so that producers get the lower block indices
-    const int nbk = (int)blk_fill.size();
-    std::vector<int> bord(nbk), bnew(nbk);
-    std::iota(bord.begin(), bord.end(), 0);
-    std::stable_sort(bord.begin(), bord.end(), [&](int a, int b) {
-        const int la = blk_level[a] < 0 ? n_levels : blk_level[a], lb = blk_level[b] < 0 ? n_levels : blk_level[b];
+    // order warps by level so that producers get the lower indices; free warps go last
+    const int nw = (int)w_fill.size();
+    std::vector<int> word(nw), wnew(nw);
+    std::iota(word.begin(), word.end(), 0);
+    std::stable_sort(word.begin(), word.end(), [&](int a, int b) {
+        const int la = w_level[a] < 0 ? n_levels : w_level[a], lb = w_level[b] < 0 ? n_levels : w_level[b];
         return la < lb;
     });
-    for (int q = 0; q < nbk; ++q) bnew[bord[q]] = q;
+    for (int q = 0; q < nw; ++q) wnew[word[q]] = q;
 
-    // per block cell lists, heavy gather rows first (uniform work inside a warp)
-    std::vector<std::vector<int>> cells(nbk);
-    for (int v = 0; v < n; ++v) cells[bnew[piece_block[piece[v]]]].push_back(v);
-    std::vector<int> cell_block(n), cell_slot(n);
-    for (int b = 0; b < nbk; ++b) {
-        std::stable_sort(cells[b].begin(), cells[b].end(), [&](int x, int y) {
-            return pl->upid[(size_t)x * 9 + 8] > pl->upid[(size_t)y * 9 + 8];
-        });
-        if ((int)cells[b].size() > C) return false;
-        for (size_t s = 0; s < cells[b].size(); ++s) {
-            cell_block[cells[b][s]] = b;
-            cell_slot[cells[b][s]] = (int)s;
-        }
+    // lanes: cells first, ghost lanes behind them
+    std::vector<int> cell_warp(n), cell_lane(n), next_lane(nw, 0);
+    for (int v = 0; v < n; ++v) {
+        const int w = wnew[piece_warp[piece[v]]];
+        cell_warp[v] = w;
+        cell_lane[v] = next_lane[w]++;
     }
-    // cut edges = routing edges whose ends sit in different blocks
-    pk.n_blocks = nbk;
+    pk.n_warps = nw;
     pk.n_levels = n_levels;
-    pk.slot_cell.assign((size_t)nbk * C, -1);
-    pk.slot_out.assign((size_t)nbk * C, -1);
-    pk.slot_nbr.assign((size_t)nbk * C, make_uint4(0, 0, 0, 0));
-    pk.slot_meta.assign((size_t)nbk * C, 0xffff0000u);
-    std::vector<std::vector<int>> ghosts(nbk);   // producing cells seen by block b
-    std::vector<int> edge_of_cell(n, -1);
+    pk.lane_cell.assign((size_t)nw * 32, -1);
+    pk.lane_gedge.assign((size_t)nw * 32, -1);
+    pk.lane_oedge.assign((size_t)nw * 32, -1);
+    pk.lane_src.assign((size_t)nw * 32, make_uint2(0, 0));
+    pk.lane_meta.assign((size_t)nw * 32, 0);
+    std::vector<int> ghost_lane(n, -1), n_ghost(nw, 0);
     for (int v = 0; v < n; ++v) {
         const int r = pl->down[v];
-        if (r >= 0 && cell_block[r] != cell_block[v]) {
-            if (cell_block[v] > cell_block[r]) return false;   // would break the producer-first order
-            edge_of_cell[v] = (int)pk.edge_prod.size();
-            pk.edge_prod.push_back(cell_block[v]);
-            pk.edge_cons.push_back(cell_block[r]);
-            ghosts[cell_block[r]].push_back(v);
+        if (r >= 0 && cell_warp[r] != cell_warp[v]) {
+            const int wp = cell_warp[v], wc = cell_warp[r];
+            if (wp > wc) return false;   // producers must precede consumers
+            const int e = (int)pk.edge_prod.size();
+            pk.edge_prod.push_back(wp);
+            pk.edge_cons.push_back(wc);
+            if (next_lane[wc] >= 32) return false;
+            const int gl = next_lane[wc]++;
+            ghost_lane[v] = gl;
+            pk.lane_gedge[(size_t)wc * 32 + gl] = e;
+            pk.lane_meta[(size_t)wc * 32 + gl] = (unsigned)n_ghost[wc]++ << 8;
+            pk.lane_oedge[(size_t)wp * 32 + cell_lane[v]] = e;
         }
     }
     pk.n_edges = (int)pk.edge_prod.size();
-    pk.ghost_ptr.assign(nbk + 1, 0);
-    for (int b = 0; b < nbk; ++b) {
-        pk.ghost_ptr[b + 1] = pk.ghost_ptr[b] + (int)ghosts[b].size();
-        pk.G = std::max(pk.G, (int)ghosts[b].size());
-    }
-    if (C + pk.G > 32767 || pk.G > T) return false;
-    pk.ghost_edge.assign(std::max(pk.ghost_ptr[nbk], 1), -1);
-    pk.ghost_down.assign(std::max(pk.ghost_ptr[nbk], 1), 0);
-    std::vector<int> ghost_local(n, -1);   // local F index of producing cell v inside its consumer
-    for (int b = 0; b < nbk; ++b)
-        for (size_t k = 0; k < ghosts[b].size(); ++k) {
-            pk.ghost_edge[pk.ghost_ptr[b] + k] = edge_of_cell[ghosts[b][k]];
-            pk.ghost_down[pk.ghost_ptr[b] + k] = cell_slot[pl->down[ghosts[b][k]]];
-            ghost_local[ghosts[b][k]] = C + (int)k;
-        }
+    for (int w = 0; w < nw; ++w) pk.G = std::max(pk.G, n_ghost[w]);
     for (int v = 0; v < n; ++v) {
-        const int b = cell_block[v];
-        const size_t g = (size_t)b * C + cell_slot[v];
-        pk.slot_cell[g] = v;
-        pk.slot_out[g] = edge_of_cell[v];
-        unsigned short e[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int w = cell_warp[v];
+        const size_t g = (size_t)w * 32 + cell_lane[v];
+        pk.lane_cell[g] = v;
+        // row of UM in column order as indices into the warp's exchange buffer:
+        // 0..31 = +F of that lane, 32 = constant zero (padding), 33 + l = -F of lane l (the self term)
+        unsigned long long bits = 0;
         const int beg = pl->row_ptr[v], cnt = pl->row_ptr[v + 1] - beg;
-        int nup = 0, ps = 0;
-        for (int s = 0; s < cnt; ++s) {
-            const int j = pl->col[beg + s];
-            if (j == v) {
-                ps = nup;   // the -F(self) term sits after `ps` upstream terms
-                continue;
+        for (int s = 0; s < 9; ++s) {
+            unsigned idx = 32;
+            if (s < cnt) {
+                const int j = pl->col[beg + s];
+                idx = (j == v) ? 33u + (unsigned)cell_lane[v]
+                               : (unsigned)((cell_warp[j] == w) ? cell_lane[j] : ghost_lane[j]);
             }
-            e[nup++] = (unsigned short)((cell_block[j] == b) ? cell_slot[j] : ghost_local[j]);
+            bits |= (unsigned long long)idx << (7 * s);
         }
-        pk.slot_nbr[g] = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
-        const int r = pl->down[v];
-        const unsigned dl = (r >= 0 && cell_block[r] == b) ? (unsigned)cell_slot[r] : 0xffffu;
-        pk.slot_meta[g] = (unsigned)nup | ((unsigned)ps << 4) | (dl << 16);
+        pk.lane_src[g] = make_uint2((unsigned)(bits & 0xffffffffu), (unsigned)(bits >> 32));
+        pk.lane_meta[g] = (unsigned)cnt;
+    }
+    // padding rows (ghost and empty lanes): all nine terms read the zero slot
+    {
+        unsigned long long zero_row = 0;
+        for (int s = 0; s < 9; ++s) zero_row |= 32ull << (7 * s);
+        for (size_t g = 0; g < pk.lane_cell.size(); ++g)
+            if (pk.lane_cell[g] < 0) pk.lane_src[g] = make_uint2((unsigned)(zero_row & 0xffffffffu), (unsigned)(zero_row >> 32));
     }
     return true;
 }
@@ -399,106 +406,136 @@ __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Row i of UM times F, accumulated from 0.0 in ascending column order (scipy csr_matvec order):
-// `nup` upstream terms (+F_j, read from shared memory) with the -F_i term after the first `ps`.
-// Cells are sorted by nup inside a block, so the nested branches are (nearly) warp-uniform and a
-// headwater cell (nup == 0, about half of all cells) touches no shared memory at all.
-__device__ __forceinline__ double um_row(const double *__restrict__ Fb, uint4 nb, unsigned meta, double Fself) {
-    const int nup = meta & 0xf, ps = (meta >> 4) & 0xf;
-    double d = 0.0;
-#define XAN_TERM(s, word, shift)                    \
-    if (ps == (s)) d = d - Fself;                   \
-    d = d + Fb[((word) >> (shift)) & 0xffffu];
-    if (nup > 0) {
-        XAN_TERM(0, nb.x, 0)
-        if (nup > 1) {
-            XAN_TERM(1, nb.x, 16)
-            if (nup > 2) {
-                XAN_TERM(2, nb.y, 0)
-                if (nup > 3) {
-                    XAN_TERM(3, nb.y, 16)
-                    if (nup > 4) {
-                        XAN_TERM(4, nb.z, 0)
-                        if (nup > 5) {
-                            XAN_TERM(5, nb.z, 16)
-                            if (nup > 6) {
-                                XAN_TERM(6, nb.w, 0)
-                                if (nup > 7) {
-                                    XAN_TERM(7, nb.w, 16)
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    }
-#undef XAN_TERM
-    if (ps == nup) d = d - Fself;
+// Row i of UM times F in ascending column order (scipy csr_matvec order).  The exchange buffer
+// holds +F of every lane (0..31), a constant 0.0 (32) and -F of every lane (33..64); a row is a
+// list of NT indices into it: the upstream terms, the cell's own -F at its column position, and
+// zero padding.  No branch, no select: NT loads and NT - 1 dependent additions.
+// (x + 0.0 == x and 0.0 + x == x for every x that is not -0.0, so the padding is exact.)
+template <int NT>
+__device__ __forceinline__ double um_row(const double *__restrict__ Fb, uint2 src) {
+    const unsigned long long bits = ((unsigned long long)src.y << 32) | src.x;
+    double d = Fb[bits & 0x7f];
+#pragma unroll
+    for (int s = 1; s < NT; ++s) d = d + Fb[(bits >> (7 * s)) & 0x7f];
     return d;
 }
 
 // =============================================================================================
-// tree kernel
+// warp kernel
 // =============================================================================================
-struct TreeArgs {
-    const int *slot_cell;
-    const uint4 *slot_nbr;
-    const unsigned *slot_meta;
-    const int *slot_out;
-    const int *ghost_ptr;
-    const int *ghost_edge;
-    const int *ghost_down;
-    const int *edge_prod;
-    const int *edge_cons;
+struct WarpArgs {
+    const int *lane_cell, *lane_gedge, *lane_oedge;
+    const uint2 *lane_src;
+    const unsigned *lane_meta;
+    const int *edge_prod, *edge_cons;
     int *progress;
-    double *ring;            // [n_edges][RING][ntmax][2]
+    double2 *ring_buf;       // [n_edges][ring][ntmax] (F, F')
     const double *runoff;    // [M][ld]
     const double *flow_dist, *velocity, *area, *chs_prev;
     const int *ndays;        // [M] device
     double *chs, *avg, *instream;
-    int C, G, ntmax, nmonths, spinup, ld;
+    int n_warps, G, ntmax, nmonths, spinup, ld, ring, sleep_ns;
     double dt;
+    long long *dbg;          // optional [n_warps][2]: cycles in compute, cycles waiting
 };
 
-template <int K>
-__global__ void __launch_bounds__(K >= 3 ? 256 : 512, 1) mrtm_tree_kernel(const TreeArgs a) {
-    extern __shared__ double smem[];
-    const int T = blockDim.x, tid = threadIdx.x, b = blockIdx.x;
-    const int C = a.C, W = a.C + a.G;
-    double *X = smem, *Y = smem + W, *Z = smem + 2 * W;   // F, F', next F (X and Z swap)
-    double *gs = smem + 3 * W;                            // [G][ntmax][2] staged ghost series
-    unsigned char *dirty = reinterpret_cast<unsigned char *>(gs + (size_t)a.G * a.ntmax * 2);   // [C]
-    const int g0 = a.ghost_ptr[b], ng = a.ghost_ptr[b + 1] - g0;
+constexpr int SB = 32;         // sub-steps of ghost series staged in shared memory at a time (x2 buffers)
+constexpr int XW = 72;         // doubles per exchange buffer (65 used)
 
-    int cell[K], oedge[K];
-    uint4 nb[K];
-    unsigned meta[K];
-    double S[K], tauinv[K], area[K], Favg[K], erl[K], qn[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-        const size_t g = (size_t)b * C + tid + j * T;
-        cell[j] = a.slot_cell[g];
-        oedge[j] = -1;
-        S[j] = 0.0; tauinv[j] = 0.0; area[j] = 0.0; Favg[j] = 0.0; erl[j] = 0.0; qn[j] = 0.0;
-        nb[j] = make_uint4(0, 0, 0, 0);
-        meta[j] = 0xffff0000u;
-        dirty[tid + j * T] = 0;
-        if (cell[j] >= 0) {
-            nb[j] = a.slot_nbr[g];
-            meta[j] = a.slot_meta[g];
-            oedge[j] = a.slot_out[g];
-            tauinv[j] = a.velocity[cell[j]] / a.flow_dist[cell[j]];                 // mrtm.py:42
-            area[j] = a.area[cell[j]];
-            S[j] = a.chs_prev ? a.chs_prev[cell[j]] : 0.0;
-            qn[j] = a.runoff[cell[j]];   // month 0 of the first pass
+struct LaneState {
+    double S, tauinv, erl, Favg, F, lastFp;
+    uint2 src;
+    bool is_cell;
+};
+
+__device__ __forceinline__ double negate(double x) {   // exact sign flip on the integer pipe
+    return __longlong_as_double(__double_as_longlong(x) ^ (long long)0x8000000000000000ULL);
+}
+
+// `len` (<= SB) sub-steps for one warp.  Xw / Yw: exchange buffers of the warp; gsl: this lane's
+// staged ghost series (F, F') or nullptr; out: ring position written by this lane or nullptr.
+// Common case (no cell of the warp clamped, no ghost flow changed): one exchange, NT loads, NT + 2
+// dependent fp64 operations, one vote.  Otherwise the warp repeats the balance with F' (mrtm.py:56-69).
+template <int NT>
+__device__ __forceinline__ void run_block(LaneState &L, double *Xw, double *Yw, const double2 *gsl, double2 *out,
+                                          int len, double dt, double dtinv, int lane) {
+    const unsigned full = 0xffffffffu;
+    double2 gcur = make_double2(0.0, 0.0);
+    if (gsl) gcur = gsl[0];
+    for (int t = 0; t < len; ++t) {
+        double2 gnext = gcur;
+        if (gsl && t + 1 < len) gnext = gsl[t + 1];      // software pipelined: off the critical path
+        const double F = gsl ? gcur.x : L.F;
+        Xw[lane] = F;
+        Xw[33 + lane] = negate(F);
+        __syncwarp();
+        const double d = um_row<NT>(Xw, L.src) + L.erl;                         // mrtm.py:51
+        const double ddt = d * dt;
+        const bool clamp = L.is_cell && (ddt < (-L.S));                         // mrtm.py:54
+        const bool changed = clamp || (gsl && __double_as_longlong(gcur.x) != __double_as_longlong(gcur.y));
+        double Fp = F, Sn = L.S + ddt;                                          // mrtm.py:76
+        if (__any_sync(full, changed)) {
+            if (clamp) Fp = d + F + L.S * dtinv;                                // mrtm.py:60
+            if (gsl) Fp = gcur.y;
+            Yw[lane] = Fp;
+            Yw[33 + lane] = negate(Fp);
+            __syncwarp();
+            Sn = clamp ? 0.0 : L.S + (um_row<NT>(Yw, L.src) + L.erl) * dt;      // mrtm.py:63, :68-69
         }
+        if (out) out[t] = make_double2(F, Fp);
+        L.S = Sn;
+        L.Favg += Fp;                                                           // mrtm.py:78
+        L.lastFp = Fp;
+        L.F = Sn * L.tauinv;                                                    // mrtm.py:50 (next sub-step)
+        gcur = gnext;
     }
-    const int my_edge = (tid < ng) ? a.ghost_edge[g0 + tid] : -1;
-    const int my_prod = (my_edge >= 0) ? a.edge_prod[my_edge] : -1;
-    const int my_gdown = (my_edge >= 0) ? a.ghost_down[g0 + tid] : 0;
+}
+
+__device__ __forceinline__ int ld_relaxed(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256, 3) mrtm_warp_kernel(const WarpArgs a) {
+    extern __shared__ double smem[];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int w = blockIdx.x * wpb + wib;
+    if (w >= a.n_warps) return;   // no block-level barrier is used below
+    const int per_warp = 2 * XW + 2 * a.G * SB * 2;              // doubles of shared memory per warp
+    double *Xw = smem + (size_t)wib * per_warp, *Yw = Xw + XW;
+    double2 *gs = reinterpret_cast<double2 *>(Xw + 2 * XW);      // [2][G][SB]
+    if (lane == 0) {
+        Xw[32] = 0.0;
+        Yw[32] = 0.0;
+    }
+
+    const size_t g = (size_t)w * 32 + lane;
+    const int cell = a.lane_cell[g], gedge = a.lane_gedge[g], oedge = a.lane_oedge[g];
+    const unsigned meta = a.lane_meta[g];
+    LaneState L;
+    L.src = a.lane_src[g];
+    L.is_cell = cell >= 0;
+    L.S = 0.0; L.tauinv = 0.0; L.erl = 0.0; L.Favg = 0.0; L.F = 0.0; L.lastFp = 0.0;
+    double area = 0.0, qn = 0.0;
+    if (L.is_cell) {
+        L.tauinv = a.velocity[cell] / a.flow_dist[cell];                            // mrtm.py:42
+        area = a.area[cell];
+        L.S = a.chs_prev ? a.chs_prev[cell] : 0.0;
+        qn = a.runoff[cell];   // month 0 of the first pass
+    }
+    const int gslot = (meta >> 8) & 0xff;
+    const double2 *gsl = (gedge >= 0) ? gs + (size_t)gslot * SB : nullptr;
+    const int prod = (gedge >= 0) ? a.edge_prod[gedge] : -1;
+    const int cons = (oedge >= 0) ? a.edge_cons[oedge] : -1;
+    const unsigned ghost_mask = __ballot_sync(full, gedge >= 0);
+    const bool has_out = __any_sync(full, oedge >= 0);
+    const bool linked = has_out || ghost_mask != 0;
+    const int ntmax_row = __reduce_max_sync(full, L.is_cell ? (int)(meta & 0xf) : 1);   // longest row of the warp
     const double dt = a.dt, dtinv = 1. / a.dt;                                      // mrtm.py:43
     const int nsteps = a.spinup + a.nmonths;
+    long long cyc_wait = 0, cyc_all0 = clock64();
 
     for (int step = 0; step < nsteps; ++step) {
         const bool store = step >= a.spinup;
@@ -506,116 +543,85 @@ __global__ void __launch_bounds__(K >= 3 ? 256 : 512, 1) mrtm_tree_kernel(const 
         const int nday = a.ndays[m];
         const int nt = (int)((double)nday * 24 * 3600 / dt);                        // mrtm.py:36
         const double secs = (double)(nday * 24 * 3600);
-        const int slot = step % RING;
-        // ---- wait: producers have finished this month; consumers have freed the ring slot -------
-        if (my_prod >= 0)
-            while (ld_acquire(a.progress + my_prod) < step + 1) __nanosleep(64);
-#pragma unroll
-        for (int j = 0; j < K; ++j)
-            if (oedge[j] >= 0 && step >= RING) {
-                const int cb = a.edge_cons[oedge[j]];
-                while (ld_acquire(a.progress + cb) < step - RING + 1) __nanosleep(64);
-            }
-        __syncthreads();
-        // ---- stage the ghost series of this month into shared memory -----------------------------
-        for (int k = 0; k < ng; ++k) {
-            const double *src = a.ring + ((size_t)a.ghost_edge[g0 + k] * RING + slot) * a.ntmax * 2;
-            double *dst = gs + (size_t)k * a.ntmax * 2;
-            for (int i = tid; i < nt * 2; i += T) dst[i] = __ldcg(src + i);
-        }
-        // ---- month setup ---------------------------------------------------------------------------
         const int mnext = (step + 1 < nsteps) ? ((step + 1 >= a.spinup) ? step + 1 - a.spinup : step + 1) : m;
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            erl[j] = (qn[j] * area[j]) * (1e6 / 1e3) / secs;                        // mrtm.py:45
-            Favg[j] = 0.0;
-            if (cell[j] >= 0) {
-                qn[j] = a.runoff[(size_t)mnext * a.ld + cell[j]];                   // prefetch next month
-                X[tid + j * T] = S[j] * tauinv[j];                                  // mrtm.py:50
-            }
+        const int slot = step % a.ring;
+        L.erl = (qn * area) * (1e6 / 1e3) / secs;                                   // mrtm.py:45
+        L.Favg = 0.0;
+        L.F = L.S * L.tauinv;                                                       // mrtm.py:50
+        if (L.is_cell) qn = a.runoff[(size_t)mnext * a.ld + cell];                  // prefetch next month
+        if (linked) {
+            const long long c0 = clock64();
+            // producers have published this month; consumers have released the ring slot
+            if (prod >= 0)
+                while (ld_relaxed(a.progress + prod) < step + 1) __nanosleep(a.sleep_ns);
+            if (cons >= 0 && step >= a.ring)
+                while (ld_relaxed(a.progress + cons) < step - a.ring + 1) __nanosleep(a.sleep_ns);
+            __threadfence();   // acquire side of the hand-over
+            __syncwarp();
+            cyc_wait += clock64() - c0;
         }
-        __syncthreads();   // staged series visible
-        if (tid < ng) X[C + tid] = gs[(size_t)tid * a.ntmax * 2 + 0];
-        __syncthreads();
+        const double2 *gsrc = (gedge >= 0) ? a.ring_buf + ((size_t)gedge * a.ring + slot) * a.ntmax : nullptr;
+        double2 *obase = (oedge >= 0) ? a.ring_buf + ((size_t)oedge * a.ring + slot) * a.ntmax : nullptr;
 
-        for (int t = 0; t < nt; ++t) {
-            double F[K], Fp[K], Sn[K];
-            bool clamp[K];
-            int flag = 0;
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-                F[j] = S[j] * tauinv[j];
-                Fp[j] = F[j];
-                Sn[j] = S[j];
-                clamp[j] = false;
-                if (cell[j] >= 0) {
-                    const double d = um_row(X, nb[j], meta[j], F[j]) + erl[j];      // mrtm.py:51
-                    clamp[j] = (d * dt) < (-S[j]);                                  // mrtm.py:54
-                    if (clamp[j]) {
-                        Fp[j] = d + F[j] + S[j] * dtinv;                            // mrtm.py:60
-                        Sn[j] = 0.0;                                                // mrtm.py:63
-                        const unsigned dl = meta[j] >> 16;
-                        if (dl != 0xffffu) {   // the receiver must redo its balance with F'
-                            dirty[dl] = 1;
-                            flag = 1;
-                        }
-                    } else {
-                        Sn[j] = S[j] + d * dt;                                      // mrtm.py:76
-                    }
-                    Y[tid + j * T] = Fp[j];
-                    Z[tid + j * T] = Sn[j] * tauinv[j];   // speculative flow of the next sub-step
+        // Ghost series are staged ring (L2) -> shared memory with cp.async, one block of SB sub-steps
+        // ahead of the computation (double buffer), so the L2 latency never sits on the critical path.
+        auto stage = [&](int t0, int buf) {
+            unsigned gm = ghost_mask;
+            while (gm) {
+                const int src_lane = __ffs(gm) - 1;
+                gm &= gm - 1;
+                const double2 *src = reinterpret_cast<const double2 *>(
+                    __shfl_sync(full, (unsigned long long)gsrc, src_lane));
+                const int sl = __shfl_sync(full, gslot, src_lane);
+                if (t0 + lane < nt) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(gs + ((size_t)buf * a.G + sl) * SB + lane);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + t0 + lane) : "memory");
                 }
             }
-            if (tid < ng) {
-                const double *g = gs + ((size_t)tid * a.ntmax + t) * 2;
-                Y[C + tid] = g[1];
-                if (t + 1 < nt) Z[C + tid] = g[2];
-                if (__double_as_longlong(g[0]) != __double_as_longlong(g[1])) {
-                    dirty[my_gdown] = 1;
-                    flag = 1;
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (ghost_mask) stage(0, 0);
+        int buf = 0;
+        for (int t0 = 0; t0 < nt; t0 += SB, buf ^= 1) {
+            const int len = min(SB, nt - t0);
+            if (ghost_mask) {
+                if (t0 + SB < nt) {
+                    stage(t0 + SB, buf ^ 1);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
                 }
+                __syncwarp();
             }
-            if (__syncthreads_or(flag)) {
-                // an inflow changed in the clamp pass: the receivers redo the balance with F' (mrtm.py:66-69)
-#pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    if (cell[j] >= 0 && dirty[tid + j * T]) {
-                        dirty[tid + j * T] = 0;
-                        if (!clamp[j]) {
-                            const double d2 = um_row(Y, nb[j], meta[j], F[j]) + erl[j];
-                            Sn[j] = S[j] + d2 * dt;
-                            Z[tid + j * T] = Sn[j] * tauinv[j];
-                        }
-                    }
-                }
-                __syncthreads();
+            const double2 *gcur = gsl ? gsl + (size_t)buf * a.G * SB : nullptr;
+            double2 *out = obase ? obase + t0 : nullptr;
+            switch (ntmax_row) {
+                case 1: run_block<1>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
+                case 2: run_block<2>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
+                case 3: run_block<3>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
+                case 4: run_block<4>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
+                case 5: run_block<5>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
+                case 6: run_block<6>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
+                case 7: run_block<7>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
+                default: run_block<9>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
             }
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-                S[j] = Sn[j];
-                Favg[j] += Fp[j];                                                   // mrtm.py:78
-                if (oedge[j] >= 0) {
-                    double *r = a.ring + (((size_t)oedge[j] * RING + slot) * a.ntmax + t) * 2;
-                    __stcg(r, F[j]);
-                    __stcg(r + 1, Fp[j]);
-                }
-            }
-            double *tmp = X; X = Z; Z = tmp;
+            if (ghost_mask) __syncwarp();   // everyone is done with this buffer before it is refilled
         }
-#pragma unroll
-        for (int j = 0; j < K; ++j)
-            if (cell[j] >= 0) {
-                if (store) {
-                    if (a.chs) stg_stream(a.chs + (size_t)m * a.ld + cell[j], S[j]);
-                    if (a.avg) stg_stream(a.avg + (size_t)m * a.ld + cell[j], Favg[j] / nt);   // mrtm.py:80
-                }
-                // instantaneous flow after the last sub-step = last published F' (still in Y)
-                if (step == nsteps - 1 && a.instream) a.instream[cell[j]] = Y[tid + j * T];
-            }
-        // ---- publish: this block has finished month `step` ------------------------------------------
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) st_release(a.progress + b, step + 1);
+        if (store && L.is_cell) {
+            if (a.chs) stg_stream(a.chs + (size_t)m * a.ld + cell, L.S);
+            if (a.avg) stg_stream(a.avg + (size_t)m * a.ld + cell, L.Favg / nt);    // mrtm.py:80
+        }
+        if (linked) {
+            // publish: this warp has finished (and, as a consumer, has finished reading) month `step`
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release(a.progress + w, step + 1);
+        }
+    }
+    if (a.instream && L.is_cell) a.instream[cell] = L.lastFp;
+    if (a.dbg && lane == 0) {
+        a.dbg[2 * w] = clock64() - cyc_all0 - cyc_wait;
+        a.dbg[2 * w + 1] = cyc_wait;
     }
 }
 
@@ -694,36 +700,17 @@ __global__ void __launch_bounds__(256) mrtm_grid_kernel(const GridArgs a) {
     }
 }
 
-template <int K>
-static int launch_tree(const xan_mrtm_plan *pl, TreeArgs &args, size_t smem, cudaStream_t s) {
-    XAN_CUDA_CHECK(cudaFuncSetAttribute(mrtm_tree_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0, dev = 0, sms = 0;
-    XAN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mrtm_tree_kernel<K>, pl->T, smem));
-    XAN_CUDA_CHECK(cudaGetDevice(&dev));
-    XAN_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (per_sm * sms < pl->n_blocks) {
-        set_error("mrtm tree kernel: %d blocks cannot be co-resident (%d per SM x %d SMs)", pl->n_blocks, per_sm, sms);
-        return XAN_E_INVALID;
-    }
-    void *kargs[] = {(void *)&args};
-    // cooperative launch = all blocks co-resident, which the cut-edge pipeline relies on
-    XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)mrtm_tree_kernel<K>, dim3(pl->n_blocks), dim3(pl->T), kargs, smem, s));
-    return XAN_OK;
-}
-
 }  // namespace xan
 
 using namespace xan;
 
 static void free_device(xan_mrtm_plan *pl) {
     cudaFree(pl->d_gcol);
-    cudaFree(pl->d_slot_cell);
-    cudaFree(pl->d_slot_nbr);
-    cudaFree(pl->d_slot_meta);
-    cudaFree(pl->d_ghost_down);
-    cudaFree(pl->d_slot_out);
-    cudaFree(pl->d_ghost_ptr);
-    cudaFree(pl->d_ghost_edge);
+    cudaFree(pl->d_lane_cell);
+    cudaFree(pl->d_lane_gedge);
+    cudaFree(pl->d_lane_oedge);
+    cudaFree(pl->d_lane_src);
+    cudaFree(pl->d_lane_meta);
     cudaFree(pl->d_edge_prod);
     cudaFree(pl->d_edge_cons);
     cudaFree(pl->d_progress);
@@ -735,6 +722,25 @@ static bool upload(const std::vector<V> &h, V **d) {
     if (cudaMalloc((void **)d, bytes) != cudaSuccess) return false;
     if (!h.empty() && cudaMemcpy(*d, h.data(), sizeof(V) * h.size(), cudaMemcpyHostToDevice) != cudaSuccess) return false;
     return true;
+}
+
+static int ensure_device(xan_mrtm_plan *pl) {
+    if (pl->on_device) return XAN_OK;
+    const Packing &pk = *pl->packing;
+    bool ok = upload(pl->h_gcol, &pl->d_gcol);
+    if (ok && pl->n_warps > 0) {
+        std::vector<int> zeros(pk.n_warps, 0);
+        ok = upload(pk.lane_cell, &pl->d_lane_cell) && upload(pk.lane_gedge, &pl->d_lane_gedge) &&
+             upload(pk.lane_oedge, &pl->d_lane_oedge) && upload(pk.lane_src, &pl->d_lane_src) &&
+             upload(pk.lane_meta, &pl->d_lane_meta) && upload(pk.edge_prod, &pl->d_edge_prod) &&
+             upload(pk.edge_cons, &pl->d_edge_cons) && upload(zeros, &pl->d_progress);
+    }
+    if (!ok) {
+        set_error("mrtm plan: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return XAN_E_CUDA;
+    }
+    pl->on_device = true;
+    return XAN_OK;
 }
 
 extern "C" {
@@ -753,7 +759,7 @@ int xan_mrtm_upstream(const double *h_coords, const int64_t *h_dsid, int ncell, 
     return host_upstream(h_coords, h_dsid, ncell, nrow, ncol, h_upid);
 }
 
-xan_mrtm_plan *xan_mrtm_plan_create(const int64_t *h_upid, int ncell, int block_threads, int cells_per_thread) {
+xan_mrtm_plan *xan_mrtm_plan_create(const int64_t *h_upid, int ncell, int block_threads, int chunk_substeps) {
     if (!h_upid || ncell <= 0) {
         set_error("xan_mrtm_plan_create: bad arguments");
         return nullptr;
@@ -764,72 +770,36 @@ xan_mrtm_plan *xan_mrtm_plan_create(const int64_t *h_upid, int ncell, int block_
         delete pl;
         return nullptr;
     }
-    // The plan itself is host-side integer work (like the reference's downstream/upstream); the
-    // device tables are uploaded by the first xan_mrtm_route call.  Without a device the SM count
-    // of a B200 is assumed for the fill target so that the packing can still be inspected.
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
-        cudaGetLastError();
-        sms = 148;
-    }
-    const char *env_t = getenv("XANTHOS_MRTM_THREADS"), *env_k = getenv("XANTHOS_MRTM_CELLS_PER_THREAD");
-    pl->T = (block_threads > 0) ? block_threads : (env_t ? atoi(env_t) : 256);
-    pl->K = (cells_per_thread > 0) ? cells_per_thread : (env_k ? atoi(env_k) : 2);
-    if (pl->T % 32 != 0 || pl->T > 512 || pl->K > 4 || (pl->K >= 3 && pl->T > 256)) {
-        set_error("xan_mrtm_plan_create: block_threads must be a multiple of 32, <= 512 (<= 256 when "
-                  "cells_per_thread >= 3), and cells_per_thread <= 4");
+    const char *env_t = getenv("XANTHOS_MRTM_THREADS"), *env_c = getenv("XANTHOS_MRTM_CHUNK"),
+               *env_l = getenv("XANTHOS_MRTM_LANES");
+    pl->block_threads = (block_threads > 0) ? block_threads : (env_t ? atoi(env_t) : 256);
+    pl->chunk = (chunk_substeps > 0) ? chunk_substeps : (env_c ? atoi(env_c) : 64);
+    const int lanes = env_l ? atoi(env_l) : 32;   // lanes a piece may occupy (tests use small values)
+    if (pl->block_threads % 32 != 0 || pl->block_threads < 32 || pl->block_threads > 256 || pl->chunk < 1 ||
+        pl->chunk > 1024 || lanes < 9 || lanes > 32) {
+        set_error("xan_mrtm_plan_create: block_threads must be a multiple of 32 in 32..256, chunk_substeps in "
+                  "1..1024 (XANTHOS_MRTM_LANES in 9..32)");
         delete pl;
         return nullptr;
     }
-    pl->C = pl->T * pl->K;
-    // fill target: spread the cells over (a multiple of) the SM count, never above the capacity
-    const char *env = getenv("XANTHOS_MRTM_BLOCK_CELLS");
-    int fill = env ? atoi(env) : 0;
-    if (fill <= 0) {
-        const int waves = std::max(1, (ncell + sms * pl->C - 1) / (sms * pl->C));
-        fill = (ncell + sms * waves - 1) / (sms * waves);
-        fill = std::max(fill + fill / 32 + 1, 32);
-    }
-    fill = std::min(fill, pl->C);
-
     // grid-kernel gather table
     pl->h_gcol.assign((size_t)9 * ncell, -1);
     for (int i = 0; i < ncell; ++i)
         for (int s = pl->row_ptr[i]; s < pl->row_ptr[i + 1]; ++s)
             pl->h_gcol[(size_t)(s - pl->row_ptr[i]) * ncell + i] = pl->col[s] | (pl->sgn[s] < 0 ? (int)0x80000000 : 0);
 
+    // The plan is host-side integer work (like the reference's upstream_genmatrix); the device
+    // tables are uploaded by the first xan_mrtm_route call.
     pl->packing = new Packing();
-    if (build_packing(pl, pl->C, pl->T, fill, *pl->packing)) {
-        pl->n_blocks = pl->packing->n_blocks;
+    if (build_packing(pl, lanes, *pl->packing)) {
+        pl->n_warps = pl->packing->n_warps;
         pl->n_edges = pl->packing->n_edges;
         pl->n_levels = pl->packing->n_levels;
         pl->G = pl->packing->G;
     } else {
-        pl->n_blocks = 0;   // tree kernel unavailable (graph with cycles or packing failure)
+        pl->n_warps = 0;   // warp kernel unavailable (graph with cycles)
     }
     return pl;
-}
-
-static int ensure_device(xan_mrtm_plan *pl) {
-    if (pl->on_device) return XAN_OK;
-    const Packing &pk = *pl->packing;
-    bool ok = upload(pl->h_gcol, &pl->d_gcol);
-    if (ok && pl->n_blocks > 0) {
-        std::vector<int> zeros(pk.n_blocks, 0);
-        ok = upload(pk.slot_cell, &pl->d_slot_cell) && upload(pk.slot_nbr, &pl->d_slot_nbr) &&
-             upload(pk.slot_meta, &pl->d_slot_meta) && upload(pk.slot_out, &pl->d_slot_out) &&
-             upload(pk.ghost_down, &pl->d_ghost_down) &&
-             upload(pk.ghost_ptr, &pl->d_ghost_ptr) && upload(pk.ghost_edge, &pl->d_ghost_edge) &&
-             upload(pk.edge_prod, &pl->d_edge_prod) && upload(pk.edge_cons, &pl->d_edge_cons) &&
-             upload(zeros, &pl->d_progress);
-    }
-    if (!ok) {
-        set_error("mrtm plan: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return XAN_E_CUDA;
-    }
-    pl->on_device = true;
-    return XAN_OK;
 }
 
 void xan_mrtm_plan_destroy(xan_mrtm_plan *pl) {
@@ -839,12 +809,10 @@ void xan_mrtm_plan_destroy(xan_mrtm_plan *pl) {
     delete pl;
 }
 
-/* test/diagnostic export of the tree-kernel packing: slot_cell [n_blocks * T * K] (cell or -1),
- * edge_prod / edge_cons [n_cut_edges] (block indices).  Any pointer may be NULL. */
-int xan_mrtm_plan_packing(const xan_mrtm_plan *pl, int *h_slot_cell, int *h_edge_prod, int *h_edge_cons) {
+int xan_mrtm_plan_packing(const xan_mrtm_plan *pl, int *h_lane_cell, int *h_edge_prod, int *h_edge_cons) {
     XAN_REQUIRE(pl && pl->packing, "xan_mrtm_plan_packing: null plan");
     const Packing &pk = *pl->packing;
-    if (h_slot_cell) std::copy(pk.slot_cell.begin(), pk.slot_cell.end(), h_slot_cell);
+    if (h_lane_cell) std::copy(pk.lane_cell.begin(), pk.lane_cell.end(), h_lane_cell);
     if (h_edge_prod) std::copy(pk.edge_prod.begin(), pk.edge_prod.end(), h_edge_prod);
     if (h_edge_cons) std::copy(pk.edge_cons.begin(), pk.edge_cons.end(), h_edge_cons);
     return XAN_OK;
@@ -867,11 +835,11 @@ int xan_mrtm_plan_info(const xan_mrtm_plan *pl, int *info) {
     info[0] = pl->is_forest ? 1 : 0;
     info[1] = pl->n_components;
     info[2] = pl->max_component;
-    info[3] = pl->n_blocks;
+    info[3] = pl->n_warps;
     info[4] = pl->n_edges;
     info[5] = pl->n_levels;
-    info[6] = pl->T;
-    info[7] = pl->K;
+    info[6] = pl->block_threads;
+    info[7] = pl->G;
     return XAN_OK;
 }
 
@@ -892,23 +860,25 @@ int xan_mrtm_route(xan_mrtm_plan *pl, const double *d_runoff, const double *d_fl
         XAN_REQUIRE(nt >= 1, "xan_mrtm_route: month %d has no sub-step (ndays=%d, dt=%g)", m, h_ndays[m], dt);
         ntmax = std::max(ntmax, nt);
     }
-    const bool tree_ok = pl->is_forest && pl->n_blocks > 0;
-    XAN_REQUIRE(method != XAN_MRTM_TREE || tree_ok, "xan_mrtm_route: the flow graph is not a forest; tree kernel unavailable");
+    const bool tree_ok = pl->is_forest && pl->n_warps > 0;
+    XAN_REQUIRE(method != XAN_MRTM_TREE || tree_ok, "xan_mrtm_route: the flow graph is not a forest; warp kernel unavailable");
     const bool use_tree = (method == XAN_MRTM_TREE) || (method == XAN_MRTM_AUTO && tree_ok);
 
+    int dev = 0, sms = 0;
+    XAN_CUDA_CHECK(cudaGetDevice(&dev));
+    XAN_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int *d_ndays = nullptr;
     XAN_CUDA_CHECK(cudaMallocAsync(&d_ndays, sizeof(int) * nmonths, s));
     XAN_CUDA_CHECK(cudaMemcpyAsync(d_ndays, h_ndays, sizeof(int) * nmonths, cudaMemcpyHostToDevice, s));
     int rc = XAN_OK;
+    bool done = false;
     if (use_tree) {
-        TreeArgs a;
-        a.slot_cell = pl->d_slot_cell;
-        a.slot_nbr = pl->d_slot_nbr;
-        a.slot_meta = pl->d_slot_meta;
-        a.ghost_down = pl->d_ghost_down;
-        a.slot_out = pl->d_slot_out;
-        a.ghost_ptr = pl->d_ghost_ptr;
-        a.ghost_edge = pl->d_ghost_edge;
+        WarpArgs a;
+        a.lane_cell = pl->d_lane_cell;
+        a.lane_gedge = pl->d_lane_gedge;
+        a.lane_oedge = pl->d_lane_oedge;
+        a.lane_src = pl->d_lane_src;
+        a.lane_meta = pl->d_lane_meta;
         a.edge_prod = pl->d_edge_prod;
         a.edge_cons = pl->d_edge_cons;
         a.progress = pl->d_progress;
@@ -921,34 +891,66 @@ int xan_mrtm_route(xan_mrtm_plan *pl, const double *d_runoff, const double *d_fl
         a.chs = d_chs;
         a.avg = d_avg;
         a.instream = d_instream;
-        a.C = pl->C;
+        a.n_warps = pl->n_warps;
         a.G = pl->G;
         a.ntmax = ntmax;
         a.nmonths = nmonths;
         a.spinup = spinup_months;
         a.ld = ld;
         a.dt = dt;
-        double *ring = nullptr;
-        const size_t ring_elems = (size_t)std::max(pl->n_edges, 1) * RING * ntmax * 2;
-        XAN_CUDA_CHECK(cudaMallocAsync(&ring, sizeof(double) * ring_elems, s));
-        XAN_CUDA_CHECK(cudaMemsetAsync(pl->d_progress, 0, sizeof(int) * pl->n_blocks, s));
-        a.ring = ring;
-        const size_t smem = sizeof(double) * (3 * (size_t)(pl->C + pl->G) + (size_t)pl->G * ntmax * 2) + (size_t)pl->C + 16;
-        if (smem > 227 * 1024) {
-            set_error("xan_mrtm_route: tree kernel needs %zu B of shared memory (G=%d, ntmax=%d)", smem, pl->G, ntmax);
+        {
+            const char *er = getenv("XANTHOS_MRTM_RING"), *es = getenv("XANTHOS_MRTM_SLEEP_NS");
+            a.ring = er ? std::max(1, atoi(er)) : RING_DEFAULT;
+            a.sleep_ns = es ? std::max(0, atoi(es)) : 100;
+        }
+        const int wpb = pl->block_threads / 32;
+        const int blocks = ceil_div(pl->n_warps, wpb);
+        const size_t smem = sizeof(double) * (size_t)wpb * (2 * XW + 2 * (size_t)pl->G * SB * 2);
+        int per_sm = 0;
+        cudaError_t e1 = cudaFuncSetAttribute(mrtm_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e2 = (e1 == cudaSuccess)
+                             ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mrtm_warp_kernel, pl->block_threads, smem)
+                             : e1;
+        if (e2 != cudaSuccess || per_sm * sms < blocks) {
+            // the cut-edge pipeline needs every warp resident at the same time
+            cudaGetLastError();
+            set_error("mrtm warp kernel: %d blocks of %d threads (%zu B smem) cannot be co-resident (%d per SM x %d SMs)",
+                      blocks, pl->block_threads, smem, per_sm, sms);
             rc = XAN_E_INVALID;
         } else {
-            switch (pl->K) {
-                case 1: rc = launch_tree<1>(pl, a, smem, s); break;
-                case 2: rc = launch_tree<2>(pl, a, smem, s); break;
-                case 3: rc = launch_tree<3>(pl, a, smem, s); break;
-                default: rc = launch_tree<4>(pl, a, smem, s); break;
+            double2 *ring = nullptr;
+            const size_t ring_elems = (size_t)std::max(pl->n_edges, 1) * a.ring * ntmax;
+            XAN_CUDA_CHECK(cudaMallocAsync(&ring, sizeof(double2) * ring_elems, s));
+            XAN_CUDA_CHECK(cudaMemsetAsync(pl->d_progress, 0, sizeof(int) * pl->n_warps, s));
+            a.ring_buf = ring;
+            a.dbg = nullptr;
+            if (getenv("XANTHOS_MRTM_DEBUG")) {
+                XAN_CUDA_CHECK(cudaMallocAsync(&a.dbg, sizeof(long long) * 2 * pl->n_warps, s));
             }
+            void *kargs[] = {(void *)&a};
+            // cooperative launch = all blocks co-resident (no grid.sync is used)
+            XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)mrtm_warp_kernel, dim3(blocks), dim3(pl->block_threads),
+                                                       kargs, smem, s));
+            if (a.dbg) {
+                std::vector<long long> h(2 * (size_t)pl->n_warps);
+                XAN_CUDA_CHECK(cudaMemcpyAsync(h.data(), a.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, s));
+                XAN_CUDA_CHECK(cudaStreamSynchronize(s));
+                FILE *f = fopen(getenv("XANTHOS_MRTM_DEBUG"), "w");
+                if (f) {
+                    for (int w = 0; w < pl->n_warps; ++w) fprintf(f, "%d %lld %lld\n", w, h[2 * w], h[2 * w + 1]);
+                    fclose(f);
+                }
+                XAN_CUDA_CHECK(cudaFreeAsync(a.dbg, s));
+            }
+            XAN_CUDA_CHECK(cudaFreeAsync(ring, s));
+            done = true;
         }
-        cudaFreeAsync(ring, s);
-        if (rc != XAN_OK && method == XAN_MRTM_AUTO) rc = 1;   // fall through to the grid kernel
+        if (!done && method == XAN_MRTM_TREE) {
+            cudaFreeAsync(d_ndays, s);
+            return rc;
+        }
     }
-    if (!use_tree || rc == 1) {
+    if (!done) {
         GridArgs g;
         g.gcol = pl->d_gcol;
         g.runoff = d_runoff;
@@ -973,10 +975,8 @@ int xan_mrtm_route(xan_mrtm_plan *pl, const double *d_runoff, const double *d_fl
         g.X = work + 3 * (size_t)pl->ncell;
         g.Y = work + 4 * (size_t)pl->ncell;
         g.Z = work + 5 * (size_t)pl->ncell;
-        int per_sm = 0, dev = 0, sms = 0;
+        int per_sm = 0;
         XAN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mrtm_grid_kernel, 256, 0));
-        XAN_CUDA_CHECK(cudaGetDevice(&dev));
-        XAN_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const int blocks = std::max(1, std::min(per_sm * sms, ceil_div(pl->ncell, 256)));
         void *kargs[] = {(void *)&g};
         XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)mrtm_grid_kernel, dim3(blocks), dim3(256), kargs, 0, s));

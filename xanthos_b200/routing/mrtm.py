@@ -55,11 +55,11 @@ class UpstreamMatrix:
     inspection; `streamrouting` / `route` consume the plan directly.
     """
 
-    def __init__(self, upid, block_threads=0, cells_per_thread=0):
+    def __init__(self, upid, block_threads=0, chunk_substeps=0):
         up, upp = C.as_c(upid, np.int64)
         self.shape = (up.shape[0], up.shape[0])
         self.ncell = up.shape[0]
-        self._plan = C.check_ptr(C.lib().xan_mrtm_plan_create(upp, self.ncell, block_threads, cells_per_thread))
+        self._plan = C.check_ptr(C.lib().xan_mrtm_plan_create(upp, self.ncell, block_threads, chunk_substeps))
 
     def __del__(self):
         try:
@@ -73,8 +73,8 @@ class UpstreamMatrix:
     def info(self):
         buf = (ctypes.c_int * 8)()
         C.check(C.lib().xan_mrtm_plan_info(self._plan, buf))
-        keys = ('is_forest', 'n_components', 'max_component', 'n_blocks', 'n_cut_edges', 'n_levels',
-                'block_threads', 'cells_per_thread')
+        keys = ('is_forest', 'n_components', 'max_component', 'n_warps', 'n_cut_edges', 'n_levels',
+                'block_threads', 'max_ghosts')
         return dict(zip(keys, list(buf)))
 
     def csr_arrays(self):
@@ -92,9 +92,9 @@ class UpstreamMatrix:
         return sparse.csr_matrix((data, indices, indptr), shape=self.shape)
 
     def packing(self):
-        """(slot_cell [n_blocks, block_cells], edge_prod, edge_cons) of the tree kernel, for tests."""
+        """(lane_cell [n_warps, 32], edge_prod, edge_cons) of the warp kernel, for tests."""
         i = self.info
-        nb, c = i['n_blocks'], i['block_threads'] * i['cells_per_thread']
+        nb, c = i['n_warps'], 32
         slot = np.full(max(nb * c, 1), -1, dtype=np.int32)
         ep = np.zeros(max(i['n_cut_edges'], 1), dtype=np.int32)
         ec = np.zeros(max(i['n_cut_edges'], 1), dtype=np.int32)
@@ -104,9 +104,9 @@ class UpstreamMatrix:
         return slot[:nb * c].reshape(nb, c), ep[:i['n_cut_edges']], ec[:i['n_cut_edges']]
 
 
-def upstream_genmatrix(upid, block_threads=0, cells_per_thread=0):
+def upstream_genmatrix(upid, block_threads=0, chunk_substeps=0):
     """UM = UP - I as a routing plan; reference mrtm.py:194-230."""
-    return UpstreamMatrix(upid, block_threads, cells_per_thread)
+    return UpstreamMatrix(upid, block_threads, chunk_substeps)
 
 
 def route_device(um, runoff, flow_dist, str_velocity, area, ndays, dt, spinup_months, chs_prev=None,
