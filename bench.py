@@ -277,7 +277,7 @@ def run_ours(args, rank, world_size, local_rank):
     per_kernel = {
         'pm_pet_kernel': dict(ms=med['pm'], alg_bytes=BYTES_PM * cm),
         'abcd_spinup+reinit+sim': dict(ms=med['abcd'], alg_bytes=BYTES_ABCD * cm),
-        'mrtm_tree_kernel': dict(ms=med['mrtm'], alg_bytes=BYTES_MRTM * cm),
+        'mrtm_warp_kernel': dict(ms=med['mrtm'], alg_bytes=BYTES_MRTM * cm),
     }
     for v in per_kernel.values():
         v['gbs'] = v['alg_bytes'] / (v['ms'] * 1e-3) / 1e9

@@ -412,11 +412,27 @@ __device__ __forceinline__ void st_release(int *p, int v) {
 // zero padding.  No branch, no select: NT loads and NT - 1 dependent additions.
 // (x + 0.0 == x and 0.0 + x == x for every x that is not -0.0, so the padding is exact.)
 template <int NT>
-__device__ __forceinline__ double um_row(const double *__restrict__ Fb, uint2 src) {
+struct RowIdx {
+    int off[NT];   // element offsets into the exchange buffer, decoded once per block of sub-steps
+};
+
+template <int NT>
+__device__ __forceinline__ RowIdx<NT> decode_row(uint2 src) {
     const unsigned long long bits = ((unsigned long long)src.y << 32) | src.x;
-    double d = Fb[bits & 0x7f];
+    RowIdx<NT> r;
 #pragma unroll
-    for (int s = 1; s < NT; ++s) d = d + Fb[(bits >> (7 * s)) & 0x7f];
+    for (int s = 0; s < NT; ++s) r.off[s] = (int)((bits >> (7 * s)) & 0x7f);
+    return r;
+}
+
+template <int NT>
+__device__ __forceinline__ double um_row(const double *__restrict__ Fb, const RowIdx<NT> &r) {
+    double v[NT];
+#pragma unroll
+    for (int s = 0; s < NT; ++s) v[s] = Fb[r.off[s]];   // all loads in flight together
+    double d = v[0];
+#pragma unroll
+    for (int s = 1; s < NT; ++s) d = d + v[s];
     return d;
 }
 
@@ -436,7 +452,7 @@ struct WarpArgs {
     double *chs, *avg, *instream;
     int n_warps, G, ntmax, nmonths, spinup, ld, ring, sleep_ns;
     double dt;
-    long long *dbg;          // optional [n_warps][2]: cycles in compute, cycles waiting
+    long long *dbg;          // optional [n_warps][4]: cycles total, hand-over wait, staging wait, sub-step loops
 };
 
 constexpr int SB = 32;         // sub-steps of ghost series staged in shared memory at a time (x2 buffers)
@@ -453,41 +469,52 @@ __device__ __forceinline__ double negate(double x) {   // exact sign flip on the
 }
 
 // `len` (<= SB) sub-steps for one warp.  Xw / Yw: exchange buffers of the warp; gsl: this lane's
-// staged ghost series (F, F') or nullptr; out: ring position written by this lane or nullptr.
+// staged ghost series (F, F') (only read when is_ghost); out: ring position written when has_out.
 // Common case (no cell of the warp clamped, no ghost flow changed): one exchange, NT loads, NT + 2
 // dependent fp64 operations, one vote.  Otherwise the warp repeats the balance with F' (mrtm.py:56-69).
 template <int NT>
-__device__ __forceinline__ void run_block(LaneState &L, double *Xw, double *Yw, const double2 *gsl, double2 *out,
-                                          int len, double dt, double dtinv, int lane) {
+__device__ __forceinline__ void run_block(LaneState &L, double *Xw, double *Yw, const double2 *gsl, bool is_ghost,
+                                          double2 *out, bool has_out, int len, double dt, double dtinv, int lane) {
     const unsigned full = 0xffffffffu;
-    double2 gcur = make_double2(0.0, 0.0);
-    if (gsl) gcur = gsl[0];
+    const RowIdx<NT> row = decode_row<NT>(L.src);
+    double gF = 0.0, gFp = 0.0;
+    if (is_ghost) {
+        const double2 g0 = gsl[0];
+        gF = g0.x;
+        gFp = g0.y;
+        L.F = gF;
+    }
     for (int t = 0; t < len; ++t) {
-        double2 gnext = gcur;
-        if (gsl && t + 1 < len) gnext = gsl[t + 1];      // software pipelined: off the critical path
-        const double F = gsl ? gcur.x : L.F;
+        double nF = 0.0, nFp = 0.0;
+        if (is_ghost && t + 1 < len) {               // software pipelined: off the critical path
+            const double2 g1 = gsl[t + 1];
+            nF = g1.x;
+            nFp = g1.y;
+        }
+        const double F = L.F;
         Xw[lane] = F;
-        Xw[33 + lane] = negate(F);
+        Xw[33 + lane] = -F;
         __syncwarp();
-        const double d = um_row<NT>(Xw, L.src) + L.erl;                         // mrtm.py:51
+        const double d = um_row<NT>(Xw, row) + L.erl;                           // mrtm.py:51
         const double ddt = d * dt;
         const bool clamp = L.is_cell && (ddt < (-L.S));                         // mrtm.py:54
-        const bool changed = clamp || (gsl && __double_as_longlong(gcur.x) != __double_as_longlong(gcur.y));
+        const bool changed = clamp || (is_ghost && __double_as_longlong(gF) != __double_as_longlong(gFp));
         double Fp = F, Sn = L.S + ddt;                                          // mrtm.py:76
         if (__any_sync(full, changed)) {
             if (clamp) Fp = d + F + L.S * dtinv;                                // mrtm.py:60
-            if (gsl) Fp = gcur.y;
+            if (is_ghost) Fp = gFp;
             Yw[lane] = Fp;
-            Yw[33 + lane] = negate(Fp);
+            Yw[33 + lane] = -Fp;
             __syncwarp();
-            Sn = clamp ? 0.0 : L.S + (um_row<NT>(Yw, L.src) + L.erl) * dt;      // mrtm.py:63, :68-69
+            Sn = clamp ? 0.0 : L.S + (um_row<NT>(Yw, row) + L.erl) * dt;        // mrtm.py:63, :68-69
         }
-        if (out) out[t] = make_double2(F, Fp);
+        if (has_out) out[t] = make_double2(F, Fp);
         L.S = Sn;
         L.Favg += Fp;                                                           // mrtm.py:78
         L.lastFp = Fp;
-        L.F = Sn * L.tauinv;                                                    // mrtm.py:50 (next sub-step)
-        gcur = gnext;
+        L.F = is_ghost ? nF : Sn * L.tauinv;                                    // mrtm.py:50 (next sub-step)
+        gF = nF;
+        gFp = nFp;
     }
 }
 
@@ -497,7 +524,7 @@ __device__ __forceinline__ int ld_relaxed(const int *p) {
     return v;
 }
 
-__global__ void __launch_bounds__(256, 3) mrtm_warp_kernel(const WarpArgs a) {
+__global__ void __launch_bounds__(256, 2) mrtm_warp_kernel(const WarpArgs a) {
     extern __shared__ double smem[];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -526,7 +553,8 @@ __global__ void __launch_bounds__(256, 3) mrtm_warp_kernel(const WarpArgs a) {
         qn = a.runoff[cell];   // month 0 of the first pass
     }
     const int gslot = (meta >> 8) & 0xff;
-    const double2 *gsl = (gedge >= 0) ? gs + (size_t)gslot * SB : nullptr;
+    const bool is_ghost = gedge >= 0, lane_out = oedge >= 0;
+    const double2 *gsl_base = gs + (size_t)(is_ghost ? gslot : 0) * SB;
     const int prod = (gedge >= 0) ? a.edge_prod[gedge] : -1;
     const int cons = (oedge >= 0) ? a.edge_cons[oedge] : -1;
     const unsigned ghost_mask = __ballot_sync(full, gedge >= 0);
@@ -535,7 +563,9 @@ __global__ void __launch_bounds__(256, 3) mrtm_warp_kernel(const WarpArgs a) {
     const int ntmax_row = __reduce_max_sync(full, L.is_cell ? (int)(meta & 0xf) : 1);   // longest row of the warp
     const double dt = a.dt, dtinv = 1. / a.dt;                                      // mrtm.py:43
     const int nsteps = a.spinup + a.nmonths;
-    long long cyc_wait = 0, cyc_all0 = clock64();
+    const bool dbg = a.dbg != nullptr;   // optional per-warp cycle accounting (XANTHOS_MRTM_DEBUG=<file>)
+    long long cyc_wait = 0, cyc_stage = 0, cyc_loop = 0;
+    const long long cyc_all0 = dbg ? clock64() : 0;
 
     for (int step = 0; step < nsteps; ++step) {
         const bool store = step >= a.spinup;
@@ -550,7 +580,7 @@ __global__ void __launch_bounds__(256, 3) mrtm_warp_kernel(const WarpArgs a) {
         L.F = L.S * L.tauinv;                                                       // mrtm.py:50
         if (L.is_cell) qn = a.runoff[(size_t)mnext * a.ld + cell];                  // prefetch next month
         if (linked) {
-            const long long c0 = clock64();
+            const long long c0 = dbg ? clock64() : 0;
             // producers have published this month; consumers have released the ring slot
             if (prod >= 0)
                 while (ld_relaxed(a.progress + prod) < step + 1) __nanosleep(a.sleep_ns);
@@ -558,10 +588,10 @@ __global__ void __launch_bounds__(256, 3) mrtm_warp_kernel(const WarpArgs a) {
                 while (ld_relaxed(a.progress + cons) < step - a.ring + 1) __nanosleep(a.sleep_ns);
             __threadfence();   // acquire side of the hand-over
             __syncwarp();
-            cyc_wait += clock64() - c0;
+            if (dbg) cyc_wait += clock64() - c0;
         }
         const double2 *gsrc = (gedge >= 0) ? a.ring_buf + ((size_t)gedge * a.ring + slot) * a.ntmax : nullptr;
-        double2 *obase = (oedge >= 0) ? a.ring_buf + ((size_t)oedge * a.ring + slot) * a.ntmax : nullptr;
+        double2 *obase = a.ring_buf + ((size_t)(lane_out ? oedge : 0) * a.ring + slot) * a.ntmax;
 
         // Ghost series are staged ring (L2) -> shared memory with cp.async, one block of SB sub-steps
         // ahead of the computation (double buffer), so the L2 latency never sits on the critical path.
@@ -584,6 +614,7 @@ __global__ void __launch_bounds__(256, 3) mrtm_warp_kernel(const WarpArgs a) {
         int buf = 0;
         for (int t0 = 0; t0 < nt; t0 += SB, buf ^= 1) {
             const int len = min(SB, nt - t0);
+            const long long cs0 = dbg ? clock64() : 0;
             if (ghost_mask) {
                 if (t0 + SB < nt) {
                     stage(t0 + SB, buf ^ 1);
@@ -593,18 +624,23 @@ __global__ void __launch_bounds__(256, 3) mrtm_warp_kernel(const WarpArgs a) {
                 }
                 __syncwarp();
             }
-            const double2 *gcur = gsl ? gsl + (size_t)buf * a.G * SB : nullptr;
-            double2 *out = obase ? obase + t0 : nullptr;
+            const long long cs1 = dbg ? clock64() : 0;
+            cyc_stage += cs1 - cs0;
+            const double2 *gcur = gsl_base + (size_t)buf * a.G * SB;
+            double2 *out = obase + t0;
+#define XAN_RUN(NT_) run_block<NT_>(L, Xw, Yw, gcur, is_ghost, out, lane_out, len, dt, dtinv, lane)
             switch (ntmax_row) {
-                case 1: run_block<1>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
-                case 2: run_block<2>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
-                case 3: run_block<3>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
-                case 4: run_block<4>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
-                case 5: run_block<5>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
-                case 6: run_block<6>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
-                case 7: run_block<7>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
-                default: run_block<9>(L, Xw, Yw, gcur, out, len, dt, dtinv, lane); break;
+                case 1: XAN_RUN(1); break;
+                case 2: XAN_RUN(2); break;
+                case 3: XAN_RUN(3); break;
+                case 4: XAN_RUN(4); break;
+                case 5: XAN_RUN(5); break;
+                case 6: XAN_RUN(6); break;
+                case 7: XAN_RUN(7); break;
+                default: XAN_RUN(9); break;
             }
+#undef XAN_RUN
+            if (dbg) cyc_loop += clock64() - cs1;
             if (ghost_mask) __syncwarp();   // everyone is done with this buffer before it is refilled
         }
         if (store && L.is_cell) {
@@ -619,9 +655,11 @@ __global__ void __launch_bounds__(256, 3) mrtm_warp_kernel(const WarpArgs a) {
         }
     }
     if (a.instream && L.is_cell) a.instream[cell] = L.lastFp;
-    if (a.dbg && lane == 0) {
-        a.dbg[2 * w] = clock64() - cyc_all0 - cyc_wait;
-        a.dbg[2 * w + 1] = cyc_wait;
+    if (dbg && lane == 0) {
+        a.dbg[4 * w] = clock64() - cyc_all0;
+        a.dbg[4 * w + 1] = cyc_wait;
+        a.dbg[4 * w + 2] = cyc_stage;
+        a.dbg[4 * w + 3] = cyc_loop;
     }
 }
 
@@ -772,7 +810,7 @@ xan_mrtm_plan *xan_mrtm_plan_create(const int64_t *h_upid, int ncell, int block_
     }
     const char *env_t = getenv("XANTHOS_MRTM_THREADS"), *env_c = getenv("XANTHOS_MRTM_CHUNK"),
                *env_l = getenv("XANTHOS_MRTM_LANES");
-    pl->block_threads = (block_threads > 0) ? block_threads : (env_t ? atoi(env_t) : 256);
+    pl->block_threads = (block_threads > 0) ? block_threads : (env_t ? atoi(env_t) : 128);
     pl->chunk = (chunk_substeps > 0) ? chunk_substeps : (env_c ? atoi(env_c) : 64);
     const int lanes = env_l ? atoi(env_l) : 32;   // lanes a piece may occupy (tests use small values)
     if (pl->block_threads % 32 != 0 || pl->block_threads < 32 || pl->block_threads > 256 || pl->chunk < 1 ||
@@ -925,19 +963,19 @@ int xan_mrtm_route(xan_mrtm_plan *pl, const double *d_runoff, const double *d_fl
             a.ring_buf = ring;
             a.dbg = nullptr;
             if (getenv("XANTHOS_MRTM_DEBUG")) {
-                XAN_CUDA_CHECK(cudaMallocAsync(&a.dbg, sizeof(long long) * 2 * pl->n_warps, s));
+                XAN_CUDA_CHECK(cudaMallocAsync(&a.dbg, sizeof(long long) * 4 * pl->n_warps, s));
             }
             void *kargs[] = {(void *)&a};
             // cooperative launch = all blocks co-resident (no grid.sync is used)
             XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)mrtm_warp_kernel, dim3(blocks), dim3(pl->block_threads),
                                                        kargs, smem, s));
             if (a.dbg) {
-                std::vector<long long> h(2 * (size_t)pl->n_warps);
+                std::vector<long long> h(4 * (size_t)pl->n_warps);
                 XAN_CUDA_CHECK(cudaMemcpyAsync(h.data(), a.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, s));
                 XAN_CUDA_CHECK(cudaStreamSynchronize(s));
                 FILE *f = fopen(getenv("XANTHOS_MRTM_DEBUG"), "w");
                 if (f) {
-                    for (int w = 0; w < pl->n_warps; ++w) fprintf(f, "%d %lld %lld\n", w, h[2 * w], h[2 * w + 1]);
+                    for (int w = 0; w < pl->n_warps; ++w) fprintf(f, "%d %lld %lld %lld %lld\n", w, h[4 * w], h[4 * w + 1], h[4 * w + 2], h[4 * w + 3]);
                     fclose(f);
                 }
                 XAN_CUDA_CHECK(cudaFreeAsync(a.dbg, s));
