@@ -1,0 +1,221 @@
+"""
+CPU tests of the host-side logic: ini parser, loader, C-ABI symbols, integer topology (host code of the
+library), packing invariants, sharding, the batched differential evolution driver, repository layout rules.
+"""
+
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from util import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from xanthos_b200 import _cuda as C
+    hdr = open(os.path.join(ROOT, 'include', 'xanthos_b200.h')).read()
+    declared = set(re.findall(r'\b(xan_[a-z0-9_]+)\s*\(', hdr))
+    declared -= {'xan_pm_tables', 'xan_abcd_plan', 'xan_mrtm_plan'}
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(C.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(C.SIGNATURES), (declared ^ set(C.SIGNATURES))
+    assert lib.xan_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from xanthos_b200.pet import hargreaves_samani as hs
+    from types import SimpleNamespace
+    case, _ = load_golden('case_a')
+    data = SimpleNamespace(coords=case['coords'], hs_tas=case['hs_tas'], hs_tmax=case['hs_tmax'], hs_tmin=case['hs_tmin'])
+    with pytest.raises(RuntimeError):
+        hs.execute(SimpleNamespace(StartYear=1999, EndYear=2001), data)
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for d, _, files in os.walk(os.path.join(ROOT, 'xanthos_b200')):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(d, f)).read()
+                if re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M):
+                    bad.append(os.path.join(d, f))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("name", ["case_a", "case_b"])
+def test_host_topology_bit_exact(name):
+    """downstream / upstream / UM are integer host code of the library: checked here without a GPU."""
+    from types import SimpleNamespace
+    from xanthos_b200.routing import mrtm
+    case, ref = load_golden(name)
+    s = SimpleNamespace(ngridrow=int(case['nrow']), ngridcol=int(case['ncol']))
+    dsid = mrtm.downstream(case['coords'], case['flow_dir'], s)
+    upid = mrtm.upstream(case['coords'], dsid, s)
+    assert np.array_equal(dsid, ref['dsid'])
+    assert np.array_equal(upid, ref['upid'])
+    um = mrtm.upstream_genmatrix(upid)
+    indptr, indices, data = um.csr_arrays()
+    assert np.array_equal(indptr, ref['um_indptr'])
+    assert np.array_equal(indices, ref['um_indices'])
+    assert np.array_equal(data, ref['um_data'])
+
+
+@pytest.mark.parametrize("lanes", [0, 9, 16])
+def test_mrtm_packing_invariants(lanes, monkeypatch):
+    from xanthos_b200 import synthetic
+    from xanthos_b200.routing import mrtm
+    if lanes:
+        monkeypatch.setenv('XANTHOS_MRTM_LANES', str(lanes))
+    w = synthetic.make_world(40, 80, 1500, 8, seed=5, coast_pull=0.0)
+    s = w.settings()
+    dsid = mrtm.downstream(w.coords, w.flow_dir, s)
+    upid = mrtm.upstream(w.coords, dsid, s)
+    um = mrtm.upstream_genmatrix(upid)
+    info = um.info
+    lane_cell, ep, ec = um.packing()
+    assert info['is_forest'] == 1
+    assert np.array_equal(np.sort(lane_cell[lane_cell >= 0]), np.arange(w.ncell))      # every cell exactly once
+    assert (ep < ec).all()                                                             # producers precede consumers
+    assert len(ep) == info['n_cut_edges']
+    # a warp has at most one consumer warp (no back-pressure cycles, see csrc/mrtm.cu)
+    cons = {}
+    for p, c in zip(ep, ec):
+        cons.setdefault(int(p), set()).add(int(c))
+    assert all(len(v) == 1 for v in cons.values())
+    # cells + ghost lanes fit a warp
+    ghosts = np.bincount(ec, minlength=lane_cell.shape[0]) if len(ec) else np.zeros(lane_cell.shape[0], dtype=int)
+    assert ((lane_cell >= 0).sum(axis=1) + ghosts <= 32).all()
+    # every cut edge joins a cell to its receiver
+    warp_of = np.empty(w.ncell, dtype=int)
+    for wi in range(lane_cell.shape[0]):
+        warp_of[lane_cell[wi][lane_cell[wi] >= 0]] = wi
+    has = dsid > 0
+    up_is_adjacent = np.zeros(w.ncell, dtype=bool)
+    for i in range(w.ncell):
+        for j in upid[i, :upid[i, 8]]:
+            up_is_adjacent[j - 1] = True
+    crossing = [(warp_of[i], warp_of[dsid[i] - 1]) for i in range(w.ncell)
+                if has[i] and up_is_adjacent[i] and warp_of[i] != warp_of[dsid[i] - 1]]
+    assert sorted(crossing) == sorted(zip(ep.tolist(), ec.tolist()))
+
+
+def test_cyclic_graph_is_not_a_forest():
+    from xanthos_b200.routing import mrtm
+    upid = np.zeros((3, 9), dtype=np.int64)
+    upid[0, 0], upid[0, 8] = 2, 1      # 2 -> 1
+    upid[1, 0], upid[1, 8] = 3, 1      # 3 -> 2
+    upid[2, 0], upid[2, 8] = 1, 1      # 1 -> 3 : a cycle
+    info = mrtm.upstream_genmatrix(upid).info
+    assert info['is_forest'] == 0 and info['n_warps'] == 0
+
+
+def test_ini_parser_and_config_reader(tmp_path):
+    from xanthos_b200 import synthetic
+    from xanthos_b200.data_reader.ini_reader import ConfigReader, parse_ini
+    from xanthos_b200.data_reader.data_load import DataLoader, ValidationException
+    w = synthetic.make_world(18, 36, 150, 4, seed=2)
+    ini, data = synthetic.write_example(str(tmp_path), w, 1999, 2001, pet='pm', routing_spinup=5)
+    raw = parse_ini(ini)
+    assert raw['PET']['penman-monteith']['pm_lc_years'] == ['1970', '1975', '1980', '1985', '1990', '1995', '2000']
+    c = ConfigReader(ini)
+    assert (c.ncell, c.ngridrow, c.ngridcol, c.nmonths) == (150, 18, 36, 36)
+    assert c.mod_cfg == 'pm_abcd_mrtm' and c.routing_spinup == 5 and c.pm_lc_years[-1] == 2000
+    assert c.output_vars == ['q', 'avgchflow'] and c.OutputUnitStr == 'mmpermonth'
+    d = DataLoader(c)
+    assert d.tair_load.shape == (150, 36) and d.basin_ids.dtype.kind == 'i'
+    assert np.allclose(d.area, w.area) and np.array_equal(d.flow_dir, w.flow_dir)
+    assert np.array_equal(d.lct_load, data['lct_load'])
+    c.update({'pm_tas': np.zeros((10, 36))})
+    with pytest.raises(ValidationException):
+        DataLoader(c)
+
+
+def test_set_month_arrays_mod4_rule():
+    from xanthos_b200.utils.general import set_month_arrays
+    from oracle.calendar_utils import set_month_arrays as oracle_sma
+    a = set_month_arrays(36, 2098, 2100)
+    assert np.array_equal(a, oracle_sma(36, 2098, 2100))
+    assert a[25, 2] == 29        # February 2100 is a leap month under the mod-4 rule
+
+
+def test_sharding_partitions():
+    from xanthos_b200 import sharding, synthetic
+    from xanthos_b200.routing import mrtm
+    w = synthetic.make_world(36, 72, 900, 12, seed=3)
+    parts = sharding.partition_basins(w.basin_ids, 4)
+    allb = np.sort(np.concatenate(parts))
+    assert np.array_equal(allb, np.arange(1, w.n_basins + 1))
+    counts = np.bincount(w.basin_ids)
+    loads = [counts[p].sum() for p in parts]
+    assert max(loads) - min(loads) <= counts.max()
+    assert [len(p) for p in sharding.partition_members(64, 8)] == [8] * 8
+    assert sum(len(p) for p in sharding.partition_members(10, 4)) == 10
+    dsid = mrtm.downstream(w.coords, w.flow_dir, w.settings())
+    assert sharding.basins_closed_under_flow(dsid, w.basin_ids)
+    wc = synthetic.make_world(36, 72, 900, 12, seed=3, cut_basins=True)
+    assert not sharding.basins_closed_under_flow(mrtm.downstream(wc.coords, wc.flow_dir, wc.settings()), wc.basin_ids)
+    sh = sharding.BasinShard(w.basin_ids, parts[1])
+    assert np.all(np.isin(w.basin_ids[sh.cells], parts[1]))
+    tair = np.arange(w.ncell, dtype=float)[:, None] * np.ones((1, 3))
+    ext = sh.take_with_halo(tair)
+    want_prev = np.where(sh.cells > 0, tair[np.maximum(sh.cells - 1, 0), 0], 0.0)
+    got_prev = np.where(sh.prev_idx >= 0, ext[np.maximum(sh.prev_idx, 0), 0], 0.0)
+    assert np.array_equal(got_prev, want_prev)
+
+
+def test_batched_differential_evolution_converges():
+    from xanthos_b200.calibrate.calibrate_abcd import differential_evolution_batched, BOUNDS_SNOW, expand_str_range
+    target = np.array([[0.3, 2.0, 0.5, 0.7, 0.1], [0.9, 7.0, 0.2, 0.1, 0.6]])
+    calls = []
+
+    def ev(x, idx):
+        calls.append(len(idx))
+        return np.sqrt(((x - target[idx][:, None, :]) ** 2).sum(axis=2))
+    r = differential_evolution_batched(ev, 2, BOUNDS_SNOW, seed=1, maxiter=400)
+    assert np.abs(r['x'] - target).max() < 1e-3
+    assert expand_str_range(['0-2', '6', '7-9']) == [0, 1, 2, 6, 7, 8, 9]
+
+
+GLOO_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from xanthos_b200 import sharding
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%s' % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+r = dist.get_rank()
+basin_ids = np.repeat(np.arange(1, 7), [5, 9, 2, 7, 4, 3])
+parts = sharding.partition_basins(basin_ids, 2)
+mine = parts[r]
+vals = torch.tensor([[float(b), float(b) * 10] for b in mine], dtype=torch.float64)
+full = sharding.gather_ragged_rows(mine - 1, vals, 6)
+assert torch.equal(full[:, 0], torch.arange(1, 7, dtype=torch.float64)), full
+agg = torch.full((3, 4), float(r), dtype=torch.float64)
+st = sharding.gather_stack(agg)
+assert st.shape == (2, 3, 4) and float(st[0].mean()) == 0.0 and float(st[1].mean()) == 1.0
+members = sharding.partition_members(5, 2)[r]
+assert list(members) == ([0, 1, 2] if r == 0 else [3, 4])
+dist.destroy_process_group()
+print("rank", r, "ok")
+'''
+
+
+def test_two_rank_gather_with_gloo(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all('ok' in o for o in outs), outs

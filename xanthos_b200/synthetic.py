@@ -379,3 +379,114 @@ def calibration_obs(basin_series, seed=4):
     """'VIC-like' observations: a model series times (1 + N(0, 0.05))."""
     rng = np.random.default_rng(seed + 3000)
     return basin_series * (1.0 + rng.normal(0.0, 0.05, basin_series.shape))
+
+
+# --------------------------------------------------------------------------
+# example project on disk (same file layout as the reference's example data)
+# --------------------------------------------------------------------------
+def write_example(root, world, start_yr, end_yr, pet='pm', routing=True, seed=1, runoff_spinup=None,
+                  routing_spinup=None, calibrate=False, output_vars='q,avgchflow', project='synthetic'):
+    """
+    Write a synthetic project under `root` in the file formats the loader reads
+    (xanthos/data_reader/ini_reader.py:428-435, data_load.py:47-72, 92-135, 200-211) and return the
+    path of its .ini file plus the dict of in-memory inputs.
+    """
+    import os
+    n, m = world.ncell, (end_yr - start_yr + 1) * 12
+    inp = os.path.join(root, 'input')
+    ref = os.path.join(inp, 'reference')
+    dirs = {k: os.path.join(inp, k) for k in ('pet', 'runoff', 'routing')}
+    for d in [ref, os.path.join(dirs['pet'], pet), os.path.join(dirs['runoff'], 'abcd'),
+              os.path.join(dirs['routing'], 'mrtm'), os.path.join(root, 'output')]:
+        os.makedirs(d, exist_ok=True)
+    np.savetxt(os.path.join(ref, 'Grid_Areas_ID.csv'), world.area * 100.0, fmt='%.17g')          # ha
+    np.savetxt(os.path.join(ref, 'coordinates.csv'), world.coords, delimiter=',', fmt='%.17g')
+    with open(os.path.join(ref, 'basin.csv'), 'w') as f:
+        f.write('basin_id\n')
+        np.savetxt(f, world.basin_ids, fmt='%d')
+    with open(os.path.join(ref, 'BasinNames235.txt'), 'w') as f:
+        f.write('\n'.join('Basin_{}'.format(i + 1) for i in range(world.n_basins)) + '\n')
+
+    data = {}
+    pdir = os.path.join(dirs['pet'], pet)
+    lines = ['[PET]', 'pet_module = {}'.format(pet)]
+    if pet == 'pm':
+        pm = pm_inputs(world, start_yr, end_yr, seed=seed)
+        data.update(pm)
+        for key, fn in (('tair_load', 'tas'), ('TMIN_load', 'tmin'), ('rhs_load', 'rhs'), ('wind_load', 'wind'),
+                        ('rsds_load', 'rsds'), ('rlds_load', 'rlds')):
+            np.save(os.path.join(pdir, fn + '.npy'), pm[key])
+        np.save(os.path.join(pdir, 'lct.npy'), pm['lct_load'])
+        np.save(os.path.join(pdir, 'elev.npy'), pm['elev'])
+        et = np.zeros((pm['nlcs'], 13))
+        for k, name in enumerate(('cL', 'beta', 'rslimit', None, None, 'Tminopen', 'Tminclose', 'VPDclose', 'VPDopen',
+                                  'RBLmin', 'RBLmax', 'rc', 'emiss')):
+            if name:
+                et[:, k] = pm[name]
+        np.savetxt(os.path.join(pdir, 'gcam_ET_para.csv'), et, delimiter=',', fmt='%.17g')
+        for name, fn in (('alpha', 'gcam_albedo'), ('lai', 'gcam_lai'), ('laimin', 'gcam_laimin'),
+                         ('laimax', 'gcam_laimax')):
+            np.savetxt(os.path.join(pdir, fn + '.csv'), pm[name], delimiter=',', fmt='%.17g')
+        lines += ['[[penman-monteith]]', 'pet_dir = pm', 'pm_tas = tas.npy', 'pm_tmin = tmin.npy', 'pm_rhs = rhs.npy',
+                  'pm_rlds = rlds.npy', 'pm_rsds = rsds.npy', 'pm_wind = wind.npy', 'pm_lct = lct.npy',
+                  'pm_nlcs = {}'.format(pm['nlcs']), 'pm_water_idx = {}'.format(pm['water_idx']),
+                  'pm_snow_idx = {}'.format(pm['snow_idx']),
+                  'pm_lc_years = ' + ', '.join(str(y) for y in pm['lc_years'])]
+    elif pet == 'hs':
+        hs = hs_inputs(world, start_yr, end_yr, seed=seed)
+        data.update(hs)
+        for k in ('hs_tas', 'hs_tmin', 'hs_tmax'):
+            np.save(os.path.join(pdir, k + '.npy'), hs[k])
+        lines += ['[[hargreaves-samani]]', 'pet_dir = hs', 'hs_tas = hs_tas.npy', 'hs_tmin = hs_tmin.npy',
+                  'hs_tmax = hs_tmax.npy']
+    elif pet == 'thornthwaite':
+        tw = thornthwaite_inputs(world, start_yr, end_yr, seed=seed)
+        data['trn_tas'] = tw['tair']
+        np.save(os.path.join(pdir, 'tas.npy'), tw['tair'])
+        lines += ['[[thornthwaite]]', 'pet_dir = thornthwaite', 'trn_tas = tas.npy']
+
+    ab = abcd_inputs(world, m, seed=seed, with_pet=False)
+    data.update(precip=ab['precip'], tmin=ab['tmin'], abcd_pars=ab['pars'])
+    rdir = os.path.join(dirs['runoff'], 'abcd')
+    np.save(os.path.join(rdir, 'pars.npy'), ab['pars'])
+    np.save(os.path.join(rdir, 'precip.npy'), ab['precip'])
+    np.save(os.path.join(rdir, 'tmin.npy'), ab['tmin'])
+    lines += ['[Runoff]', 'runoff_module = abcd', '[[abcd]]', 'runoff_dir = abcd', 'calib_file = pars.npy',
+              'runoff_spinup = {}'.format(m if runoff_spinup is None else runoff_spinup), 'jobs = -1',
+              'PrecipitationFile = ' + os.path.join(rdir, 'precip.npy'), 'TempMinFile = ' + os.path.join(rdir, 'tmin.npy')]
+    if routing:
+        mdir = os.path.join(dirs['routing'], 'mrtm')
+        np.save(os.path.join(mdir, 'velocity.npy'), world.velocity)
+        np.save(os.path.join(mdir, 'fdistance.npy'), world.flow_dist)
+        np.save(os.path.join(mdir, 'fdirection.npy'), world.flow_dir)
+        lines += ['[Routing]', 'routing_module = mrtm', '[[mrtm]]', 'routing_dir = mrtm',
+                  'routing_spinup = {}'.format(m if routing_spinup is None else routing_spinup),
+                  'channel_velocity = velocity.npy', 'flow_distance = fdistance.npy', 'flow_direction = fdirection.npy']
+    project_lines = [
+        '[Project]', 'ProjectName = ' + project, 'RootDir = ' + root, 'InputFolder = input', 'OutputFolder = output',
+        'RefDir = reference', 'pet_dir = pet', 'RoutingDir = routing', 'RunoffDir = runoff',
+        'ncell = {}'.format(n), 'ngridrow = {}'.format(world.nrow), 'ngridcol = {}'.format(world.ncol),
+        'HistFlag = True', 'n_basins = {}'.format(world.n_basins), 'StartYear = {}'.format(start_yr),
+        'EndYear = {}'.format(end_yr), 'output_vars = ' + output_vars, 'OutputFormat = 4', 'OutputUnit = 0',
+        'OutputInYear = 0', 'AggregateRunoffBasin = 1', 'AggregateRunoffCountry = 0', 'AggregateRunoffGCAMRegion = 0',
+        'PerformDiagnostics = 0', 'CreateTimeSeriesPlot = 0', 'CalculateDroughtStats = 0',
+        'CalculateAccessibleWater = 0', 'CalculateHydropowerPotential = 0', 'CalculateHydropowerActual = 0',
+        'Calibrate = {}'.format(int(calibrate))]
+    if calibrate:
+        lines += ['[Calibrate]', 'set_calibrate = 0', 'observed = ' + os.path.join(root, 'input', 'obs.csv'),
+                  'obs_unit = km3_per_mth', 'calib_out_dir = ' + os.path.join(root, 'output', 'calib'),
+                  'calibration_basins = 1-{}'.format(world.n_basins)]
+    ini = os.path.join(root, project + '.ini')
+    with open(ini, 'w') as f:
+        f.write('\n'.join(project_lines + lines) + '\n')
+    return ini, data
+
+
+def write_observations(path, series, start_yr):
+    """Observed basin runoff CSV: header + rows basin,year,month,value (docs/calibration_tutorial.md:7-8)."""
+    nb, m = series.shape
+    with open(path, 'w') as f:
+        f.write('basin,year,month,value\n')
+        for b in range(nb):
+            for k in range(m):
+                f.write('{},{},{},{:.17g}\n'.format(b + 1, start_yr + k // 12, k % 12 + 1, series[b, k]))
