@@ -217,14 +217,17 @@ def run_ours(args, rank, world_size, local_rank):
     def e2e_step():
         """Reference-facing plug-in calls on host buffers (the Components.simulation sequence)."""
         C.forget_all()
-        pet = pm_mod.run_pmpet(data_ns(host, host['lct_load']), ncell, NLCS, START_YR, end_yr, pm['water_idx'],
-                               pm['snow_idx'], lc_years)
-        pet, aet, q, sav = abcd_mod.abcd_execute(n_basins=world.n_basins, basin_ids=world.basin_ids, pet=pet,
-                                                 precip=host['precip'], tmin=host['tmin'], calib_file=ab['pars'],
-                                                 n_months=nmonths, spinup_steps=spin_ro, jobs=-1)
-        chs, avg, inst = mrtm_mod.route(um, q, world.flow_dist, world.velocity, world.area, ndays, DT, spin_rt)
+        with C.async_host():          # exactly what Components.simulation does (xanthos_b200/components.py)
+            C.prefetch(host['precip'])
+            C.prefetch(host['tmin'])
+            pet = pm_mod.run_pmpet(data_ns(host, host['lct_load']), ncell, NLCS, START_YR, end_yr, pm['water_idx'],
+                                   pm['snow_idx'], lc_years)
+            pet, aet, q, sav = abcd_mod.abcd_execute(n_basins=world.n_basins, basin_ids=world.basin_ids, pet=pet,
+                                                     precip=host['precip'], tmin=host['tmin'], calib_file=ab['pars'],
+                                                     n_months=nmonths, spinup_steps=spin_ro, jobs=-1)
+            chs, avg, inst = mrtm_mod.route(um, q, world.flow_dist, world.velocity, world.area, ndays, DT, spin_rt)
         d2h_bytes_holder[0] = sum(a.nbytes for a in (pet, aet, q, sav, chs, avg, inst))
-        return float(avg[0, -1])
+        return float(avg[0, -1]) + float(pet[0, 0]) + float(sav[-1, -1])
 
     def barrier():
         if world_size > 1:

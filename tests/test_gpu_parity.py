@@ -78,6 +78,22 @@ def test_pm_golden(name):
     assert max_rel(out, ref['pm_pet'], floor=1e-6) < RTOL
 
 
+@pytest.mark.parametrize("exact", ["0", "1"])
+def test_pm_full_width_vs_oracle(exact, monkeypatch):
+    """All 67,420 cells x 2 years (incl. a leap year): throughput kernel and exact-order kernel vs the oracle."""
+    from xanthos_b200 import synthetic
+    from xanthos_b200.pet import penman_monteith as pm
+    from oracle import pet as opet
+    monkeypatch.setenv('XANTHOS_PM_EXACT', exact)
+    w = synthetic.make_world(seed=0)
+    d = synthetic.pm_inputs(w, 1971, 1972, seed=1)
+    for k in ('tair_load', 'TMIN_load', 'rhs_load', 'wind_load', 'rsds_load', 'rlds_load'):
+        d[k] = np.nan_to_num(d[k])
+    want = opet.pm_pet(d, w.ncell, d['nlcs'], 1971, 1972, d['water_idx'], d['snow_idx'], d['lc_years'])
+    got = pm.run_pmpet(SimpleNamespace(**d), w.ncell, d['nlcs'], 1971, 1972, d['water_idx'], d['snow_idx'], d['lc_years'])
+    assert max_rel(got, want, floor=1e-6) < (1e-12 if exact == "1" else 1e-11)
+
+
 @pytest.mark.parametrize("name", ["case_a", "case_b"])
 def test_abcd_golden(name, tmp_path):
     from xanthos_b200.runoff import abcd

@@ -18,6 +18,7 @@ import time
 
 import numpy as np
 
+from . import _cuda as C
 from .utils import general as helper
 from .calibrate import calibrate_abcd as calib_mod
 from .data_writer.out_writer import OutWriter
@@ -117,6 +118,7 @@ class Components:
                                    self.yr_imth_dys[:, 2], self.routing_timestep_hours, self.s.routing_spinup,
                                    chs_prev=self.chs_prev)
             self.ChStorage, self.Avg_ChFlow, self.instream_flow = sr
+            C.host_sync()                                   # the copy of ChStorage may still be in flight
             self.chs_prev = np.copy(self.ChStorage[:, -1])
             return self.Avg_ChFlow
 
@@ -129,6 +131,15 @@ class Components:
 
         logging.info("---{} in progress...".format(notify))
         t0 = time.time()
+        with C.async_host():      # D2H of each stage's results overlaps the next stage; complete on exit
+            self._simulation(run_pet, run_runoff, run_routing)
+        logging.info("---{0} has finished successfully: {1} seconds ---".format(notify, time.time() - t0))
+
+    def _simulation(self, run_pet, run_runoff, run_routing):
+        if run_runoff and self.s.runoff_module == 'abcd':
+            # start uploading the runoff forcing while PET computes
+            C.prefetch(self.data.precip)
+            C.prefetch(self.data.tmin)
 
         if run_pet:
             logging.info("\tProcessing PET...")
@@ -149,8 +160,6 @@ class Components:
             t = time.time()
             self.calculate_routing(self.Q)
             logging.info("\tRouting processed in {} seconds---".format(time.time() - t))
-
-        logging.info("---{0} has finished successfully: {1} seconds ---".format(notify, time.time() - t0))
 
     # ---- post-processing: outside the hot path -------------------
     def _skipped(self, flag, name):

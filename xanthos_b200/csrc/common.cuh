@@ -61,4 +61,27 @@ __device__ __forceinline__ void stg_stream(double *p, double v) {
     asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
+// numpy's pairwise summation order for a contiguous reduction of k <= 128 elements
+// (see oracle/pet.py:numpy_pairwise_sum).  `get(i)` returns element i.
+template <typename F>
+__device__ __forceinline__ double numpy_pairwise_sum(int k, F get) {
+    if (k < 8) {
+        double r = 0.0;
+        for (int i = 0; i < k; ++i) r = r + get(i);
+        return r;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = get(j);
+    int i = 8;
+    const int kb = k - (k % 8);
+    for (; i < kb; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = r[j] + get(i + j);
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < k; ++i) res = res + get(i);
+    return res;
+}
+
 }  // namespace xan

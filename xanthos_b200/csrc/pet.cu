@@ -2,34 +2,12 @@
 // Compiled with -fmad=false: the operation order of the reference formulas is kept so that
 // results differ from numpy only through the <= 2 ulp transcendental functions.
 #include "common.cuh"
+#include "pm_common.cuh"
 
 #include <vector>
 #include <cstring>
 
 namespace xan {
-
-// numpy's pairwise summation order for a contiguous reduction of k <= 128 elements
-// (see oracle/pet.py:numpy_pairwise_sum).  `get(i)` returns element i.
-template <typename F>
-__device__ __forceinline__ double numpy_pairwise_sum(int k, F get) {
-    if (k < 8) {
-        double r = 0.0;
-        for (int i = 0; i < k; ++i) r = r + get(i);
-        return r;
-    }
-    double r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = get(j);
-    int i = 8;
-    const int kb = k - (k % 8);
-    for (; i < kb; i += 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = r[j] + get(i + j);
-    }
-    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-    for (; i < k; ++i) res = res + get(i);
-    return res;
-}
 
 // =============================================================================================
 // Hargreaves-Samani (xanthos/pet/hargreaves_samani.py:31-65, 91-119)
@@ -154,17 +132,6 @@ __global__ void __launch_bounds__(256)
 // =============================================================================================
 // Penman-Monteith (xanthos/pet/penman_monteith.py)
 // =============================================================================================
-struct PmTab {
-    int nlcs, water_idx, snow_idx, pad;
-    double cL[XAN_PM_MAX_CLASSES], beta[XAN_PM_MAX_CLASSES], rslimit[XAN_PM_MAX_CLASSES],
-        Tminopen[XAN_PM_MAX_CLASSES], Tminclose[XAN_PM_MAX_CLASSES], VPDclose[XAN_PM_MAX_CLASSES],
-        VPDopen[XAN_PM_MAX_CLASSES], RBLmin[XAN_PM_MAX_CLASSES], RBLmax[XAN_PM_MAX_CLASSES],
-        rc[XAN_PM_MAX_CLASSES], emiss[XAN_PM_MAX_CLASSES];
-    double alpha[XAN_PM_MAX_CLASSES][12], lai[XAN_PM_MAX_CLASSES][12], laimin[XAN_PM_MAX_CLASSES][12],
-        laimax[XAN_PM_MAX_CLASSES][12];
-    unsigned char lc_index[512];   // land-cover slice per simulated year
-};
-
 // per-(class, month) quantities shared by every cell, built once per block in shared memory
 struct PmShared {
     double fc[XAN_PM_MAX_CLASSES][12];      // vegetation cover fraction (:257-261)
@@ -175,12 +142,6 @@ struct PmShared {
         vopen[XAN_PM_MAX_CLASSES], rblmin[XAN_PM_MAX_CLASSES], rblmax[XAN_PM_MAX_CLASSES],
         rc[XAN_PM_MAX_CLASSES], inv_rc[XAN_PM_MAX_CLASSES], emiss[XAN_PM_MAX_CLASSES];
 };
-
-constexpr double PM_LAMBDA1 = 2.46e6;   // :76-81
-constexpr double PM_CP = 1006;
-constexpr double PM_SIGMA = 4.9e-3;
-constexpr double PM_SIGMA2 = 5.67e-8;
-constexpr double PM_GAMMA = 0.67;
 
 // thread = (cell, year); months outer, land classes inner.
 __global__ void __launch_bounds__(128)
@@ -479,9 +440,14 @@ int xan_pm_pet(const double *d_tair, const double *d_tmin, const double *d_rhs, 
     }
     XAN_CUDA_CHECK(cudaMallocAsync(&d_tab, sizeof(PmTab), s));
     XAN_CUDA_CHECK(cudaMemcpyAsync(d_tab, h_tab, sizeof(PmTab), cudaMemcpyHostToDevice, s));
-    pm_pet_kernel<<<dim3(ceil_div(ncell, 128), nyears), 128, 0, s>>>(d_tair, d_tmin, d_rhs, d_wind, d_rsds,
-                                                                    d_rlds, d_lct, d_elev, d_prev_idx, d_tab,
-                                                                    d_pet, ncell, ld, start_year);
+    const char *exact = getenv("XANTHOS_PM_EXACT");
+    if (exact && exact[0] == '1')
+        pm_pet_kernel<<<dim3(ceil_div(ncell, 128), nyears), 128, 0, s>>>(d_tair, d_tmin, d_rhs, d_wind, d_rsds,
+                                                                        d_rlds, d_lct, d_elev, d_prev_idx, d_tab,
+                                                                        d_pet, ncell, ld, start_year);
+    else
+        launch_pm_pet_fast(d_tair, d_tmin, d_rhs, d_wind, d_rsds, d_rlds, d_lct, d_elev, d_prev_idx, d_tab, d_pet,
+                           ncell, nyears, ld, start_year, s);
     XAN_CUDA_CHECK(cudaGetLastError());
     XAN_CUDA_CHECK(cudaFreeAsync(d_tab, s));
     return XAN_OK;

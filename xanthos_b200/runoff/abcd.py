@@ -100,6 +100,7 @@ def _execute(n_basins, basin_ids, pet, precip, tmin, prm, n_months, spinup_steps
         pet_f = C.Field(e.t[:int(n_months)], e.ncell)
         pet_h = C.remember(pet_f.to_host(), pet_f)
         if (rows < 0).any():
+            C.host_sync()
             pet_h[rows < 0, :] = np.nan
     aet = C.remember(res['aet'].to_host(), res['aet'])
     q = C.remember(res['q'].to_host(), res['q'])
