@@ -46,14 +46,14 @@ struct xan_mrtm_plan {
     std::vector<int> h_gcol;
     int *d_gcol = nullptr;              // [9][ncell] column (bit 31 set = minus sign), -1 = empty
     // ---- warp kernel ------------------------------------------------------------------------
-    int block_threads = 256, chunk = 64;
+    int block_threads = 256, chunk = 64, lanes = 31;   // lanes: lanes of a warp the packing may occupy
     int n_warps = 0, n_edges = 0, n_levels = 0, G = 0;   // G = max ghost lanes of a warp
     xan::Packing *packing = nullptr;    // host copy of the lane tables
     int *d_lane_cell = nullptr;         // [n_warps * 32] cell index or -1
     int *d_lane_gedge = nullptr;        // [n_warps * 32] cut edge READ by this (ghost) lane or -1
     int *d_lane_oedge = nullptr;        // [n_warps * 32] cut edge WRITTEN by this lane or -1
-    uint2 *d_lane_src = nullptr;        // [n_warps * 32] source lane of upstream term 0..7 (8 bit each)
-    unsigned *d_lane_meta = nullptr;    // [n_warps * 32] nup | ps << 4 | ghost slot << 8
+    uint2 *d_lane_src = nullptr;        // [n_warps * 32] row of UM in column order, 9 x 7 bit (see build_packing)
+    unsigned *d_lane_meta = nullptr;    // [n_warps * 32] row length | ghost slot << 8
     int *d_edge_prod = nullptr;         // [n_edges] producing warp
     int *d_edge_cons = nullptr;         // [n_edges] consuming warp
     int *d_progress = nullptr;          // [n_warps] chunks completed (reset per run)
@@ -331,9 +331,33 @@ static bool build_packing(xan_mrtm_plan *pl, int lanes, Packing &pk) {
     });
     for (int q = 0; q < nw; ++q) wnew[word[q]] = q;
 
-    // lanes: cells first, ghost lanes behind them
+    // lanes: cells first, ghost lanes behind them.  Cells take their lanes in depth-first post-order
+    // (every cell right after the sub-tree of its last tributary): along a river reach the upstream
+    // neighbour then sits in the previous lane, so the 64-bit gathers of a half-warp hit 16 different
+    // bank pairs instead of random ones.
+    std::vector<int> post;
+    post.reserve(n);
+    {
+        std::vector<std::pair<int, int>> stack;   // (cell, next child slot)
+        for (int r = 0; r < n; ++r) {
+            if (pl->down[r] >= 0) continue;
+            stack.emplace_back(r, 0);
+            while (!stack.empty()) {
+                auto &top = stack.back();
+                const int v = top.first;
+                if (top.second < pl->upid[(size_t)v * 9 + 8]) {
+                    const int c = pl->upid[(size_t)v * 9 + top.second] - 1;
+                    ++top.second;
+                    stack.emplace_back(c, 0);
+                } else {
+                    post.push_back(v);
+                    stack.pop_back();
+                }
+            }
+        }
+    }
     std::vector<int> cell_warp(n), cell_lane(n), next_lane(nw, 0);
-    for (int v = 0; v < n; ++v) {
+    for (int v : post) {
         const int w = wnew[piece_warp[piece[v]]];
         cell_warp[v] = w;
         cell_lane[v] = next_lane[w]++;
@@ -368,8 +392,8 @@ static bool build_packing(xan_mrtm_plan *pl, int lanes, Packing &pk) {
         const int w = cell_warp[v];
         const size_t g = (size_t)w * 32 + cell_lane[v];
         pk.lane_cell[g] = v;
-        // row of UM in column order as indices into the warp's exchange buffer:
-        // 0..31 = +F of that lane, 32 = constant zero (padding), 33 + l = -F of lane l (the self term)
+        // row of UM in column order, 7 bits per term: 0..31 = +F of that lane, 32 = zero padding,
+        // 33 + l = -F of lane l (the cell's own term)
         unsigned long long bits = 0;
         const int beg = pl->row_ptr[v], cnt = pl->row_ptr[v + 1] - beg;
         for (int s = 0; s < 9; ++s) {
@@ -406,165 +430,264 @@ __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Row i of UM times F in ascending column order (scipy csr_matvec order).  The exchange buffer
-// holds +F of every lane (0..31), a constant 0.0 (32) and -F of every lane (33..64); a row is a
-// list of NT indices into it: the upstream terms, the cell's own -F at its column position, and
-// zero padding.  No branch, no select: NT loads and NT - 1 dependent additions.
-// (x + 0.0 == x and 0.0 + x == x for every x that is not -0.0, so the padding is exact.)
-template <int NT>
-struct RowIdx {
-    int off[NT];   // element offsets into the exchange buffer, decoded once per block of sub-steps
-};
-
-template <int NT>
-__device__ __forceinline__ RowIdx<NT> decode_row(uint2 src) {
-    const unsigned long long bits = ((unsigned long long)src.y << 32) | src.x;
-    RowIdx<NT> r;
-#pragma unroll
-    for (int s = 0; s < NT; ++s) r.off[s] = (int)((bits >> (7 * s)) & 0x7f);
-    return r;
-}
-
-template <int NT>
-__device__ __forceinline__ double um_row(const double *__restrict__ Fb, const RowIdx<NT> &r) {
-    double v[NT];
-#pragma unroll
-    for (int s = 0; s < NT; ++s) v[s] = Fb[r.off[s]];   // all loads in flight together
-    double d = v[0];
-#pragma unroll
-    for (int s = 1; s < NT; ++s) d = d + v[s];
-    return d;
-}
-
 // =============================================================================================
 // warp kernel
 // =============================================================================================
+constexpr int NM_MAX = 2;      // ensemble members advanced together by one warp (independent chains = ILP)
+
 struct WarpArgs {
     const int *lane_cell, *lane_gedge, *lane_oedge;
     const uint2 *lane_src;
     const unsigned *lane_meta;
     const int *edge_prod, *edge_cons;
     int *progress;
-    double2 *ring_buf;       // [n_edges][ring][ntmax] (F, F')
-    const double *runoff;    // [M][ld]
-    const double *flow_dist, *velocity, *area, *chs_prev;
-    const int *ndays;        // [M] device
-    double *chs, *avg, *instream;
-    int n_warps, G, ntmax, nmonths, spinup, ld, ring, sleep_ns;
+    double2 *ring_buf;                 // [n_edges][ring][ntmax][NM] (F, F')
+    const double *runoff[NM_MAX];      // per member [M][ld]
+    const double *chs_prev[NM_MAX];    // per member [ncell] or null
+    const double *flow_dist, *velocity, *area;
+    const int *ndays;                  // [M] device
+    double *chs[NM_MAX], *avg[NM_MAX], *instream[NM_MAX];
+    int n_warps, G, ntmax, nmonths, spinup, ld, ring, sleep_ns, sb;
     double dt;
-    long long *dbg;          // optional [n_warps][4]: cycles total, hand-over wait, staging wait, sub-step loops
+    long long *dbg;          // optional [n_warps][6]: cycles total, hand-over wait, staging wait, sub-step loops, redo count, SM id
 };
 
-constexpr int SB = 32;         // sub-steps of ghost series staged in shared memory at a time (x2 buffers)
-constexpr int XW = 72;         // doubles per exchange buffer (65 used)
-
+template <int NM>
 struct LaneState {
-    double S, tauinv, erl, Favg, F, lastFp;
+    double S[NM], erl[NM], Favg[NM], F[NM];
+    double tauinv;
     uint2 src;
     bool is_cell;
 };
 
-__device__ __forceinline__ double negate(double x) {   // exact sign flip on the integer pipe
-    return __longlong_as_double(__double_as_longlong(x) ^ (long long)0x8000000000000000ULL);
-}
-
-// `len` (<= SB) sub-steps for one warp.  Xw / Yw: exchange buffers of the warp; gsl: this lane's
-// staged ghost series (F, F') (only read when is_ghost); out: ring position written when has_out.
-// Common case (no cell of the warp clamped, no ghost flow changed): one exchange, NT loads, NT + 2
-// dependent fp64 operations, one vote.  Otherwise the warp repeats the balance with F' (mrtm.py:56-69).
+// ---------------------------------------------------------------------------------------------
+// Row i of UM times F in ascending column order (scipy csr_matvec order) without leaving the
+// register file.  A row is NT source lanes; the cell's own term reads its own lane and flips the
+// sign bit (an integer XOR on the high word, exact), padding terms read lane 31, which the packing
+// keeps empty (F == 0.0 for the whole run; x + 0.0 == x for every x that is not -0.0).  Per sub-step
+// and member: 2 NT SHFL.IDX, NT LOP, NT + 5 fp64 instructions, one vote - no shared-memory traffic,
+// no bank conflicts, no __syncwarp.
+// (Splitting the row at the own term into "before" and "after" lists saves the XOR and some rounds,
+// but needs 25 x 2 loop instantiations instead of 8 x 4; with 16 warps of an SM in different loops the
+// 32 KB instruction cache thrashes - measured 78 ms against 53 ms.)
+// ---------------------------------------------------------------------------------------------
 template <int NT>
-__device__ __forceinline__ void run_block(LaneState &L, double *Xw, double *Yw, const double2 *gsl, bool is_ghost,
-                                          double2 *out, bool has_out, int len, double dt, double dtinv, int lane) {
-    const unsigned full = 0xffffffffu;
-    const RowIdx<NT> row = decode_row<NT>(L.src);
-    double gF = 0.0, gFp = 0.0;
-    if (is_ghost) {
-        const double2 g0 = gsl[0];
-        gF = g0.x;
-        gFp = g0.y;
-        L.F = gF;
+struct RowSrc {
+    int lane[NT];
+    unsigned sgn[NT];
+};
+
+template <int NT>
+__device__ __forceinline__ RowSrc<NT> decode_row(uint2 src) {
+    const unsigned long long bits = ((unsigned long long)src.y << 32) | src.x;
+    RowSrc<NT> r;
+#pragma unroll
+    for (int s = 0; s < NT; ++s) {
+        const int idx = (int)((bits >> (7 * s)) & 0x7f);   // 0..31 lane, 32 zero, 33 + l = -F of lane l
+        r.lane[s] = (idx < 32) ? idx : ((idx == 32) ? 31 : idx - 33);
+        r.sgn[s] = (idx > 32) ? 0x80000000u : 0u;
     }
-    for (int t = 0; t < len; ++t) {
-        double nF = 0.0, nFp = 0.0;
-        if (is_ghost && t + 1 < len) {               // software pipelined: off the critical path
-            const double2 g1 = gsl[t + 1];
-            nF = g1.x;
-            nFp = g1.y;
-        }
-        const double F = L.F;
-        Xw[lane] = F;
-        Xw[33 + lane] = -F;
-        __syncwarp();
-        const double d = um_row<NT>(Xw, row) + L.erl;                           // mrtm.py:51
-        const double ddt = d * dt;
-        const bool clamp = L.is_cell && (ddt < (-L.S));                         // mrtm.py:54
-        const bool changed = clamp || (is_ghost && __double_as_longlong(gF) != __double_as_longlong(gFp));
-        double Fp = F, Sn = L.S + ddt;                                          // mrtm.py:76
-        if (__any_sync(full, changed)) {
-            if (clamp) Fp = d + F + L.S * dtinv;                                // mrtm.py:60
-            if (is_ghost) Fp = gFp;
-            Yw[lane] = Fp;
-            Yw[33 + lane] = -Fp;
-            __syncwarp();
-            Sn = clamp ? 0.0 : L.S + (um_row<NT>(Yw, row) + L.erl) * dt;        // mrtm.py:63, :68-69
-        }
-        if (has_out) out[t] = make_double2(F, Fp);
-        L.S = Sn;
-        L.Favg += Fp;                                                           // mrtm.py:78
-        L.lastFp = Fp;
-        L.F = is_ghost ? nF : Sn * L.tauinv;                                    // mrtm.py:50 (next sub-step)
-        gF = nF;
-        gFp = nFp;
-    }
+    return r;
 }
 
-__device__ __forceinline__ int ld_relaxed(const int *p) {
-    int v;
-    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+template <int NT>
+__device__ __forceinline__ double um_row(double F, const RowSrc<NT> &r) {
+    const unsigned full = 0xffffffffu;
+    const int lo = __double2loint(F), hi = __double2hiint(F);
+    double v[NT];
+#pragma unroll
+    for (int s = 0; s < NT; ++s) {   // all shuffles in flight together
+        const int l = __shfl_sync(full, lo, r.lane[s]);
+        const int h = __shfl_sync(full, hi, r.lane[s]) ^ (int)r.sgn[s];
+        v[s] = __hiloint2double(h, l);
+    }
+    double d = v[0];
+#pragma unroll
+    for (int s = 1; s < NT; ++s) d = d + v[s];
+    return d;
+}
+
+// Per-lane predicated memory operations as opaque PTX.  Written as C++ `if (is_ghost) ...` the compiler
+// unswitches the sub-step loop on the (loop-invariant, per-lane) condition; ghost and cell lanes then
+// run in different copies of the loop and every shuffle becomes a WARPSYNC.COLLECTIVE rendezvous of
+// a diverged warp.  With predication the warp stays converged.
+__device__ __forceinline__ void lds_v2_pred(double &x, double &y, const double2 *p, int pred) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t@p ld.shared.v2.f64 {%0, %1}, [%2];\n\t}"
+                 : "+d"(x), "+d"(y)
+                 : "r"(addr), "r"(pred));
+}
+__device__ __forceinline__ void stg_v2_pred(double2 *p, double x, double y, int pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t@p st.global.v2.f64 [%0], {%1, %2};\n\t}" ::"l"(p),
+                 "d"(x), "d"(y), "r"(pred)
+                 : "memory");
+}
+__device__ __forceinline__ double bit_select(double a, double b, long long mask) {   // mask ? a : b, bitwise
+    return __longlong_as_double((__double_as_longlong(a) & mask) | (__double_as_longlong(b) & ~mask));
+}
+// relaxed load if pred != 0, else `dflt`
+__device__ __forceinline__ int ld_relaxed_pred(const int *p, int pred, int dflt) {
+    int v = dflt;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.relaxed.gpu.global.s32 %0, [%1];\n\t}"
+                 : "+r"(v)
+                 : "l"(p), "r"(pred)
+                 : "memory");
     return v;
 }
 
+// `len` (<= sb) sub-steps for one warp and NM members.  gsl: this lane's staged ghost series [len + 1][NM]
+// of (F, F') (only read by ghost lanes; entry `len` is read but never used); out: ring position [len][NM]
+// written by lanes that feed a cut edge.  GHOST: the warp has ghost lanes; OUT: it feeds a cut edge.
+// Lanes that hold no cell (ghost and empty lanes) have S == 0, tauinv == 0, erl == 0 and an all-zero row,
+// so they never clamp and need no `is_cell` test.
+//
+// The loop is rotated by one gather: an iteration starts with d = UM.F + erlateral of sub-step t already
+// summed, and ends by gathering and summing the trial flows of sub-step t + 1.  The vote "did any flow of
+// this warp change" (a clamp in the warp or a ghost series with F' != F) is issued before that gather and
+// only consumed after it, so in the common case neither the vote nor its branch is on the loop-carried
+// chain  d -> DMUL -> DADD -> DMUL -> SHFL -> LOP -> NT x DADD -> DADD.  When a flow changed the balance is
+// repeated with F' (mrtm.py:56-69) and the look-ahead is redone from the corrected storage.
+// The members are independent dependency chains (ILP).
+template <int NT, int NM, bool GHOST, bool OUT>
+__device__ __forceinline__ void run_block(LaneState<NM> &L, const double2 *gsl, bool is_ghost, double2 *out,
+                                          bool lane_out, int len, double dt, double dtinv, double (&lastFp)[NM],
+                                          int &n_redo) {
+    const unsigned full = 0xffffffffu;
+    const RowSrc<NT> row = decode_row<NT>(L.src);
+    const int ghost_i = is_ghost ? 1 : 0, out_i = lane_out ? 1 : 0;
+    const long long gmask = -(long long)ghost_i;
+    double gF[NM], gFp[NM];   // stay 0.0 on lanes that are not ghosts
+    double d[NM];
+#pragma unroll
+    for (int mm = 0; mm < NM; ++mm) {
+        gF[mm] = 0.0;
+        gFp[mm] = 0.0;
+        if (GHOST) {
+            lds_v2_pred(gF[mm], gFp[mm], gsl + mm, ghost_i);
+            L.F[mm] = bit_select(gF[mm], L.F[mm], gmask);
+        }
+        d[mm] = um_row<NT>(L.F[mm], row) + L.erl[mm];                            // mrtm.py:51
+    }
+    const double2 *gnext = gsl + NM;
+    double2 *op = out;
+#pragma unroll 2
+    for (int t = 0; t < len; ++t) {
+        double nF[NM], nFp[NM], Fp[NM], Sn[NM], Fn[NM], dn[NM];
+        bool clamp[NM];
+        bool changed = false;
+#pragma unroll
+        for (int mm = 0; mm < NM; ++mm) {
+            nF[mm] = gF[mm];
+            nFp[mm] = gFp[mm];
+            if (GHOST) lds_v2_pred(nF[mm], nFp[mm], gnext + mm, ghost_i);       // ghost flows of sub-step t + 1
+        }
+#pragma unroll
+        for (int mm = 0; mm < NM; ++mm) {
+            const double ddt = d[mm] * dt;
+            clamp[mm] = ddt < (-L.S[mm]);                                        // mrtm.py:54
+            changed = changed || clamp[mm];
+            if (GHOST) changed = changed || (__double_as_longlong(gF[mm]) != __double_as_longlong(gFp[mm]));
+            Sn[mm] = L.S[mm] + ddt;                                              // mrtm.py:76
+            Fn[mm] = Sn[mm] * L.tauinv;                                          // mrtm.py:50 of sub-step t + 1
+            if (GHOST) Fn[mm] = bit_select(nF[mm], Fn[mm], gmask);
+        }
+        const bool redo = __any_sync(full, changed);
+#pragma unroll
+        for (int mm = 0; mm < NM; ++mm) {                                        // look-ahead, assumes !redo
+            dn[mm] = um_row<NT>(Fn[mm], row) + L.erl[mm];
+            Fp[mm] = L.F[mm];
+        }
+        if (redo) {
+            ++n_redo;
+#pragma unroll
+            for (int mm = 0; mm < NM; ++mm) {
+                const double Fc = d[mm] + L.F[mm] + L.S[mm] * dtinv;             // mrtm.py:60
+                Fp[mm] = clamp[mm] ? Fc : L.F[mm];
+                if (GHOST) Fp[mm] = bit_select(gFp[mm], Fp[mm], gmask);
+                const double S2 = L.S[mm] + (um_row<NT>(Fp[mm], row) + L.erl[mm]) * dt;   // mrtm.py:68-69
+                Sn[mm] = clamp[mm] ? 0.0 : S2;                                   // mrtm.py:63
+                Fn[mm] = Sn[mm] * L.tauinv;
+                if (GHOST) Fn[mm] = bit_select(nF[mm], Fn[mm], gmask);
+                dn[mm] = um_row<NT>(Fn[mm], row) + L.erl[mm];
+            }
+        }
+#pragma unroll
+        for (int mm = 0; mm < NM; ++mm) {
+            if (OUT) stg_v2_pred(op + mm, L.F[mm], Fp[mm], out_i);
+            L.S[mm] = Sn[mm];
+            L.Favg[mm] += Fp[mm];                                                // mrtm.py:78
+            lastFp[mm] = Fp[mm];
+            L.F[mm] = Fn[mm];
+            d[mm] = dn[mm];
+            gF[mm] = nF[mm];
+            gFp[mm] = nFp[mm];
+        }
+        gnext += NM;
+        op += NM;
+    }
+}
+
+template <int NT, int NM>
+__device__ __forceinline__ void run_block_nt(bool has_ghost, bool has_out, LaneState<NM> &L, const double2 *gsl,
+                                             bool is_ghost, double2 *out, bool lane_out, int len, double dt,
+                                             double dtinv, double (&lastFp)[NM], int &n_redo) {
+    if (has_ghost && has_out)
+        run_block<NT, NM, true, true>(L, gsl, is_ghost, out, lane_out, len, dt, dtinv, lastFp, n_redo);
+    else if (has_ghost)
+        run_block<NT, NM, true, false>(L, gsl, is_ghost, out, lane_out, len, dt, dtinv, lastFp, n_redo);
+    else if (has_out)
+        run_block<NT, NM, false, true>(L, gsl, is_ghost, out, lane_out, len, dt, dtinv, lastFp, n_redo);
+    else
+        run_block<NT, NM, false, false>(L, gsl, is_ghost, out, lane_out, len, dt, dtinv, lastFp, n_redo);
+}
+
+template <int NM>
 __global__ void __launch_bounds__(256, 2) mrtm_warp_kernel(const WarpArgs a) {
     extern __shared__ double smem[];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int w = blockIdx.x * wpb + wib;
     if (w >= a.n_warps) return;   // no block-level barrier is used below
-    const int per_warp = 2 * XW + 2 * a.G * SB * 2;              // doubles of shared memory per warp
-    double *Xw = smem + (size_t)wib * per_warp, *Yw = Xw + XW;
-    double2 *gs = reinterpret_cast<double2 *>(Xw + 2 * XW);      // [2][G][SB]
-    if (lane == 0) {
-        Xw[32] = 0.0;
-        Yw[32] = 0.0;
-    }
+    const int SB = a.sb;                                               // sub-steps of ghost series staged at a time
+    const int SBP = SB + 1;                                            // + 1: the look-ahead reads one entry past a block
+    const int per_warp = 2 * a.G * SBP * NM * 2;                       // doubles of shared memory per warp
+    double2 *gs = reinterpret_cast<double2 *>(smem + (size_t)wib * per_warp);   // [2][G][SB + 1][NM]
 
     const size_t g = (size_t)w * 32 + lane;
     const int cell = a.lane_cell[g], gedge = a.lane_gedge[g], oedge = a.lane_oedge[g];
     const unsigned meta = a.lane_meta[g];
-    LaneState L;
+    LaneState<NM> L;
     L.src = a.lane_src[g];
     L.is_cell = cell >= 0;
-    L.S = 0.0; L.tauinv = 0.0; L.erl = 0.0; L.Favg = 0.0; L.F = 0.0; L.lastFp = 0.0;
-    double area = 0.0, qn = 0.0;
+    L.tauinv = 0.0;
+    double area = 0.0, qn[NM], lastFp[NM];
     if (L.is_cell) {
         L.tauinv = a.velocity[cell] / a.flow_dist[cell];                            // mrtm.py:42
         area = a.area[cell];
-        L.S = a.chs_prev ? a.chs_prev[cell] : 0.0;
-        qn = a.runoff[cell];   // month 0 of the first pass
+    }
+#pragma unroll
+    for (int mm = 0; mm < NM; ++mm) {
+        L.S[mm] = 0.0; L.erl[mm] = 0.0; L.Favg[mm] = 0.0; L.F[mm] = 0.0;
+        qn[mm] = 0.0;
+        lastFp[mm] = 0.0;
+        if (L.is_cell) {
+            L.S[mm] = a.chs_prev[mm] ? a.chs_prev[mm][cell] : 0.0;
+            qn[mm] = a.runoff[mm][cell];   // month 0 of the first pass
+        }
     }
     const int gslot = (meta >> 8) & 0xff;
+    const int ntmax_row = __reduce_max_sync(full, L.is_cell ? (int)(meta & 0xf) : 1);   // longest row of the warp
     const bool is_ghost = gedge >= 0, lane_out = oedge >= 0;
-    const double2 *gsl_base = gs + (size_t)(is_ghost ? gslot : 0) * SB;
     const int prod = (gedge >= 0) ? a.edge_prod[gedge] : -1;
     const int cons = (oedge >= 0) ? a.edge_cons[oedge] : -1;
     const unsigned ghost_mask = __ballot_sync(full, gedge >= 0);
     const bool has_out = __any_sync(full, oedge >= 0);
     const bool linked = has_out || ghost_mask != 0;
-    const int ntmax_row = __reduce_max_sync(full, L.is_cell ? (int)(meta & 0xf) : 1);   // longest row of the warp
     const double dt = a.dt, dtinv = 1. / a.dt;                                      // mrtm.py:43
     const int nsteps = a.spinup + a.nmonths;
     const bool dbg = a.dbg != nullptr;   // optional per-warp cycle accounting (XANTHOS_MRTM_DEBUG=<file>)
     long long cyc_wait = 0, cyc_stage = 0, cyc_loop = 0;
+    int n_redo = 0;
     const long long cyc_all0 = dbg ? clock64() : 0;
 
     for (int step = 0; step < nsteps; ++step) {
@@ -575,37 +698,51 @@ __global__ void __launch_bounds__(256, 2) mrtm_warp_kernel(const WarpArgs a) {
         const double secs = (double)(nday * 24 * 3600);
         const int mnext = (step + 1 < nsteps) ? ((step + 1 >= a.spinup) ? step + 1 - a.spinup : step + 1) : m;
         const int slot = step % a.ring;
-        L.erl = (qn * area) * (1e6 / 1e3) / secs;                                   // mrtm.py:45
-        L.Favg = 0.0;
-        L.F = L.S * L.tauinv;                                                       // mrtm.py:50
-        if (L.is_cell) qn = a.runoff[(size_t)mnext * a.ld + cell];                  // prefetch next month
+#pragma unroll
+        for (int mm = 0; mm < NM; ++mm) {
+            L.erl[mm] = (qn[mm] * area) * (1e6 / 1e3) / secs;                       // mrtm.py:45
+            L.Favg[mm] = 0.0;
+            L.F[mm] = L.S[mm] * L.tauinv;                                           // mrtm.py:50
+            if (L.is_cell) qn[mm] = a.runoff[mm][(size_t)mnext * a.ld + cell];      // prefetch next month
+        }
         if (linked) {
             const long long c0 = dbg ? clock64() : 0;
-            // producers have published this month; consumers have released the ring slot
-            if (prod >= 0)
-                while (ld_relaxed(a.progress + prod) < step + 1) __nanosleep(a.sleep_ns);
-            if (cons >= 0 && step >= a.ring)
-                while (ld_relaxed(a.progress + cons) < step - a.ring + 1) __nanosleep(a.sleep_ns);
+            // Producers have published this month; consumers have released the ring slot.
+            // Polled by the whole warp in lock step (predicated loads, one vote per round).  A per-lane
+            // `while` here leaves the polling lane diverged from the other 31 for the rest of the month:
+            // the sub-step loop then runs twice per warp and every shuffle takes the divergent path
+            // (measured: 4.5x slower).
+            const int want_p = step + 1, want_c = step - a.ring + 1;
+            const int poll_p = (prod >= 0) ? 1 : 0, poll_c = (cons >= 0 && step >= a.ring) ? 1 : 0;
+            const int *pp = a.progress + (prod >= 0 ? prod : 0), *pc = a.progress + (cons >= 0 ? cons : 0);
+            for (;;) {
+                const int vp = ld_relaxed_pred(pp, poll_p, want_p), vc = ld_relaxed_pred(pc, poll_c, want_c);
+                if (__all_sync(full, vp >= want_p && vc >= want_c)) break;
+                __nanosleep(a.sleep_ns);
+            }
             __threadfence();   // acquire side of the hand-over
             __syncwarp();
             if (dbg) cyc_wait += clock64() - c0;
         }
-        const double2 *gsrc = (gedge >= 0) ? a.ring_buf + ((size_t)gedge * a.ring + slot) * a.ntmax : nullptr;
-        double2 *obase = a.ring_buf + ((size_t)(lane_out ? oedge : 0) * a.ring + slot) * a.ntmax;
+        const double2 *gsrc = (gedge >= 0) ? a.ring_buf + ((size_t)gedge * a.ring + slot) * a.ntmax * NM : nullptr;
+        double2 *obase = a.ring_buf + ((size_t)(lane_out ? oedge : 0) * a.ring + slot) * a.ntmax * NM;
 
         // Ghost series are staged ring (L2) -> shared memory with cp.async, one block of SB sub-steps
         // ahead of the computation (double buffer), so the L2 latency never sits on the critical path.
         auto stage = [&](int t0, int buf) {
             unsigned gm = ghost_mask;
+            const int cnt = min(SB, nt - t0) * NM;
             while (gm) {
                 const int src_lane = __ffs(gm) - 1;
                 gm &= gm - 1;
                 const double2 *src = reinterpret_cast<const double2 *>(
                     __shfl_sync(full, (unsigned long long)gsrc, src_lane));
                 const int sl = __shfl_sync(full, gslot, src_lane);
-                if (t0 + lane < nt) {
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(gs + ((size_t)buf * a.G + sl) * SB + lane);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + t0 + lane) : "memory");
+                for (int i = lane; i < cnt; i += 32) {
+                    const unsigned dst =
+                        (unsigned)__cvta_generic_to_shared(gs + ((size_t)buf * a.G + sl) * SBP * NM + i);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)t0 * NM + i)
+                                 : "memory");
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -626,9 +763,10 @@ __global__ void __launch_bounds__(256, 2) mrtm_warp_kernel(const WarpArgs a) {
             }
             const long long cs1 = dbg ? clock64() : 0;
             cyc_stage += cs1 - cs0;
-            const double2 *gcur = gsl_base + (size_t)buf * a.G * SB;
-            double2 *out = obase + t0;
-#define XAN_RUN(NT_) run_block<NT_>(L, Xw, Yw, gcur, is_ghost, out, lane_out, len, dt, dtinv, lane)
+            const double2 *gcur = gs + ((size_t)buf * a.G + (is_ghost ? gslot : 0)) * SBP * NM;
+            double2 *out = obase + (size_t)t0 * NM;
+#define XAN_RUN(NT_) \
+    run_block_nt<NT_, NM>(ghost_mask != 0, has_out, L, gcur, is_ghost, out, lane_out, len, dt, dtinv, lastFp, n_redo)
             switch (ntmax_row) {
                 case 1: XAN_RUN(1); break;
                 case 2: XAN_RUN(2); break;
@@ -644,8 +782,11 @@ __global__ void __launch_bounds__(256, 2) mrtm_warp_kernel(const WarpArgs a) {
             if (ghost_mask) __syncwarp();   // everyone is done with this buffer before it is refilled
         }
         if (store && L.is_cell) {
-            if (a.chs) stg_stream(a.chs + (size_t)m * a.ld + cell, L.S);
-            if (a.avg) stg_stream(a.avg + (size_t)m * a.ld + cell, L.Favg / nt);    // mrtm.py:80
+#pragma unroll
+            for (int mm = 0; mm < NM; ++mm) {
+                if (a.chs[mm]) stg_stream(a.chs[mm] + (size_t)m * a.ld + cell, L.S[mm]);
+                if (a.avg[mm]) stg_stream(a.avg[mm] + (size_t)m * a.ld + cell, L.Favg[mm] / nt);   // mrtm.py:80
+            }
         }
         if (linked) {
             // publish: this warp has finished (and, as a consumer, has finished reading) month `step`
@@ -654,12 +795,20 @@ __global__ void __launch_bounds__(256, 2) mrtm_warp_kernel(const WarpArgs a) {
             if (lane == 0) st_release(a.progress + w, step + 1);
         }
     }
-    if (a.instream && L.is_cell) a.instream[cell] = L.lastFp;
+    if (L.is_cell) {
+#pragma unroll
+        for (int mm = 0; mm < NM; ++mm)
+            if (a.instream[mm]) a.instream[mm][cell] = lastFp[mm];
+    }
     if (dbg && lane == 0) {
-        a.dbg[4 * w] = clock64() - cyc_all0;
-        a.dbg[4 * w + 1] = cyc_wait;
-        a.dbg[4 * w + 2] = cyc_stage;
-        a.dbg[4 * w + 3] = cyc_loop;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.dbg[6 * w] = clock64() - cyc_all0;
+        a.dbg[6 * w + 1] = cyc_wait;
+        a.dbg[6 * w + 2] = cyc_stage;
+        a.dbg[6 * w + 3] = cyc_loop;
+        a.dbg[6 * w + 4] = n_redo;
+        a.dbg[6 * w + 5] = smid;
     }
 }
 
@@ -812,11 +961,14 @@ xan_mrtm_plan *xan_mrtm_plan_create(const int64_t *h_upid, int ncell, int block_
                *env_l = getenv("XANTHOS_MRTM_LANES");
     pl->block_threads = (block_threads > 0) ? block_threads : (env_t ? atoi(env_t) : 128);
     pl->chunk = (chunk_substeps > 0) ? chunk_substeps : (env_c ? atoi(env_c) : 64);
-    const int lanes = env_l ? atoi(env_l) : 32;   // lanes a piece may occupy (tests use small values)
+    // lanes a warp may occupy (tests use small values); 31 keeps lane 31 empty, which the shuffle
+    // exchange uses as its constant-zero source
+    const int lanes = env_l ? atoi(env_l) : 31;
+    pl->lanes = lanes;
     if (pl->block_threads % 32 != 0 || pl->block_threads < 32 || pl->block_threads > 256 || pl->chunk < 1 ||
-        pl->chunk > 1024 || lanes < 9 || lanes > 32) {
+        pl->chunk > 1024 || lanes < 9 || lanes > 31) {
         set_error("xan_mrtm_plan_create: block_threads must be a multiple of 32 in 32..256, chunk_substeps in "
-                  "1..1024 (XANTHOS_MRTM_LANES in 9..32)");
+                  "1..1024 (XANTHOS_MRTM_LANES in 9..31)");
         delete pl;
         return nullptr;
     }
@@ -881,12 +1033,108 @@ int xan_mrtm_plan_info(const xan_mrtm_plan *pl, int *info) {
     return XAN_OK;
 }
 
-int xan_mrtm_route(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_dist, const double *d_velocity,
-                   const double *d_area, const double *d_chs_prev, const int *h_ndays, int nmonths, int spinup_months,
-                   int ld, double dt, int method, double *d_chs, double *d_avg, double *d_instream, void *stream) {
-    XAN_REQUIRE(pl && d_runoff && d_flow_dist && d_velocity && d_area && h_ndays, "xan_mrtm_route: null pointer");
+}  // extern "C"
+
+// Launch the warp kernel for `nm` (1..NM_MAX) members.  Returns XAN_OK, or XAN_E_INVALID when the
+// blocks cannot all be resident (the caller may then fall back to the grid kernel).
+template <int NM>
+static int launch_warp(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, cudaStream_t s) {
+    const int wpb = pl->block_threads / 32;
+    const int blocks = ceil_div(pl->n_warps, wpb);
+    XAN_CUDA_CHECK(cudaFuncSetAttribute(mrtm_warp_kernel<NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int per_sm = 0;
+    size_t smem = 0;
+    for (int sb : {32, 16, 8}) {   // shrink the staging blocks until every warp fits on the device
+        a.sb = sb;
+        smem = sizeof(double) * (size_t)wpb * (2 * (size_t)pl->G * (sb + 1) * NM * 2);
+        if (smem > 200 * 1024) continue;
+        XAN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mrtm_warp_kernel<NM>, pl->block_threads, smem));
+        if (per_sm * sms >= blocks) break;
+    }
+    if (per_sm * sms < blocks) {
+        // the cut-edge pipeline needs every warp resident at the same time
+        set_error("mrtm warp kernel: %d blocks of %d threads (%zu B smem, %d members) cannot be co-resident "
+                  "(%d per SM x %d SMs)", blocks, pl->block_threads, smem, NM, per_sm, sms);
+        return XAN_E_INVALID;
+    }
+    const char *er = getenv("XANTHOS_MRTM_RING"), *es = getenv("XANTHOS_MRTM_SLEEP_NS");
+    a.ring = er ? std::max(1, atoi(er)) : RING_DEFAULT;
+    a.sleep_ns = es ? std::max(0, atoi(es)) : 100;
+    double2 *ring = nullptr;
+    const size_t ring_elems = (size_t)std::max(pl->n_edges, 1) * a.ring * ntmax * NM;
+    XAN_CUDA_CHECK(cudaMallocAsync(&ring, sizeof(double2) * ring_elems, s));
+    XAN_CUDA_CHECK(cudaMemsetAsync(pl->d_progress, 0, sizeof(int) * pl->n_warps, s));
+    a.ring_buf = ring;
+    a.dbg = nullptr;
+    if (getenv("XANTHOS_MRTM_DEBUG")) XAN_CUDA_CHECK(cudaMallocAsync(&a.dbg, sizeof(long long) * 6 * pl->n_warps, s));
+    void *kargs[] = {(void *)&a};
+    // cooperative launch = all blocks co-resident (no grid.sync is used)
+    XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)mrtm_warp_kernel<NM>, dim3(blocks), dim3(pl->block_threads), kargs,
+                                               smem, s));
+    if (a.dbg) {
+        std::vector<long long> h(6 * (size_t)pl->n_warps);
+        XAN_CUDA_CHECK(cudaMemcpyAsync(h.data(), a.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, s));
+        XAN_CUDA_CHECK(cudaStreamSynchronize(s));
+        FILE *f = fopen(getenv("XANTHOS_MRTM_DEBUG"), "w");
+        if (f) {
+            for (int w = 0; w < pl->n_warps; ++w)
+                fprintf(f, "%d %lld %lld %lld %lld %lld %lld\n", w, h[6 * w], h[6 * w + 1], h[6 * w + 2], h[6 * w + 3],
+                        h[6 * w + 4], h[6 * w + 5]);
+            fclose(f);
+        }
+        XAN_CUDA_CHECK(cudaFreeAsync(a.dbg, s));
+    }
+    XAN_CUDA_CHECK(cudaFreeAsync(ring, s));
+    return XAN_OK;
+}
+
+static int route_grid(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_dist, const double *d_velocity,
+                      const double *d_area, const double *d_chs_prev, const int *d_ndays, int nmonths, int spinup_months,
+                      int ld, double dt, double *d_chs, double *d_avg, double *d_instream, int sms, cudaStream_t s) {
+    GridArgs g;
+    g.gcol = pl->d_gcol;
+    g.runoff = d_runoff;
+    g.flow_dist = d_flow_dist;
+    g.velocity = d_velocity;
+    g.area = d_area;
+    g.chs_prev = d_chs_prev;
+    g.ndays = d_ndays;
+    g.chs = d_chs;
+    g.avg = d_avg;
+    g.instream = d_instream;
+    g.ncell = pl->ncell;
+    g.nmonths = nmonths;
+    g.spinup = spinup_months;
+    g.ld = ld;
+    g.dt = dt;
+    double *work = nullptr;
+    XAN_CUDA_CHECK(cudaMallocAsync(&work, sizeof(double) * 6 * (size_t)pl->ncell, s));
+    g.S = work;
+    g.Favg = work + pl->ncell;
+    g.D = work + 2 * (size_t)pl->ncell;
+    g.X = work + 3 * (size_t)pl->ncell;
+    g.Y = work + 4 * (size_t)pl->ncell;
+    g.Z = work + 5 * (size_t)pl->ncell;
+    int per_sm = 0;
+    XAN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mrtm_grid_kernel, 256, 0));
+    const int blocks = std::max(1, std::min(per_sm * sms, ceil_div(pl->ncell, 256)));
+    void *kargs[] = {(void *)&g};
+    XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)mrtm_grid_kernel, dim3(blocks), dim3(256), kargs, 0, s));
+    XAN_CUDA_CHECK(cudaFreeAsync(work, s));
+    return XAN_OK;
+}
+
+extern "C" {
+
+int xan_mrtm_route_batch(xan_mrtm_plan *pl, int n_members, const double *const *h_runoff, const double *d_flow_dist,
+                         const double *d_velocity, const double *d_area, const double *const *h_chs_prev,
+                         const int *h_ndays, int nmonths, int spinup_months, int ld, double dt, int method,
+                         double *const *h_chs, double *const *h_avg, double *const *h_instream, void *stream) {
+    XAN_REQUIRE(pl && h_runoff && d_flow_dist && d_velocity && d_area && h_ndays && n_members >= 1,
+                "xan_mrtm_route_batch: null pointer");
     XAN_REQUIRE(nmonths > 0 && spinup_months >= 0 && spinup_months <= nmonths && ld >= pl->ncell && dt > 0,
                 "xan_mrtm_route: bad arguments nmonths=%d spinup=%d ld=%d dt=%g", nmonths, spinup_months, ld, dt);
+    for (int k = 0; k < n_members; ++k) XAN_REQUIRE(h_runoff[k], "xan_mrtm_route_batch: runoff of member %d is null", k);
     cudaStream_t s = (cudaStream_t)stream;
     {
         const int rc0 = ensure_device(pl);
@@ -900,7 +1148,7 @@ int xan_mrtm_route(xan_mrtm_plan *pl, const double *d_runoff, const double *d_fl
     }
     const bool tree_ok = pl->is_forest && pl->n_warps > 0;
     XAN_REQUIRE(method != XAN_MRTM_TREE || tree_ok, "xan_mrtm_route: the flow graph is not a forest; warp kernel unavailable");
-    const bool use_tree = (method == XAN_MRTM_TREE) || (method == XAN_MRTM_AUTO && tree_ok);
+    bool use_tree = (method == XAN_MRTM_TREE) || (method == XAN_MRTM_AUTO && tree_ok);
 
     int dev = 0, sms = 0;
     XAN_CUDA_CHECK(cudaGetDevice(&dev));
@@ -908,121 +1156,67 @@ int xan_mrtm_route(xan_mrtm_plan *pl, const double *d_runoff, const double *d_fl
     int *d_ndays = nullptr;
     XAN_CUDA_CHECK(cudaMallocAsync(&d_ndays, sizeof(int) * nmonths, s));
     XAN_CUDA_CHECK(cudaMemcpyAsync(d_ndays, h_ndays, sizeof(int) * nmonths, cudaMemcpyHostToDevice, s));
+
+    const char *env_nm = getenv("XANTHOS_MRTM_MEMBERS");
+    const int nm_cap = std::max(1, std::min(NM_MAX, env_nm ? atoi(env_nm) : 2));   // members per warp-pass
     int rc = XAN_OK;
-    bool done = false;
-    if (use_tree) {
-        WarpArgs a;
-        a.lane_cell = pl->d_lane_cell;
-        a.lane_gedge = pl->d_lane_gedge;
-        a.lane_oedge = pl->d_lane_oedge;
-        a.lane_src = pl->d_lane_src;
-        a.lane_meta = pl->d_lane_meta;
-        a.edge_prod = pl->d_edge_prod;
-        a.edge_cons = pl->d_edge_cons;
-        a.progress = pl->d_progress;
-        a.runoff = d_runoff;
-        a.flow_dist = d_flow_dist;
-        a.velocity = d_velocity;
-        a.area = d_area;
-        a.chs_prev = d_chs_prev;
-        a.ndays = d_ndays;
-        a.chs = d_chs;
-        a.avg = d_avg;
-        a.instream = d_instream;
-        a.n_warps = pl->n_warps;
-        a.G = pl->G;
-        a.ntmax = ntmax;
-        a.nmonths = nmonths;
-        a.spinup = spinup_months;
-        a.ld = ld;
-        a.dt = dt;
-        {
-            const char *er = getenv("XANTHOS_MRTM_RING"), *es = getenv("XANTHOS_MRTM_SLEEP_NS");
-            a.ring = er ? std::max(1, atoi(er)) : RING_DEFAULT;
-            a.sleep_ns = es ? std::max(0, atoi(es)) : 100;
-        }
-        const int wpb = pl->block_threads / 32;
-        const int blocks = ceil_div(pl->n_warps, wpb);
-        const size_t smem = sizeof(double) * (size_t)wpb * (2 * XW + 2 * (size_t)pl->G * SB * 2);
-        int per_sm = 0;
-        cudaError_t e1 = cudaFuncSetAttribute(mrtm_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaError_t e2 = (e1 == cudaSuccess)
-                             ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mrtm_warp_kernel, pl->block_threads, smem)
-                             : e1;
-        if (e2 != cudaSuccess || per_sm * sms < blocks) {
-            // the cut-edge pipeline needs every warp resident at the same time
-            cudaGetLastError();
-            set_error("mrtm warp kernel: %d blocks of %d threads (%zu B smem) cannot be co-resident (%d per SM x %d SMs)",
-                      blocks, pl->block_threads, smem, per_sm, sms);
-            rc = XAN_E_INVALID;
+    for (int k0 = 0; k0 < n_members && rc == XAN_OK;) {
+        const int nm = std::min(nm_cap, n_members - k0);
+        if (use_tree) {
+            WarpArgs a;
+            memset(&a, 0, sizeof(a));
+            a.lane_cell = pl->d_lane_cell;
+            a.lane_gedge = pl->d_lane_gedge;
+            a.lane_oedge = pl->d_lane_oedge;
+            a.lane_src = pl->d_lane_src;
+            a.lane_meta = pl->d_lane_meta;
+            a.edge_prod = pl->d_edge_prod;
+            a.edge_cons = pl->d_edge_cons;
+            a.progress = pl->d_progress;
+            for (int k = 0; k < nm; ++k) {
+                a.runoff[k] = h_runoff[k0 + k];
+                a.chs_prev[k] = h_chs_prev ? h_chs_prev[k0 + k] : nullptr;
+                a.chs[k] = h_chs ? h_chs[k0 + k] : nullptr;
+                a.avg[k] = h_avg ? h_avg[k0 + k] : nullptr;
+                a.instream[k] = h_instream ? h_instream[k0 + k] : nullptr;
+            }
+            a.flow_dist = d_flow_dist;
+            a.velocity = d_velocity;
+            a.area = d_area;
+            a.ndays = d_ndays;
+            a.n_warps = pl->n_warps;
+            a.G = pl->G;
+            a.ntmax = ntmax;
+            a.nmonths = nmonths;
+            a.spinup = spinup_months;
+            a.ld = ld;
+            a.dt = dt;
+            int r = XAN_OK;
+            if (nm == 1) r = launch_warp<1>(pl, a, ntmax, sms, s);
+            else r = launch_warp<2>(pl, a, ntmax, sms, s);
+            if (r == XAN_E_INVALID && method == XAN_MRTM_AUTO) {
+                use_tree = false;   // does not fit: grid kernel for this and the remaining members
+                continue;
+            }
+            rc = r;
+            k0 += nm;
         } else {
-            double2 *ring = nullptr;
-            const size_t ring_elems = (size_t)std::max(pl->n_edges, 1) * a.ring * ntmax;
-            XAN_CUDA_CHECK(cudaMallocAsync(&ring, sizeof(double2) * ring_elems, s));
-            XAN_CUDA_CHECK(cudaMemsetAsync(pl->d_progress, 0, sizeof(int) * pl->n_warps, s));
-            a.ring_buf = ring;
-            a.dbg = nullptr;
-            if (getenv("XANTHOS_MRTM_DEBUG")) {
-                XAN_CUDA_CHECK(cudaMallocAsync(&a.dbg, sizeof(long long) * 4 * pl->n_warps, s));
-            }
-            void *kargs[] = {(void *)&a};
-            // cooperative launch = all blocks co-resident (no grid.sync is used)
-            XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)mrtm_warp_kernel, dim3(blocks), dim3(pl->block_threads),
-                                                       kargs, smem, s));
-            if (a.dbg) {
-                std::vector<long long> h(4 * (size_t)pl->n_warps);
-                XAN_CUDA_CHECK(cudaMemcpyAsync(h.data(), a.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, s));
-                XAN_CUDA_CHECK(cudaStreamSynchronize(s));
-                FILE *f = fopen(getenv("XANTHOS_MRTM_DEBUG"), "w");
-                if (f) {
-                    for (int w = 0; w < pl->n_warps; ++w) fprintf(f, "%d %lld %lld %lld %lld\n", w, h[4 * w], h[4 * w + 1], h[4 * w + 2], h[4 * w + 3]);
-                    fclose(f);
-                }
-                XAN_CUDA_CHECK(cudaFreeAsync(a.dbg, s));
-            }
-            XAN_CUDA_CHECK(cudaFreeAsync(ring, s));
-            done = true;
-        }
-        if (!done && method == XAN_MRTM_TREE) {
-            cudaFreeAsync(d_ndays, s);
-            return rc;
+            rc = route_grid(pl, h_runoff[k0], d_flow_dist, d_velocity, d_area, h_chs_prev ? h_chs_prev[k0] : nullptr,
+                            d_ndays, nmonths, spinup_months, ld, dt, h_chs ? h_chs[k0] : nullptr,
+                            h_avg ? h_avg[k0] : nullptr, h_instream ? h_instream[k0] : nullptr, sms, s);
+            k0 += 1;
         }
     }
-    if (!done) {
-        GridArgs g;
-        g.gcol = pl->d_gcol;
-        g.runoff = d_runoff;
-        g.flow_dist = d_flow_dist;
-        g.velocity = d_velocity;
-        g.area = d_area;
-        g.chs_prev = d_chs_prev;
-        g.ndays = d_ndays;
-        g.chs = d_chs;
-        g.avg = d_avg;
-        g.instream = d_instream;
-        g.ncell = pl->ncell;
-        g.nmonths = nmonths;
-        g.spinup = spinup_months;
-        g.ld = ld;
-        g.dt = dt;
-        double *work = nullptr;
-        XAN_CUDA_CHECK(cudaMallocAsync(&work, sizeof(double) * 6 * (size_t)pl->ncell, s));
-        g.S = work;
-        g.Favg = work + pl->ncell;
-        g.D = work + 2 * (size_t)pl->ncell;
-        g.X = work + 3 * (size_t)pl->ncell;
-        g.Y = work + 4 * (size_t)pl->ncell;
-        g.Z = work + 5 * (size_t)pl->ncell;
-        int per_sm = 0;
-        XAN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mrtm_grid_kernel, 256, 0));
-        const int blocks = std::max(1, std::min(per_sm * sms, ceil_div(pl->ncell, 256)));
-        void *kargs[] = {(void *)&g};
-        XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)mrtm_grid_kernel, dim3(blocks), dim3(256), kargs, 0, s));
-        XAN_CUDA_CHECK(cudaFreeAsync(work, s));
-        rc = XAN_OK;
-    }
-    XAN_CUDA_CHECK(cudaFreeAsync(d_ndays, s));
+    cudaFreeAsync(d_ndays, s);
     return rc;
+}
+
+int xan_mrtm_route(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_dist, const double *d_velocity,
+                   const double *d_area, const double *d_chs_prev, const int *h_ndays, int nmonths, int spinup_months,
+                   int ld, double dt, int method, double *d_chs, double *d_avg, double *d_instream, void *stream) {
+    XAN_REQUIRE(d_runoff, "xan_mrtm_route: null pointer");
+    return xan_mrtm_route_batch(pl, 1, &d_runoff, d_flow_dist, d_velocity, d_area, &d_chs_prev, h_ndays, nmonths,
+                                spinup_months, ld, dt, method, &d_chs, &d_avg, &d_instream, stream);
 }
 
 }  // extern "C"
