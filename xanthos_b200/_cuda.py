@@ -255,17 +255,25 @@ class HostPool:
         self.free = {}
         self.live_bytes = 0
         self.limit_bytes = limit_bytes
+        self.n_fresh = self.n_reused = self.n_pageable = 0
 
     def acquire(self, shape):
         torch = torch_cuda()
         n = int(np.prod(shape))
         lst = self.free.get(n)
         if lst:
+            self.n_reused += 1
             return lst.pop().view(*shape)
         if self.live_bytes + 8 * n > self.limit_bytes:
+            self.n_pageable += 1
             return torch.empty(shape, dtype=torch.float64)
         self.live_bytes += 8 * n
+        self.n_fresh += 1
         return torch.empty(shape, dtype=torch.float64, pin_memory=True)
+
+    def stats(self):
+        return dict(fresh=self.n_fresh, reused=self.n_reused, pageable=self.n_pageable, live_bytes=self.live_bytes,
+                    free=sum(len(v) for v in self.free.values()))
 
     def as_array(self, t):
         import weakref
