@@ -135,7 +135,7 @@ int xan_mrtm_upstream(const double *h_coords, const int64_t *h_dsid, int ncell, 
 
 /* Execution plan; replaces upstream_genmatrix (mrtm.py:194-230): from h_upid [ncell][9] it
  * builds the rows of UM = UP - I, checks that the flow graph is a forest, cuts large river trees
- * into pieces of at most 32 lanes and packs them into warps.  block_threads (multiple of 32,
+ * into pieces of at most 31 lanes and packs them into warps (lane 31 of every warp stays empty).  block_threads (multiple of 32,
  * <= 256) / chunk_substeps (sub-steps per hand-over between warps) <= 0 pick defaults.  Plan
  * creation is host-side integer work and needs no device; the device tables are uploaded by the
  * first xan_mrtm_route call. */
@@ -170,6 +170,18 @@ int xan_mrtm_route(xan_mrtm_plan *plan, const double *d_runoff, const double *d_
                    const double *d_velocity, const double *d_area, const double *d_chs_prev,
                    const int *h_ndays, int nmonths, int spinup_months, int ld, double dt,
                    int method, double *d_chs, double *d_avg, double *d_instream, void *stream);
+
+/* Ensemble variant of xan_mrtm_route: n_members independent scenarios (same topology, same static
+ * fields, same calendar) in one call.  The h_* arguments are HOST arrays of n_members DEVICE
+ * pointers (h_chs_prev, h_chs, h_avg, h_instream and any of their entries may be NULL).  Members are
+ * advanced two at a time by every warp of the warp-dataflow kernel (independent dependency chains
+ * hide the latency of the sequential sub-step recurrence; XANTHOS_MRTM_MEMBERS=1 disables it).
+ * Results are bit-identical to n_members calls of xan_mrtm_route. */
+int xan_mrtm_route_batch(xan_mrtm_plan *plan, int n_members, const double *const *h_runoff,
+                         const double *d_flow_dist, const double *d_velocity, const double *d_area,
+                         const double *const *h_chs_prev, const int *h_ndays, int nmonths,
+                         int spinup_months, int ld, double dt, int method, double *const *h_chs,
+                         double *const *h_avg, double *const *h_instream, void *stream);
 
 /* ---- device-resident output staging (OutWriter, xanthos/data_writer/out_writer.py:237-265) -- */
 /* sums (or means) every 12 consecutive months: [nmonths][ld] -> [nmonths/12][ld] */

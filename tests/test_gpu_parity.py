@@ -209,6 +209,27 @@ def test_mrtm_cut_trees_match_oracle(kw, lanes, monkeypatch):
     assert bitwise_equal(got[0][:, :3], want[0]) and bitwise_equal(got[1][:, :3], want[1])
 
 
+def test_mrtm_member_batch_is_bitwise_the_single_member_run():
+    """xan_mrtm_route_batch: two and three members per call (two per warp pass) == one call per member."""
+    from xanthos_b200 import synthetic
+    from xanthos_b200.routing import mrtm
+    from xanthos_b200 import _cuda as C
+    from oracle.calendar_utils import set_month_arrays
+    w = synthetic.make_world(40, 80, 1500, 8, seed=5, coast_pull=0.0)
+    s = w.settings()
+    m = 14
+    um = mrtm.upstream_genmatrix(mrtm.upstream(w.coords, mrtm.downstream(w.coords, w.flow_dir, s), s))
+    assert um.info['n_cut_edges'] > 0
+    ndays = set_month_arrays(24, 2003, 2004)[:m, 2]
+    qs = [C.Field.from_host(synthetic.runoff_input(w, m, seed=20 + k)) for k in range(3)]
+    single = [mrtm.route_device(um, q, w.flow_dist, w.velocity, w.area, ndays, 10800, 6) for q in qs]
+    for k in (2, 3):
+        batch = mrtm.route_device_batch(um, qs[:k], w.flow_dist, w.velocity, w.area, ndays, 10800, 6)
+        for (c1, a1, i1), (c2, a2, i2) in zip(single[:k], batch):
+            assert bitwise_equal(c1.to_host(), c2.to_host()) and bitwise_equal(a1.to_host(), a2.to_host())
+            assert bitwise_equal(i1.cpu().numpy(), i2.cpu().numpy())
+
+
 def test_transposes_roundtrip():
     from xanthos_b200 import _cuda as C
     rng = np.random.default_rng(0)

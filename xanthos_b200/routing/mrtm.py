@@ -133,6 +133,34 @@ def route_device(um, runoff, flow_dist, str_velocity, area, ndays, dt, spinup_mo
     return chs, avg, inst
 
 
+def route_device_batch(um, runoffs, flow_dist, str_velocity, area, ndays, dt, spinup_months, method=C.MRTM_AUTO):
+    """
+    Ensemble routing: `runoffs` is a list of Fields (one per member, same shape and leading dimension).
+    Returns a list of (ChStorage Field, Avg_ChFlow Field, instream_flow tensor), bit-identical to one
+    `route_device` call per member; every warp advances two members at a time.
+    """
+    import ctypes
+    torch = C.torch_cuda()
+    qs = [C.as_field(r) for r in runoffs]
+    n, m, ld = qs[0].ncell, qs[0].nmonths, qs[0].ld
+    if any((q.ncell, q.nmonths, q.ld) != (n, m, ld) for q in qs):
+        raise C.ValidationException("route_device_batch: members differ in shape")
+    L, V, A = C.dev_vector(flow_dist), C.dev_vector(str_velocity), C.dev_vector(area)
+    nd, ndp = C.as_c(np.asarray(ndays).reshape(-1)[:m], np.int32)
+    k = len(qs)
+    outs = [(C.Field.empty(n, m, ld), C.Field.empty(n, m, ld), torch.empty(n, dtype=torch.float64, device='cuda'))
+            for _ in range(k)]
+    arr = ctypes.c_void_p * k
+
+    def ptrs(ts):
+        return arr(*[t.data_ptr() for t in ts])
+    C.check(C.lib().xan_mrtm_route_batch(um._plan, k, ptrs([q.t for q in qs]), C.ptr(L), C.ptr(V), C.ptr(A), None, ndp,
+                                         m, int(spinup_months), ld, float(dt), int(method),
+                                         ptrs([o[0].t for o in outs]), ptrs([o[1].t for o in outs]),
+                                         ptrs([o[2] for o in outs]), C.stream_ptr()))
+    return outs
+
+
 def route(um, runoff, flow_dist, str_velocity, area, ndays, dt, spinup_months, chs_prev=None, method=C.MRTM_AUTO):
     """
     The routing loops of Components.calculate_routing (components.py:273-294) in one call.
