@@ -48,10 +48,10 @@ def test_run_model_matches_oracle(tmp_path, pet_kind):
     want = _oracle_pipeline(w, data, sy, ey, 36, 7, pet_kind)
     assert res.Q.shape == (w.ncell, 36)
     for k in ('PET', 'AET', 'Q', 'Sav'):
-        assert max_rel(getattr(res, k), want[k], floor=1e-6) < RTOL, k
+        assert max_rel(getattr(res, k), want[k], floor=1e-6) < RTOL, (k, max_rel(getattr(res, k), want[k], floor=1e-6))
     # routing is bit-exact given identical runoff; here the runoff differs by ~1e-15, so compare to tolerance
     for k in ('ChStorage', 'Avg_ChFlow'):
-        assert max_rel(getattr(res, k), want[k], floor=1e-3) < 1e-8, k
+        assert max_rel(getattr(res, k), want[k], floor=1e-3) < 1e-8, (k, max_rel(getattr(res, k), want[k], floor=1e-3))
     out = os.path.join(str(tmp_path), 'output', 'synthetic')
     q_file = np.load(os.path.join(out, 'q_mmpermonth_synthetic.npy'))
     assert bitwise_equal(q_file, res.Q)
