@@ -183,6 +183,26 @@ int xan_mrtm_route_batch(xan_mrtm_plan *plan, int n_members, const double *const
                          int spinup_months, int ld, double dt, int method, double *const *h_chs,
                          double *const *h_avg, double *const *h_instream, void *stream);
 
+/* ---- step-wise (legacy v1) path: Hargreaves PET + GWAM runoff ------------------------------- */
+/* Replaces hargreaves.calculate_pet (xanthos/pet/hargreaves.py:17-73), which Components.simulation
+ * calls once per month (components.py:329-340), for the whole series in one launch.  d_temp / d_dtr
+ * month-major [nmonths][ld] (NaN -> 0 and negative dtr -> 0 are applied inside, components.py:143-176,
+ * hargreaves.py:32); h_solar_dec / h_dr [nmonths] from calc_sinusoidal_factor
+ * (utils/general.py:53-90); h_days [nmonths] days per month (mod-4 leap rule). */
+int xan_hargreaves_pet(const double *d_temp, const double *d_dtr, const double *d_lat_rad,
+                       const double *h_solar_dec, const double *h_dr, const int *h_days,
+                       double *d_pet, int ncell, int nmonths, int ld, void *stream);
+/* Replaces the month loop around gwam.runoffgen (xanthos/runoff/gwam.py:18-88; components.py:358-366)
+ * including the spin-up pass of ConfigRunner.run (configurations.py:106-113): `spinup_months` months
+ * from d_sm_prev that only carry the soil moisture over, then nmonths months from month 0.
+ * d_sm_max [ncell]: maximum soil moisture, 999 = water body, 0 = no soil.  Outputs month-major
+ * [nmonths][ld] (any may be NULL); d_sm_after_spinup / d_sm_last [ncell] (may be NULL) are the carried
+ * soil moisture after the spin-up pass and after the last month. */
+int xan_gwam_run(const double *d_pet, const double *d_precip, const double *d_sm_max,
+                 const double *d_sm_prev, int ncell, int nmonths, int spinup_months, int ld,
+                 double *d_aet, double *d_q, double *d_sav, double *d_sm_after_spinup,
+                 double *d_sm_last, void *stream);
+
 /* ---- device-resident output staging (OutWriter, xanthos/data_writer/out_writer.py:237-265) -- */
 /* sums (or means) every 12 consecutive months: [nmonths][ld] -> [nmonths/12][ld] */
 int xan_agg_to_year(const double *d_src, double *d_dst, int ncell, int nmonths, int ld,

@@ -35,4 +35,7 @@ def load():
     import xanthos.routing.mrtm as mrtm
     import xanthos.calibrate.calibrate_abcd as cal
     import xanthos.utils.general as general
-    return SimpleNamespace(pm=pm, hs=hs, tw=tw, abcd=abcd, mrtm=mrtm, cal=cal, general=general)
+    import xanthos.pet.hargreaves as hargreaves
+    import xanthos.runoff.gwam as gwam
+    return SimpleNamespace(pm=pm, hs=hs, tw=tw, abcd=abcd, mrtm=mrtm, cal=cal, general=general,
+                           hargreaves=hargreaves, gwam=gwam)

@@ -18,7 +18,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from xanthos_b200 import synthetic  # noqa: E402
-from oracle import ref_loader, pet as opet, abcd as oabcd, mrtm as omrtm, calibrate as ocal  # noqa: E402
+from oracle import ref_loader, pet as opet, abcd as oabcd, mrtm as omrtm, calibrate as ocal, stepwise as osw  # noqa: E402
 from oracle.calendar_utils import set_month_arrays  # noqa: E402
 
 
@@ -160,6 +160,59 @@ def run_oracle(case, fast_upstream=False):
     return out
 
 
+def build_stepwise_case(nrow=24, ncol=48, ncell=300, n_basins=6, start_yr=1999, end_yr=2001, seed=31, spinup=14):
+    """Inputs of the step-wise (Hargreaves + GWAM) parity case."""
+    w = synthetic.make_world(nrow, ncol, ncell, n_basins, seed=seed)
+    m = (end_yr - start_yr + 1) * 12
+    case = dict(ncell=ncell, nmonths=m, start_yr=start_yr, end_yr=end_yr, spinup=spinup, lat=w.lat.copy())
+    case.update(synthetic.stepwise_inputs(w, start_yr, end_yr, seed=seed + 1))
+    return case
+
+
+def run_reference_stepwise(case, ref=None):
+    """Hargreaves + GWAM through the reference's own functions, driven like Components.simulation
+    (components.py:143-186, 329-366) under ConfigRunner.run (configurations.py:106-123)."""
+    import warnings
+    ref = ref or ref_loader.load()
+    n, m = case['ncell'], case['nmonths']
+    ymd = ref.general.set_month_arrays(m, case['start_yr'], case['end_yr'])
+    solar_dec, dr = ref.general.calc_sinusoidal_factor(ymd)
+    lat_rad = np.radians(case['lat'])
+    s = SimpleNamespace(ncell=n)
+    out = dict(solar_dec=solar_dec, dr=dr)
+
+    def pet_month(k):
+        T = np.nan_to_num(case['temp'][:, k])                   # prep_arrays
+        D = np.nan_to_num(case['dtr'][:, k])
+        return ref.hargreaves.calculate_pet(np.nan_to_num(T), np.nan_to_num(D), lat_rad, np.copy(solar_dec[k]),
+                                            np.copy(dr[k]), np.copy(ymd[k, 2]))
+    pet = np.zeros((n, m))
+    for k in range(m):
+        pet[:, k] = pet_month(k)
+    sm = np.copy(case['sm_prev'])
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for k in range(case['spinup']):                         # spin-up pass: only sm_prev survives
+            rg = ref.gwam.runoffgen(pet[:, k], np.copy(case['precip'][:, k]), s, case['soil_moisture'], sm)
+            sm = np.copy(rg[3])
+        out['sm_after_spinup'] = np.copy(sm)
+        aet, q, sav = np.zeros((n, m)), np.zeros((n, m)), np.zeros((n, m))
+        for k in range(m):
+            rg = ref.gwam.runoffgen(pet[:, k], np.copy(case['precip'][:, k]), s, case['soil_moisture'], sm)
+            aet[:, k], q[:, k], sav[:, k] = rg[1], rg[2], rg[3]
+            sm = np.copy(sav[:, k])
+    out.update(pet=pet, aet=aet, q=q, sav=sav)
+    return out
+
+
+def run_oracle_stepwise(case):
+    ymd = set_month_arrays(case['nmonths'], case['start_yr'], case['end_yr'])
+    out = osw.stepwise_run(case['temp'], case['dtr'], case['precip'], np.radians(case['lat']), case['soil_moisture'],
+                           case['sm_prev'], ymd, case['spinup'])
+    out['solar_dec'], out['dr'] = osw.calc_sinusoidal_factor(ymd)
+    return out
+
+
 def oracle_calibration(case, ref_out):
     b = int(ref_out['cal_basin'])
     idx = np.where(case['basin_ids'] == b)[0]
@@ -206,6 +259,13 @@ def main():
         for k, (bit, relerr, same_nan) in res.items():
             ok &= bit
         ok &= rel < 1e-12
+    for kw in (dict(), dict(nrow=36, ncol=72, ncell=900, n_basins=12, seed=7, start_yr=2096, end_yr=2100, spinup=30)):
+        case = build_stepwise_case(**kw)
+        r, o = run_reference_stepwise(case, ref), run_oracle_stepwise(case)
+        for k in sorted(r):
+            bit = np.array_equal(np.asarray(r[k]), np.asarray(o[k]), equal_nan=True)
+            print("  stepwise {:18s} bitwise={}".format(k, bit))
+            ok &= bit
     print("ORACLE PINNED" if ok else "ORACLE MISMATCH")
     return 0 if ok else 1
 

@@ -8,7 +8,8 @@ Each fixture is a compressed .npz holding every input array of a parity case
 (`in_*`) and the outputs of the reference's own functions (`ref_*`):
 run_pmpet, hargreaves_samani.execute, thornthwaite.execute, abcd_execute
 (jobs=1, jobs=-1, no-snow), downstream / upstream / upstream_genmatrix,
-streamrouting driven like Components.calculate_routing, and objective_kge.
+streamrouting driven like Components.calculate_routing, and objective_kge; case_c holds the
+step-wise path (hargreaves.calculate_pet, calc_sinusoidal_factor, gwam.runoffgen with its spin-up pass).
 """
 
 import os
@@ -20,7 +21,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle import ref_loader  # noqa: E402
-from oracle.validate_against_reference import build_case, run_reference  # noqa: E402
+from oracle.validate_against_reference import (build_case, run_reference, build_stepwise_case,  # noqa: E402
+                                               run_reference_stepwise)
 
 CASES = {
     # 3 years around the leap year 2000, spin-up = whole period
@@ -42,6 +44,14 @@ def main():
         path = os.path.join(HERE, name + '.npz')
         np.savez_compressed(path, **blob)
         print(name, '->', path, '{:.2f} MB'.format(os.path.getsize(path) / 1e6))
+    # step-wise (v1) path: Hargreaves PET + GWAM runoff with its spin-up pass; 2003-2005 (leap year 2004)
+    case = build_stepwise_case(nrow=24, ncol=48, ncell=300, n_basins=6, start_yr=2003, end_yr=2005, seed=31, spinup=14)
+    out = run_reference_stepwise(case, ref)
+    blob = {'in_' + k: np.asarray(v) for k, v in case.items()}
+    blob.update({'ref_' + k: np.asarray(v) for k, v in out.items()})
+    path = os.path.join(HERE, 'case_c.npz')
+    np.savez_compressed(path, **blob)
+    print('case_c', '->', path, '{:.2f} MB'.format(os.path.getsize(path) / 1e6))
 
 
 if __name__ == '__main__':

@@ -230,6 +230,46 @@ def test_mrtm_member_batch_is_bitwise_the_single_member_run():
             assert bitwise_equal(i1.cpu().numpy(), i2.cpu().numpy())
 
 
+def test_hargreaves_pet_matches_golden():
+    """Series launch and the reference's per-month signature (hargreaves.py:17-39) against case_c."""
+    from xanthos_b200.pet import hargreaves as hg
+    from xanthos_b200.utils.general import set_month_arrays
+    case, ref = load_golden('case_c')
+    ymd = set_month_arrays(case['nmonths'], case['start_yr'], case['end_yr'])
+    lat = np.radians(case['lat'])
+    pet = hg.series_device(case['temp'], case['dtr'], lat, ref['solar_dec'], ref['dr'], ymd[:, 2]).to_host()
+    assert max_rel(pet, ref['pet'], floor=1e-6) < RTOL
+    assert np.array_equal(pet == 0, ref['pet'] == 0)                # clipped months and NaN -> 0 inputs agree exactly
+    k = 7
+    dtr = np.nan_to_num(case['dtr'][:, k])
+    one = hg.calculate_pet(np.nan_to_num(case['temp'][:, k]), dtr, lat, ref['solar_dec'][k], ref['dr'][k], ymd[k, 2])
+    assert one.shape == (case['ncell'],) and max_rel(one, ref['pet'][:, k], floor=1e-6) < RTOL
+    assert (dtr >= 0).all()                                         # mutated in place like the reference (:32)
+
+
+def test_gwam_matches_golden():
+    """Fused spin-up + simulation, the two-call form Components uses, and the per-month signature (gwam.py:18-88)."""
+    from types import SimpleNamespace
+    from xanthos_b200.runoff import gwam
+    case, ref = load_golden('case_c')
+    n, m, spin = case['ncell'], case['nmonths'], int(case['spinup'])
+    res = gwam.run_device(ref['pet'], case['precip'], case['soil_moisture'], case['sm_prev'], m, spin)
+    for k in ('aet', 'q', 'sav'):
+        got = res[k].to_host()
+        assert max_rel(got, ref[k], floor=1e-6) < RTOL, k
+        assert np.array_equal(got == 0, ref[k] == 0), k             # branch decisions (lakes, no soil, NaN forcing)
+    assert max_rel(res['sm_after_spinup'].cpu().numpy(), ref['sm_after_spinup'], floor=1e-6) < RTOL
+    a = gwam.run_device(ref['pet'], case['precip'], case['soil_moisture'], case['sm_prev'], spin, 0, want=())
+    b = gwam.run_device(ref['pet'], case['precip'], case['soil_moisture'], a['sm_last'].cpu().numpy(), m, 0)
+    for k in ('aet', 'q', 'sav'):
+        assert bitwise_equal(b[k].to_host(), res[k].to_host()), k
+    rg = gwam.runoffgen(ref['pet'][:, 0], case['precip'][:, 0], SimpleNamespace(ncell=n), case['soil_moisture'],
+                        ref['sm_after_spinup'])
+    assert rg[0] is not None and len(rg) == 4
+    for got, k in zip(rg[1:], ('aet', 'q', 'sav')):
+        assert max_rel(got, ref[k][:, 0], floor=1e-6) < RTOL, k
+
+
 def test_transposes_roundtrip():
     from xanthos_b200 import _cuda as C
     rng = np.random.default_rng(0)

@@ -149,6 +149,32 @@ def test_set_month_arrays_mod4_rule():
     assert a[25, 2] == 29        # February 2100 is a leap month under the mod-4 rule
 
 
+def test_sinusoidal_factor_bitwise():
+    """utils/general.py::calc_sinusoidal_factor (host logic of the Hargreaves PET) against the reference's output."""
+    from xanthos_b200.utils.general import calc_sinusoidal_factor, set_month_arrays
+    case, ref = load_golden('case_c')
+    sd, dr = calc_sinusoidal_factor(set_month_arrays(case['nmonths'], case['start_yr'], case['end_yr']))
+    assert np.array_equal(sd, ref['solar_dec']) and np.array_equal(dr, ref['dr'])
+
+
+def test_stepwise_project_config(tmp_path):
+    """hargreaves + gwam + mrtm project (the configuration of xanthos/test/test_hargreaves_gwam_mrtm.py) from disk."""
+    from xanthos_b200 import synthetic
+    from xanthos_b200.data_reader.ini_reader import ConfigReader
+    from xanthos_b200.data_reader.data_load import DataLoader
+    from xanthos_b200.configurations import ConfigRunner
+    w = synthetic.make_world(24, 48, 320, 6, seed=21)
+    ini, data = synthetic.write_example(str(tmp_path), w, 2003, 2005, pet='hargreaves', routing_spinup=7, runoff_spinup=14)
+    c = ConfigReader(ini)
+    assert (c.pet_module, c.runoff_module, c.routing_module, c.runoff_spinup) == ('hargreaves', 'gwam', 'mrtm', 14)
+    d = DataLoader(c)
+    assert np.array_equal(d.soil_moisture, data['soil_moisture']) and np.array_equal(d.sm_prev, 0.5 * data['soil_moisture'])
+    assert np.array_equal(d.precip, data['precip'], equal_nan=True)
+    assert (d.dtr[~np.isnan(d.dtr)] >= 0).all()                     # neg_to_zero (data_load.py:83-84)
+    r = ConfigRunner(c)
+    assert r.spinup and r.pet_timestep == 36 and r.runoff_timestep == 36 and r.routing_timestep == 0
+
+
 def test_sharding_partitions():
     from xanthos_b200 import sharding, synthetic
     from xanthos_b200.routing import mrtm

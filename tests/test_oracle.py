@@ -10,7 +10,8 @@ import pytest
 
 from oracle import pet as opet, mrtm as omrtm, abcd as oabcd
 from oracle import ref_loader
-from oracle.validate_against_reference import run_oracle, oracle_calibration, build_case, run_reference, compare
+from oracle.validate_against_reference import (run_oracle, oracle_calibration, build_case, run_reference, compare,
+                                               run_oracle_stepwise, build_stepwise_case, run_reference_stepwise)
 from util import load_golden, bitwise_equal
 
 
@@ -22,6 +23,15 @@ def test_oracle_matches_golden_bitwise(name):
         assert bitwise_equal(v, ref[k]), k
     ed = oracle_calibration(case, ref)
     assert np.max(np.abs(ed - ref['cal_ed']) / np.abs(ref['cal_ed'])) < 1e-12
+
+
+def test_stepwise_oracle_matches_golden_bitwise():
+    """Hargreaves PET + GWAM runoff with its spin-up pass (tests/golden/case_c.npz, produced by the reference)."""
+    case, ref = load_golden("case_c")
+    out = run_oracle_stepwise(case)
+    assert set(out) == set(ref)
+    for k, v in out.items():
+        assert bitwise_equal(v, ref[k]), k
 
 
 def test_upstream_fast_equals_loop():
@@ -62,3 +72,7 @@ def test_oracle_matches_live_reference():
     o = run_oracle(case)
     for k, (bit, rel, same_nan) in compare(r, o, verbose=False).items():
         assert bit, (k, rel)
+    sc = build_stepwise_case(nrow=20, ncol=40, ncell=180, n_basins=5, seed=78, start_yr=2003, end_yr=2004, spinup=9)
+    r, o = run_reference_stepwise(sc), run_oracle_stepwise(sc)
+    for k in r:
+        assert bitwise_equal(r[k], o[k]), k

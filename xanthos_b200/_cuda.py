@@ -66,6 +66,9 @@ SIGNATURES = {
                                _P, _P, _P, _P]),
     'xan_mrtm_route_batch': (c_int, [_P, c_int, POINTER(_P), _P, _P, _P, POINTER(_P), POINTER(c_int), c_int, c_int,
                                      c_int, c_double, c_int, POINTER(_P), POINTER(_P), POINTER(_P), _P]),
+    'xan_hargreaves_pet': (c_int, [_P, _P, _P, POINTER(c_double), POINTER(c_double), POINTER(c_int), _P, c_int, c_int,
+                                   c_int, _P]),
+    'xan_gwam_run': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     'xan_agg_to_year': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     'xan_basin_sum': (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
 }
@@ -76,7 +79,7 @@ _lib = None
 KERNELS_PER_CALL = {
     'xan_to_month_major': 1, 'xan_to_cell_major': 1, 'xan_hs_pet': 2, 'xan_thornthwaite_pet': 2,
     'xan_thornthwaite_daylight': 1, 'xan_pm_pet': 1, 'xan_abcd_run': 3, 'xan_abcd_kge_batch': 1,
-    'xan_mrtm_route': 1, 'xan_mrtm_route_batch': 1, 'xan_agg_to_year': 1, 'xan_basin_sum': 1,
+    'xan_mrtm_route': 1, 'xan_mrtm_route_batch': 1, 'xan_hargreaves_pet': 1, 'xan_gwam_run': 1, 'xan_agg_to_year': 1, 'xan_basin_sum': 1,
 }
 launch_count = 0
 

@@ -38,6 +38,16 @@ class Components:
         self.data = DataLoader(config)
         self.yr_imth_dys = helper.set_month_arrays(self.s.nmonths, self.s.StartYear, self.s.EndYear)
 
+        if self.s.pet_module == 'hargreaves':                      # components.py:57-63
+            self.pet_out = None
+            self.solar_dec, self.dr = helper.calc_sinusoidal_factor(self.yr_imth_dys)
+        if self.s.runoff_module == 'gwam':                         # components.py:75-77
+            self.soil_moisture = self.data.soil_moisture
+            self.sm_prev = self.data.sm_prev
+        self.P = self.T = self.D = None
+        self.mth_solar_dec = self.mth_dr = self.mth_days = None
+        self.pet_t = None
+
         if self.s.routing_module == 'mrtm':
             self.flow_dist = None
             self.flow_dir = None
@@ -62,20 +72,47 @@ class Components:
     def import_core(self):
         """Bind the PET / runoff / routing plug-in modules (components.py:114-142)."""
         global pet_mod, runoff_mod, routing_mod
-        if self.s.pet_module == 'hs':
+        if self.s.pet_module == 'hargreaves':
+            from .pet import hargreaves as pet_mod
+        elif self.s.pet_module == 'hs':
             from .pet import hargreaves_samani as pet_mod
         elif self.s.pet_module == 'pm':
             from .pet import penman_monteith as pet_mod
         elif self.s.pet_module == 'thornthwaite':
             from .pet import thornthwaite as pet_mod
-        if self.s.runoff_module == 'abcd':
+        if self.s.runoff_module == 'gwam':
+            from .runoff import gwam as runoff_mod
+        elif self.s.runoff_module == 'abcd':
             from .runoff import abcd as runoff_mod
         if self.s.routing_module == 'mrtm':
             from .routing import mrtm as routing_mod
 
+    def prep_arrays(self, nm=None):
+        """Climate arrays of one month, or of all months (components.py:143-157)."""
+        if nm is None:
+            self.P = np.copy(self.data.precip)                      # keep nan in P
+            self.T = np.nan_to_num(self.data.temp)
+            self.D = np.nan_to_num(self.data.dtr)
+        else:
+            self.P = np.copy(self.data.precip[:, nm])
+            self.T = np.nan_to_num(self.data.temp[:, nm])
+            self.D = np.nan_to_num(self.data.dtr[:, nm])
+
+    def prep_pet(self, nm):
+        """Per-month scalars and arrays of the Hargreaves PET (components.py:159-186)."""
+        if self.s.pet_module == 'hargreaves':
+            self.mth_solar_dec = np.copy(self.solar_dec[nm])
+            self.mth_dr = np.copy(self.dr[nm])
+            self.mth_days = np.copy(self.yr_imth_dys[nm, 2])
+            self.mth_temp_pet = np.nan_to_num(self.T)
+            self.mth_dtr_pet = np.nan_to_num(self.D)
+
     def calculate_pet(self):
         """Monthly potential evapotranspiration (components.py:189-210)."""
-        if self.s.pet_module == 'hs':
+        if self.s.pet_module == 'hargreaves':
+            return pet_mod.calculate_pet(self.mth_temp_pet, self.mth_dtr_pet, self.data.lat_radians,
+                                         self.mth_solar_dec, self.mth_dr, self.mth_days)
+        elif self.s.pet_module == 'hs':
             return pet_mod.execute(self.s, self.data)
         elif self.s.pet_module == 'pm':
             return pet_mod.run_pmpet(self.data, self.s.ncell, self.s.pm_nlcs, self.s.StartYear, self.s.EndYear,
@@ -86,8 +123,11 @@ class Components:
             return self.data.pet_out
 
     def calculate_runoff(self, step_num=None, pet=None):
-        """Runoff (components.py:212-247); ABCD iterates internally."""
-        if self.s.runoff_module == 'abcd':
+        """Runoff (components.py:212-247); ABCD iterates internally, GWAM is one month per call."""
+        if self.s.runoff_module == 'gwam':
+            rg = runoff_mod.runoffgen(self.pet_t, self.P, self.s, self.soil_moisture, self.sm_prev)
+            self.PET[:, step_num], self.AET[:, step_num], self.Q[:, step_num], self.Sav[:, step_num] = rg
+        elif self.s.runoff_module == 'abcd':
             rg = runoff_mod.abcd_execute(n_basins=self.s.n_basins, basin_ids=self.data.basin_ids,
                                          pet=pet, precip=self.data.precip, tmin=self.data.tmin,
                                          calib_file=self.s.calib_file, n_months=self.s.nmonths,
@@ -132,8 +172,54 @@ class Components:
         logging.info("---{} in progress...".format(notify))
         t0 = time.time()
         with C.async_host():      # D2H of each stage's results overlaps the next stage; complete on exit
-            self._simulation(run_pet, run_runoff, run_routing)
+            if pet_num_steps > 0 or runoff_num_steps > 0:
+                self._simulation_stepwise(run_pet, run_runoff, run_routing, pet_num_steps, runoff_num_steps, notify)
+            else:
+                self._simulation(run_pet, run_runoff, run_routing)
         logging.info("---{0} has finished successfully: {1} seconds ---".format(notify, time.time() - t0))
+
+    def _simulation_stepwise(self, run_pet, run_runoff, run_routing, pet_num_steps, runoff_num_steps, notify):
+        """
+        The month loops of the reference (components.py:329-340 Hargreaves, :358-366 GWAM) as two launches:
+        PET of every month is independent, and GWAM's soil moisture feedback (sm_prev) stays in registers.
+        In the 'Spin Up' pass of ConfigRunner (configurations.py:106-113) the reference also fills the first
+        months of PET/AET/Q/Sav and routes them; every one of those values is overwritten by the simulation
+        pass, only `sm_prev` survives - so only `sm_prev` is produced here.
+        """
+        spin_pass = notify == 'Spin Up'
+        pet_f = None
+        if run_pet and self.s.pet_module == 'hargreaves':
+            logging.info("\tProcessing PET...")
+            t = time.time()
+            if getattr(self, '_pet_series', None) is None:
+                self._pet_series = pet_mod.series_device(self.data.temp, self.data.dtr, self.data.lat_radians,
+                                                         self.solar_dec, self.dr, self.yr_imth_dys[:, 2])
+            pet_f = self._pet_series
+            logging.info("\tPET processed in {} seconds---".format(time.time() - t))
+        elif run_pet or self.s.pet_module == 'none':
+            pet_f = C.as_field(self.calculate_pet())
+
+        if run_runoff and self.s.runoff_module == 'gwam':
+            logging.info("\tProcessing Runoff...")
+            t = time.time()
+            res = runoff_mod.run_device(pet_f, self.data.precip, self.soil_moisture, self.sm_prev,
+                                        n_months=runoff_num_steps, spinup_months=0,
+                                        want=() if spin_pass else ('aet', 'q', 'sav'))
+            self.sm_prev = res['sm_last'].cpu().numpy()             # components.py:366
+            if not spin_pass:
+                self.PET = C.remember(pet_f.to_host(), pet_f)
+                self.AET = C.remember(res['aet'].to_host(), res['aet'])
+                self.Q = C.remember(res['q'].to_host(), res['q'])
+                self.Sav = C.remember(res['sav'].to_host(), res['sav'])
+            logging.info("\tRunoff processed in {} seconds---".format(time.time() - t))
+        elif run_runoff:
+            self.calculate_runoff(pet=C.remember(pet_f.to_host(), pet_f))
+
+        if run_routing and not spin_pass:
+            logging.info("\tProcessing Routing...")
+            t = time.time()
+            self.calculate_routing(self.Q)
+            logging.info("\tRouting processed in {} seconds---".format(time.time() - t))
 
     def _simulation(self, run_pet, run_runoff, run_routing):
         if run_runoff and self.s.runoff_module == 'abcd':

@@ -63,6 +63,10 @@ class DataLoader:
         elif s.pet_module == 'thornthwaite':
             self.tair = self.load_to_array(s.trn_tas, 'trn_tas', nan_to_num=True, warn_nan=True)
 
+        elif s.pet_module == 'hargreaves':                         # data_load.py:77-84
+            self.temp = self.load_to_array(s.TemperatureFile, var_name=s.TempVarName)
+            self.dtr = self.load_to_array(s.DailyTemperatureRangeFile, var_name=s.DTRVarName, neg_to_zero=True)
+
         elif s.pet_module == 'none' and getattr(s, 'pet_file', None) is not None:
             self.pet_out = self.load_to_array(s.pet_file)
 
@@ -77,6 +81,21 @@ class DataLoader:
                 self.tmin = self.load_to_array(s.TempMinFile, var_name=s.TempMinVarName, nan_to_num=True,
                                                warn_nan=True)
 
+        elif s.runoff_module == 'gwam':                            # data_load.py:147-182
+            self.precip = self.load_to_array(s.PrecipitationFile, var_name=s.PrecipVarName)
+            self.max_soil_moist = self._vector(s.max_soil_moisture, 1)
+            self.lakes_msm = self._pairs(s.lakes_msm)
+            self.addit_water_msm = self._pairs(s.addit_water_msm)
+            sm = np.array(self.max_soil_moist, dtype=float)
+            sm[self.lakes_msm[:, 0]] = self.lakes_msm[:, 1]          # water bodies: 999 (load_soil_moisture :241-252)
+            sm[self.addit_water_msm[:, 0]] = self.addit_water_msm[:, 1]
+            self.grid_area = np.copy(self.area)
+            self.soil_moisture = sm
+            if str(s.HistFlag).lower() == "true":
+                self.sm_prev = 0.5 * self.soil_moisture
+            else:
+                self.sm_prev = self.load_data(s.SavFile, 0, s.SavVarName)[:, -1]
+
         # ---- routing (data_load.py:200-211) ---------------------------------------------------------------
         if s.routing_module == 'mrtm':
             self.flow_dist = self.load_routing_data(s.flow_distance, rep_val=1000)
@@ -89,6 +108,16 @@ class DataLoader:
             self.cal_obs = self.load_data(s.cal_observed, 0)[:, [0, 3]]
 
     # ---------------------------------------------------------------------------------------------
+    def _vector(self, f, header_num=0):
+        return np.asarray(f, dtype=float).reshape(-1) if isinstance(f, np.ndarray) else self.load_data(f, header_num)
+
+    def _pairs(self, f):
+        """[k, 2] (1-based cell number, value) tables of water bodies -> 0-based int rows (data_load.py:154-160)."""
+        a = np.asarray(f) if isinstance(f, np.ndarray) else self.load_data(f)
+        a = np.atleast_2d(a).astype(int).reshape(-1, 2)
+        a[:, 0] -= 1
+        return a
+
     @staticmethod
     def _optional(s, attr, fn):
         f = getattr(s, attr, None)

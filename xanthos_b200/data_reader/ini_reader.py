@@ -189,9 +189,23 @@ class ConfigReader:
                     "USAGE: Must provide a pet_file variable in the PET config section that "
                     "contains the full path to an input PET file if not using an existing module.")
 
-        elif self.pet_module == 'hargreaves':
-            raise ValidationException("PET module 'hargreaves' is not part of the B200 hot path "
-                                      "(hs, pm and thornthwaite are); see DESIGN.md.")
+        elif self.pet_module == 'hargreaves':                      # ini_reader.py:216-243
+            m = pet_config['hargreaves']
+            self.pet_dir = os.path.join(self.PET, m['pet_dir'])
+            try:
+                self.TemperatureFile = os.path.join(self.pet_dir, m['TemperatureFile'])
+            except KeyError:
+                logging.exception("File path not provided for the TemperatureFile "
+                                  "variable in the PET section of the config file.")
+                raise
+            self.TempVarName = m.get('TempVarName')
+            try:
+                self.DailyTemperatureRangeFile = os.path.join(self.pet_dir, m['DailyTemperatureRangeFile'])
+            except KeyError:
+                logging.exception("File path not provided for the DailyTemperatureRangeFile "
+                                  "variable in the PET section of the config file.")
+                raise
+            self.DTRVarName = m.get('DTRVarName')
         else:
             raise ValidationException("ERROR: PET module '{0}' not found. Please check "
                                       "spelling and try again.".format(self.pet_module))
@@ -221,8 +235,33 @@ class ConfigReader:
 
         elif self.runoff_module == 'none':
             pass
-        elif self.runoff_module == 'gwam':
-            raise ValidationException("Runoff module 'gwam' is not part of the B200 hot path (abcd is); see DESIGN.md.")
+        elif self.runoff_module == 'gwam':                         # ini_reader.py:311-345
+            m = runoff_config['gwam']
+            self.ro_model_dir = os.path.join(self.RunoffDir, m['runoff_dir'])
+            self.runoff_spinup = int(m['runoff_spinup'])
+            self.max_soil_moisture = os.path.join(self.ro_model_dir, m['max_soil_moisture'])
+            self.lakes_msm = os.path.join(self.ro_model_dir, m['lakes_msm'])
+            self.addit_water_msm = os.path.join(self.ro_model_dir, m['addit_water_msm'])
+            self.ChStorageFile = None
+            self.ChStorageVarName = None
+            self.SavFile = None
+            self.SavVarName = None
+            if str(self.HistFlag) == 'False':
+                try:
+                    self.ChStorageFile = m['ChStorageFile']
+                    self.ChStorageVarName = m['ChStorageVarName']
+                    self.SavFile = m['SavFile']
+                    self.SavVarName = m['SavVarName']
+                except KeyError:
+                    raise ValidationException("Error: ChStorageFile and ChStorageVarName "
+                                              "are not defined for Future Mode.")
+            try:
+                self.PrecipitationFile = os.path.join(self.ro_model_dir, m['PrecipitationFile'])
+            except KeyError:
+                logging.exception("File path not provided for the PrecipitationFile variable "
+                                  "in the GWAM runoff section of the config file.")
+                raise
+            self.PrecipVarName = m.get('PrecipVarName')
         else:
             raise ValidationException("ERROR: Runoff module '{0}' not found. Please check "
                                       "spelling and try again.".format(self.runoff_module))

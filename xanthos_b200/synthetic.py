@@ -343,6 +343,29 @@ def thornthwaite_inputs(world, start_yr, end_yr, seed=5):
     return dict(tair=tas)
 
 
+def stepwise_inputs(world, start_yr, end_yr, seed=6):
+    """
+    Inputs of the step-wise (v1) path, Hargreaves PET + GWAM runoff: temp, dtr (with negatives and NaN),
+    precip (NaN kept), maximum soil moisture (with 999 = water bodies, 0 = no soil) and the historic-mode
+    initial soil moisture 0.5 * max (data_load.py:77-84, 147-182).
+    """
+    rng = np.random.default_rng(seed + 3000)
+    n = world.ncell
+    m = (end_yr - start_yr + 1) * 12
+    temp = _seasonal_temperature(rng, world, m)
+    dtr = rng.uniform(-1.0, 16.0, (n, m))
+    k = max(1, (n * m) // 2000)
+    temp.ravel()[rng.choice(n * m, size=k, replace=False)] = np.nan
+    dtr.ravel()[rng.choice(n * m, size=k, replace=False)] = np.nan
+    precip = np.abs(rng.normal(70.0, 60.0, (n, m)))
+    precip.ravel()[rng.choice(n * m, size=k, replace=False)] = np.nan
+    precip[rng.choice(n, size=max(1, n // 300), replace=False), :] = np.nan      # a cell without data
+    sm_max = rng.uniform(15.0, 450.0, n)
+    sm_max[rng.choice(n, size=max(2, n // 60), replace=False)] = 999.0           # lakes (data_load.py:154-160)
+    sm_max[rng.choice(n, size=max(1, n // 150), replace=False)] = 0.0
+    return dict(temp=temp, dtr=dtr, precip=precip, soil_moisture=sm_max, sm_prev=0.5 * sm_max)
+
+
 def abcd_inputs(world, nmonths, seed=1, with_pet=True):
     """Precipitation (with ~0.1 % NaN), tmin, optional PET and [n_basins, 5] parameters."""
     rng = np.random.default_rng(seed + 1000)
@@ -444,16 +467,44 @@ def write_example(root, world, start_yr, end_yr, pet='pm', routing=True, seed=1,
         data['trn_tas'] = tw['tair']
         np.save(os.path.join(pdir, 'tas.npy'), tw['tair'])
         lines += ['[[thornthwaite]]', 'pet_dir = thornthwaite', 'trn_tas = tas.npy']
+    elif pet == 'hargreaves':
+        # the step-wise v1 configuration of the reference's own integration test
+        # (xanthos/test/configs/hargreaves_gwam_mrtm.ini): Hargreaves PET + GWAM runoff (+ MRTM)
+        sw = stepwise_inputs(world, start_yr, end_yr, seed=seed)
+        data.update(sw)
+        np.save(os.path.join(pdir, 'tas.npy'), sw['temp'])
+        np.save(os.path.join(pdir, 'dtr.npy'), sw['dtr'])
+        lines += ['[[hargreaves]]', 'pet_dir = hargreaves', 'TemperatureFile = tas.npy',
+                  'DailyTemperatureRangeFile = dtr.npy']
+        gdir = os.path.join(dirs['runoff'], 'gwam')
+        os.makedirs(gdir, exist_ok=True)
+        lakes = np.nonzero(sw['soil_moisture'] == 999.0)[0]
+        base = np.where(sw['soil_moisture'] == 999.0, 123.0, sw['soil_moisture'])     # lakes come from the two tables
+        with open(os.path.join(gdir, 'max_soil_moisture.csv'), 'w') as f:
+            f.write('max_soil_moisture\n')
+            np.savetxt(f, base, fmt='%.17g')
+        half = len(lakes) // 2
+        np.savetxt(os.path.join(gdir, 'lakes.csv'), np.c_[lakes[:half] + 1, np.full(half, 999)], delimiter=',', fmt='%d')
+        np.savetxt(os.path.join(gdir, 'addit_water.csv'), np.c_[lakes[half:] + 1, np.full(len(lakes) - half, 999)],
+                   delimiter=',', fmt='%d')
+        np.save(os.path.join(gdir, 'precip.npy'), sw['precip'])
+        lines += ['[Runoff]', 'runoff_module = gwam', '[[gwam]]', 'runoff_dir = gwam',
+                  'runoff_spinup = {}'.format(m if runoff_spinup is None else runoff_spinup),
+                  'max_soil_moisture = max_soil_moisture.csv', 'lakes_msm = lakes.csv',
+                  'addit_water_msm = addit_water.csv', 'PrecipitationFile = precip.npy']
 
     ab = abcd_inputs(world, m, seed=seed, with_pet=False)
-    data.update(precip=ab['precip'], tmin=ab['tmin'], abcd_pars=ab['pars'])
+    if pet != 'hargreaves':
+        data.update(precip=ab['precip'], tmin=ab['tmin'], abcd_pars=ab['pars'])
     rdir = os.path.join(dirs['runoff'], 'abcd')
     np.save(os.path.join(rdir, 'pars.npy'), ab['pars'])
     np.save(os.path.join(rdir, 'precip.npy'), ab['precip'])
     np.save(os.path.join(rdir, 'tmin.npy'), ab['tmin'])
-    lines += ['[Runoff]', 'runoff_module = abcd', '[[abcd]]', 'runoff_dir = abcd', 'calib_file = pars.npy',
-              'runoff_spinup = {}'.format(m if runoff_spinup is None else runoff_spinup), 'jobs = -1',
-              'PrecipitationFile = ' + os.path.join(rdir, 'precip.npy'), 'TempMinFile = ' + os.path.join(rdir, 'tmin.npy')]
+    if pet != 'hargreaves':
+        lines += ['[Runoff]', 'runoff_module = abcd', '[[abcd]]', 'runoff_dir = abcd', 'calib_file = pars.npy',
+                  'runoff_spinup = {}'.format(m if runoff_spinup is None else runoff_spinup), 'jobs = -1',
+                  'PrecipitationFile = ' + os.path.join(rdir, 'precip.npy'),
+                  'TempMinFile = ' + os.path.join(rdir, 'tmin.npy')]
     if routing:
         mdir = os.path.join(dirs['routing'], 'mrtm')
         np.save(os.path.join(mdir, 'velocity.npy'), world.velocity)

@@ -24,3 +24,31 @@ def set_month_arrays(n_months, start_year, end_year):
             out[k] = (y, j, days[j])
             k += 1
     return out
+
+
+def calc_sinusoidal_factor(yr_imth_ndays, startmonth=1):
+    """
+    Monthly means of the solar declination (radians) and of the inverse relative Earth-Sun distance
+    (general.py:53-90): daily values 0.409 sin(2 pi j / N - 1.39 + ph) and 1 + 0.033 cos(2 pi j / N + ph)
+    averaged over the days of the month, N = 365 or 366 by the `year % 4` rule.  Host-side: 2 x nmonths
+    scalars that parameterise the Hargreaves kernel.  Returns (solar_dec, dr).
+    """
+    ymd = np.asarray(yr_imth_ndays)
+    n = ymd.shape[0]
+    solar_dec, dr = np.zeros(n), np.zeros(n)
+    ph = (startmonth - 1.) / 12. * 2. * np.pi
+    cache = {}
+    for i in range(n):
+        leap = int(ymd[i, 0]) % 4 == 0
+        if leap not in cache:
+            mdays = _M2 if leap else _M1
+            ends = np.cumsum(mdays)
+            j = np.arange(1, ends[-1] + 1)
+            cache[leap] = (ends - np.asarray(mdays), ends,
+                           0.409 * np.sin(2 * np.pi * j / max(j) - 1.39 + ph),
+                           1. + 0.033 * np.cos(2 * np.pi * j / max(j) + ph))
+        beg, end, lam, d = cache[leap]
+        mth = int(ymd[i, 1])
+        solar_dec[i] = np.mean(lam[beg[mth]:end[mth]])
+        dr[i] = np.mean(d[beg[mth]:end[mth]])
+    return solar_dec, dr
