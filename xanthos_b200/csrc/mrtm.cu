@@ -554,17 +554,22 @@ __device__ __forceinline__ void run_block(LaneState<NM> &L, const double2 *gsl, 
                                           int &n_redo) {
     const unsigned full = 0xffffffffu;
     const RowSrc<NT> row = decode_row<NT>(L.src);
-    const int ghost_i = is_ghost ? 1 : 0, out_i = lane_out ? 1 : 0;
-    const long long gmask = -(long long)ghost_i;
-    double gF[NM], gFp[NM];   // stay 0.0 on lanes that are not ghosts
-    double d[NM];
+    const int out_i = lane_out ? 1 : 0;
+    const long long gmask = -(long long)(is_ghost ? 1 : 0);
+    // Every lane reads a staged series without predication: ghost lanes their cut edge, all other lanes the
+    // warp's all-zero slot (one broadcast wavefront).  (F, F') == (0, 0) never reports a change, so the values
+    // need no per-lane guard and are plain SSA values from one iteration to the next (no in-out registers).
+    double gFp[NM], d[NM];
+    bool gchg[NM];
 #pragma unroll
     for (int mm = 0; mm < NM; ++mm) {
-        gF[mm] = 0.0;
         gFp[mm] = 0.0;
+        gchg[mm] = false;
         if (GHOST) {
-            lds_v2_pred(gF[mm], gFp[mm], gsl + mm, ghost_i);
-            L.F[mm] = bit_select(gF[mm], L.F[mm], gmask);
+            const double2 g0 = gsl[mm];
+            L.F[mm] = bit_select(g0.x, L.F[mm], gmask);
+            gFp[mm] = g0.y;
+            gchg[mm] = __double_as_longlong(g0.x) != __double_as_longlong(g0.y);
         }
         d[mm] = um_row<NT>(L.F[mm], row) + L.erl[mm];                            // mrtm.py:51
     }
@@ -577,16 +582,20 @@ __device__ __forceinline__ void run_block(LaneState<NM> &L, const double2 *gsl, 
         bool changed = false;
 #pragma unroll
         for (int mm = 0; mm < NM; ++mm) {
-            nF[mm] = gF[mm];
-            nFp[mm] = gFp[mm];
-            if (GHOST) lds_v2_pred(nF[mm], nFp[mm], gnext + mm, ghost_i);       // ghost flows of sub-step t + 1
+            nF[mm] = 0.0;
+            nFp[mm] = 0.0;
+            if (GHOST) {                                                         // ghost flows of sub-step t + 1
+                const double2 g1 = gnext[mm];
+                nF[mm] = g1.x;
+                nFp[mm] = g1.y;
+            }
         }
 #pragma unroll
         for (int mm = 0; mm < NM; ++mm) {
             const double ddt = d[mm] * dt;
             clamp[mm] = ddt < (-L.S[mm]);                                        // mrtm.py:54
             changed = changed || clamp[mm];
-            if (GHOST) changed = changed || (__double_as_longlong(gF[mm]) != __double_as_longlong(gFp[mm]));
+            if (GHOST) changed = changed || gchg[mm];
             Sn[mm] = L.S[mm] + ddt;                                              // mrtm.py:76
             Fn[mm] = Sn[mm] * L.tauinv;                                          // mrtm.py:50 of sub-step t + 1
             if (GHOST) Fn[mm] = bit_select(nF[mm], Fn[mm], gmask);
@@ -619,8 +628,10 @@ __device__ __forceinline__ void run_block(LaneState<NM> &L, const double2 *gsl, 
             lastFp[mm] = Fp[mm];
             L.F[mm] = Fn[mm];
             d[mm] = dn[mm];
-            gF[mm] = nF[mm];
-            gFp[mm] = nFp[mm];
+            if (GHOST) {
+                gFp[mm] = nFp[mm];
+                gchg[mm] = __double_as_longlong(nF[mm]) != __double_as_longlong(nFp[mm]);
+            }
         }
         gnext += NM;
         op += NM;
@@ -650,8 +661,11 @@ __global__ void __launch_bounds__(256, 2) mrtm_warp_kernel(const WarpArgs a) {
     if (w >= a.n_warps) return;   // no block-level barrier is used below
     const int SB = a.sb;                                               // sub-steps of ghost series staged at a time
     const int SBP = SB + 1;                                            // + 1: the look-ahead reads one entry past a block
-    const int per_warp = 2 * a.G * SBP * NM * 2;                       // doubles of shared memory per warp
-    double2 *gs = reinterpret_cast<double2 *>(smem + (size_t)wib * per_warp);   // [2][G][SB + 1][NM]
+    const int GS = a.G + 1;                                            // + 1: an all-zero series for the lanes without ghost
+    const int per_warp = 2 * GS * SBP * NM * 2;                        // doubles of shared memory per warp
+    double2 *gs = reinterpret_cast<double2 *>(smem + (size_t)wib * per_warp);   // [2][G + 1][SB + 1][NM]
+    for (int i = lane; i < 2 * GS * SBP * NM; i += 32) gs[i] = make_double2(0.0, 0.0);
+    __syncwarp();
 
     const size_t g = (size_t)w * 32 + lane;
     const int cell = a.lane_cell[g], gedge = a.lane_gedge[g], oedge = a.lane_oedge[g];
@@ -740,7 +754,7 @@ __global__ void __launch_bounds__(256, 2) mrtm_warp_kernel(const WarpArgs a) {
                 const int sl = __shfl_sync(full, gslot, src_lane);
                 for (int i = lane; i < cnt; i += 32) {
                     const unsigned dst =
-                        (unsigned)__cvta_generic_to_shared(gs + ((size_t)buf * a.G + sl) * SBP * NM + i);
+                        (unsigned)__cvta_generic_to_shared(gs + ((size_t)buf * GS + sl) * SBP * NM + i);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)t0 * NM + i)
                                  : "memory");
                 }
@@ -763,7 +777,7 @@ __global__ void __launch_bounds__(256, 2) mrtm_warp_kernel(const WarpArgs a) {
             }
             const long long cs1 = dbg ? clock64() : 0;
             cyc_stage += cs1 - cs0;
-            const double2 *gcur = gs + ((size_t)buf * a.G + (is_ghost ? gslot : 0)) * SBP * NM;
+            const double2 *gcur = gs + ((size_t)buf * GS + (is_ghost ? gslot : a.G)) * SBP * NM;
             double2 *out = obase + (size_t)t0 * NM;
 #define XAN_RUN(NT_) \
     run_block_nt<NT_, NM>(ghost_mask != 0, has_out, L, gcur, is_ghost, out, lane_out, len, dt, dtinv, lastFp, n_redo)
@@ -1046,7 +1060,7 @@ static int launch_warp(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, cudaS
     size_t smem = 0;
     for (int sb : {32, 16, 8}) {   // shrink the staging blocks until every warp fits on the device
         a.sb = sb;
-        smem = sizeof(double) * (size_t)wpb * (2 * (size_t)pl->G * (sb + 1) * NM * 2);
+        smem = sizeof(double) * (size_t)wpb * (2 * ((size_t)pl->G + 1) * (sb + 1) * NM * 2);
         if (smem > 200 * 1024) continue;
         XAN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mrtm_warp_kernel<NM>, pl->block_threads, smem));
         if (per_sm * sms >= blocks) break;
