@@ -136,6 +136,47 @@ def test_batched_objective_all_basins_vs_oracle():
     assert abs(ed2[0, 0] - want) / abs(want) < RTOL
 
 
+@pytest.mark.parametrize("snow,unit", [(True, 'km3_per_mth'), (False, 'mm_per_mth')])
+def test_population_layout_of_the_objective(snow, unit, monkeypatch):
+    """
+    xan_abcd_kge_batch switches to the population layout (lane = candidate, warp = chunk of cells) for >= 16
+    candidates: 40 candidates (not a multiple of 32), all basins incl. ones smaller than a chunk, NaN precipitation;
+    against the oracle and against the block-per-(candidate, basin) kernel.
+    """
+    from xanthos_b200 import synthetic
+    from xanthos_b200.calibrate import calibrate_abcd as cal
+    from oracle import calibrate as ocal
+    w = synthetic.make_world(30, 60, 700, 9, seed=33)
+    m = 48
+    ab = synthetic.abcd_inputs(w, m, seed=6)
+    tmin = np.nan_to_num(ab['tmin']) if snow else None
+    rng = np.random.default_rng(2)
+    nb, P = w.n_basins, 40
+    pars = np.stack([rng.uniform(1e-4, hi, (nb, P)) for hi in (0.9999, 7.9999, 0.9999, 0.9999, 0.9999)], axis=2)
+    if not snow:
+        pars = pars[:, :, :4]
+    obs = rng.uniform(0.5, 2.0, (nb, m))
+    bnums = np.arange(1, nb + 1)
+    ev = cal.BasinEvaluator(w.basin_ids, w.area, ab['precip'], ab['pet'], tmin, m, 36, unit)
+    ed, series = ev.evaluate(bnums, pars, obs, want_series=True)
+    monkeypatch.setenv('XANTHOS_KGE_LAYOUT', 'block')
+    ed_b, series_b = ev.evaluate(bnums, pars, obs, want_series=True)
+    assert max_rel(series, series_b, floor=1e-12) < 1e-12 and max_rel(ed, ed_b, floor=1e-12) < 1e-11
+    monkeypatch.delenv('XANTHOS_KGE_LAYOUT')
+    for b in (0, 4, nb - 1):
+        idx = np.where(w.basin_ids == b + 1)[0]
+        for p in (0, 31, 32, P - 1):
+            want_s = ocal.basin_series(pars[b, p], ab['pet'][idx], ab['precip'][idx], None if tmin is None else tmin[idx],
+                                       m, 36, unit, w.area[idx])
+            assert max_rel(series[b, p], want_s, floor=1e-12) < RTOL
+            want = ocal.kge_distance(want_s, obs[b])
+            assert abs(ed[b, p] - want) / abs(want) < RTOL
+    # a subset of basins in caller order (slots != plan rows)
+    sub = np.array([7, 2, 5])
+    ed_s = ev.evaluate(sub, pars[sub - 1], obs[sub - 1])
+    assert bitwise_equal(ed_s, ed[sub - 1])
+
+
 def test_calibrate_all_recovers_synthetic_truth(tmp_path):
     """config 4 in miniature: DE against 'VIC-like' observations generated from hidden parameters."""
     import xanthos_b200

@@ -9,6 +9,7 @@
 //   3. abcd_sim_kernel      - thread per cell, state in registers, streams AET / Q / SW out.
 #include "common.cuh"
 
+#include <cstring>
 #include <vector>
 #include <algorithm>
 #include <numeric>
@@ -418,6 +419,164 @@ __global__ void __launch_bounds__(KGE_NT)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Calibration objective, population layout (used when a generation has >= 16 candidates).
+// lane = candidate parameter set, warp = a chunk of KC cells of one basin.  The 32 candidates of a
+// warp read the SAME forcing (one broadcast load serves 32 evaluations), every lane keeps the state of
+// its KC cells in registers for the whole pass (KC independent recurrences per thread = ILP), and no
+// shared memory or barrier is used.  Per chunk and candidate the spin-up pass leaves 12 partial
+// (sum, count) values for the basin re-initialisation and the simulation pass one partial basin sum per
+// month; two small kernels add the chunks of a basin in index order (deterministic) and finish the KGE.
+//   kge_pop_spinup_kernel -> kge_pop_reinit_kernel -> kge_pop_sim_kernel -> kge_pop_series_kernel -> kge_pop_finish_kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int KC = 4;   // cells per warp-chunk
+
+struct KgeChunk {
+    int slot;    // caller's basin slot
+    int beg;     // first index into `order`
+    int n;       // cells in this chunk (1..KC)
+};
+
+template <bool SNOW, bool SIM>
+__global__ void __launch_bounds__(128)
+    kge_pop_pass_kernel(const double *__restrict__ pet, const double *__restrict__ precip,
+                        const double *__restrict__ tmin, const double *__restrict__ area,
+                        const int *__restrict__ order, const KgeChunk *__restrict__ chunks, int nchunks,
+                        const double *__restrict__ pars, const double *__restrict__ init /* [nb][npar][2], SIM */,
+                        int npar, int npad, int nsteps, int ld, int unit_km3,
+                        double *__restrict__ out /* SIM: [nchunks][nsteps][npad]; else [nchunks][12][npad] */) {
+    const int lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int ngroups = npad >> 5;
+    if (unit >= nchunks * ngroups) return;
+    const int ch = unit / ngroups, grp = unit - ch * ngroups;
+    const KgeChunk c = chunks[ch];
+    const int p = grp * 32 + lane;
+    const int pp = min(p, npar - 1);                       // padding lanes repeat the last candidate
+    const AbcdPar par = load_par(pars, c.slot * npar + pp, SNOW);
+    int cell[KC];
+    double sn[KC], sw[KC], g[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        cell[k] = order[c.beg + min(k, c.n - 1)];          // short chunks repeat their last cell (masked below)
+        sn[k] = 0.0;
+        sw[k] = SIM ? init[((size_t)c.slot * npar + pp) * 2] : SW_INIT;
+        g[k] = SIM ? init[((size_t)c.slot * npar + pp) * 2 + 1] : GW_INIT;
+    }
+    const int s1 = nsteps - 25, s2 = nsteps - 13, s3 = nsteps - 1;   // Decembers -25, -13, -1 (abcd.py:255)
+    double *o = out + (size_t)ch * (SIM ? nsteps : 12) * npad + p;
+    for (int i = 0; i < nsteps; ++i) {
+        const size_t off = (size_t)i * ld;
+        double e[KC], pr[KC], t[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {                     // warp-uniform addresses: one broadcast per load
+            pr[k] = __ldg(precip + off + cell[k]);
+            e[k] = __ldg(pet + off + cell[k]);
+            t[k] = SNOW ? __ldg(tmin + off + cell[k]) : 0.0;
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            double aet, q;
+            abcd_step<SNOW>(i == 0, pr[k], e[k], t[k], par, sn[k], sw[k], g[k], aet, q);
+            if (SIM) {
+                const double v = unit_km3 ? (q * __ldg(area + cell[k]) * 1e-6) : q;   // rsim * area * 1e-6 (:159)
+                if (k < c.n && !isnan(v)) acc += v;
+            }
+        }
+        if (SIM) {
+            o[(size_t)i * npad] = acc;
+        } else if (i == s1 || i == s2 || i == s3) {
+            const int which = (i == s3) ? 0 : (i == s2) ? 1 : 2;
+            double ssw = 0.0, nsw = 0.0, sg = 0.0, ng = 0.0;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                if (k < c.n) {
+                    if (!isnan(sw[k])) { ssw += sw[k]; nsw += 1.0; }
+                    if (!isnan(g[k])) { sg += g[k]; ng += 1.0; }
+                }
+            }
+            o[(size_t)(which) * npad] = ssw;
+            o[(size_t)(3 + which) * npad] = nsw;
+            o[(size_t)(6 + which) * npad] = sg;
+            o[(size_t)(9 + which) * npad] = ng;
+        }
+    }
+}
+
+// set_vals with every cell of the basin in one group (calibrate_abcd.py:143): mean over the three Decembers
+// of the nanmean over cells.  thread = (slot, candidate); chunks of the slot are added in index order.
+__global__ void __launch_bounds__(64)
+    kge_pop_reinit_kernel(const double *__restrict__ snap /* [nchunks][12][npad] */, const int *__restrict__ slot_chunk0,
+                          int npar, int npad, double *__restrict__ init /* [nb][npar][2] */) {
+    const int slot = blockIdx.x;
+    const int c0 = slot_chunk0[slot], c1 = slot_chunk0[slot + 1];
+    for (int p = threadIdx.x; p < npar; p += blockDim.x) {
+        double acc[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) acc[j] = 0.0;
+        for (int c = c0; c < c1; ++c) {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) acc[j] += snap[((size_t)c * 12 + j) * npad + p];
+        }
+        double m_sw = 0.0, m_g = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            m_sw = m_sw + acc[k] / acc[3 + k];             // nanmean; 0/0 -> NaN like numpy
+            m_g = m_g + acc[6 + k] / acc[9 + k];
+        }
+        init[((size_t)slot * npar + p) * 2] = m_sw / 3.0;
+        init[((size_t)slot * npar + p) * 2 + 1] = m_g / 3.0;
+    }
+}
+
+// series[slot][m][p] = sum over the chunks of the slot (index order) of part[chunk][m][p]
+__global__ void __launch_bounds__(256)
+    kge_pop_series_kernel(const double *__restrict__ part, const int *__restrict__ slot_chunk0, int nmonths, int npad,
+                          double *__restrict__ series /* [nb][nmonths][npad] */) {
+    const int slot = blockIdx.x;
+    const int c0 = slot_chunk0[slot], c1 = slot_chunk0[slot + 1];
+    const int total = nmonths * npad;
+    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < total; idx += gridDim.y * blockDim.x) {
+        double a = 0.0;
+        for (int c = c0; c < c1; ++c) a += part[(size_t)c * total + idx];
+        series[(size_t)slot * total + idx] = a;
+    }
+}
+
+// KGE distance (calibrate_abcd.py:197-211); thread = (slot, candidate), sequential over months.
+__global__ void __launch_bounds__(64)
+    kge_pop_finish_kernel(const double *__restrict__ series /* [nb][nmonths][npad] */, const double *__restrict__ obs,
+                          int npar, int npad, int nmonths, double *__restrict__ ed_out, double *__restrict__ series_out) {
+    const int slot = blockIdx.x;
+    const double *ob = obs + (size_t)slot * nmonths;
+    for (int p = threadIdx.x; p < npar; p += blockDim.x) {
+        const double *sr = series + (size_t)slot * nmonths * npad + p;
+        double sm = 0.0, so = 0.0;
+        for (int i = 0; i < nmonths; ++i) {
+            const double m = sr[(size_t)i * npad];
+            if (series_out) series_out[((size_t)slot * npar + p) * nmonths + i] = m;
+            sm += m;
+            so += ob[i];
+        }
+        const double mean_m = sm / nmonths, mean_o = so / nmonths;
+        double vm = 0.0, vo = 0.0, cov = 0.0;
+        for (int i = 0; i < nmonths; ++i) {
+            const double dm = sr[(size_t)i * npad] - mean_m, dob = ob[i] - mean_o;
+            vm += dm * dm;
+            vo += dob * dob;
+            cov += dm * dob;
+        }
+        const double sd_m = sqrt(vm / nmonths), sd_o = sqrt(vo / nmonths);
+        const double relvar = sd_m / sd_o;
+        const double bias = mean_m / mean_o;
+        double r = cov / sqrt(vm * vo);
+        r = fmin(fmax(r, -1.0), 1.0);   // np.corrcoef clips to [-1, 1]
+        ed_out[(size_t)slot * npar + p] =
+            sqrt(((r - 1) * (r - 1)) + ((relvar - 1) * (relvar - 1)) + ((bias - 1) * (bias - 1)));
+    }
+}
+
 // out[m][b] = nansum over the cells of basin b of src[m][c] * w[c]; one warp per (basin, month).
 __global__ void __launch_bounds__(256)
     basin_sum_kernel(const double *__restrict__ src, const double *__restrict__ w, const int *__restrict__ order,
@@ -514,8 +673,8 @@ int xan_abcd_run(const xan_abcd_plan *pl, const double *d_pet, const double *d_p
     cudaStream_t s = (cudaStream_t)stream;
     const int ncell = pl->ncell;
     double *snap = nullptr, *init = nullptr;
-    XAN_CUDA_CHECK(cudaMallocAsync(&snap, sizeof(double) * 6 * (size_t)ncell, s));
-    XAN_CUDA_CHECK(cudaMallocAsync(&init, sizeof(double) * 2 * (size_t)pl->n_basins, s));
+    XAN_CUDA_CHECK(scratch_alloc(&snap, sizeof(double) * 6 * (size_t)ncell, s));
+    XAN_CUDA_CHECK(scratch_alloc(&init, sizeof(double) * 2 * (size_t)pl->n_basins, s));
     const int grid = ceil_div(ncell, 128);
     if (d_tmin)
         abcd_spinup_kernel<true><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, pl->d_basin_idx, d_pars, ncell,
@@ -536,6 +695,61 @@ int xan_abcd_run(const xan_abcd_plan *pl, const double *d_pet, const double *d_p
     return XAN_OK;
 }
 
+// Population layout of the calibration objective (see kge_pop_pass_kernel).
+static int kge_population(const xan_abcd_plan *pl, const int *h_basins, int nb, int npar, const double *d_pet,
+                          const double *d_precip, const double *d_tmin, const double *d_area, const double *d_pars,
+                          const double *d_obs, int nmonths, int spinup, int ld, int unit_km3, double *d_ed,
+                          double *d_series, cudaStream_t s) {
+    const int npad = (npar + 31) / 32 * 32;
+    std::vector<KgeChunk> chunks;
+    std::vector<int> slot_chunk0(nb + 1, 0);
+    for (int i = 0; i < nb; ++i) {
+        const int beg = pl->h_offsets[h_basins[i]], end = pl->h_offsets[h_basins[i] + 1];
+        slot_chunk0[i] = (int)chunks.size();
+        for (int b = beg; b < end; b += KC) chunks.push_back(KgeChunk{i, b, std::min(KC, end - b)});
+    }
+    slot_chunk0[nb] = (int)chunks.size();
+    const int nch = (int)chunks.size();
+    KgeChunk *d_chunks = nullptr;
+    int *d_slot0 = nullptr;
+    double *snap = nullptr, *init = nullptr, *part = nullptr, *series = nullptr;
+    XAN_CUDA_CHECK(scratch_alloc(&d_chunks, sizeof(KgeChunk) * nch, s));
+    XAN_CUDA_CHECK(scratch_alloc(&d_slot0, sizeof(int) * (nb + 1), s));
+    XAN_CUDA_CHECK(scratch_alloc(&snap, sizeof(double) * 12 * (size_t)nch * npad, s));
+    XAN_CUDA_CHECK(scratch_alloc(&init, sizeof(double) * 2 * (size_t)nb * npar, s));
+    XAN_CUDA_CHECK(scratch_alloc(&part, sizeof(double) * (size_t)nch * nmonths * npad, s));
+    XAN_CUDA_CHECK(scratch_alloc(&series, sizeof(double) * (size_t)nb * nmonths * npad, s));
+    XAN_CUDA_CHECK(cudaMemcpyAsync(d_chunks, chunks.data(), sizeof(KgeChunk) * nch, cudaMemcpyHostToDevice, s));
+    XAN_CUDA_CHECK(cudaMemcpyAsync(d_slot0, slot_chunk0.data(), sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, s));
+    const int units = nch * (npad / 32);
+    const int grid = ceil_div(units, 4);
+    if (d_tmin)
+        kge_pop_pass_kernel<true, false><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, d_area, pl->d_order, d_chunks, nch,
+                                                              d_pars, nullptr, npar, npad, spinup, ld, unit_km3, snap);
+    else
+        kge_pop_pass_kernel<false, false><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, d_area, pl->d_order, d_chunks, nch,
+                                                               d_pars, nullptr, npar, npad, spinup, ld, unit_km3, snap);
+    kge_pop_reinit_kernel<<<nb, 64, 0, s>>>(snap, d_slot0, npar, npad, init);
+    if (d_tmin)
+        kge_pop_pass_kernel<true, true><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, d_area, pl->d_order, d_chunks, nch,
+                                                             d_pars, init, npar, npad, nmonths, ld, unit_km3, part);
+    else
+        kge_pop_pass_kernel<false, true><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, d_area, pl->d_order, d_chunks, nch,
+                                                              d_pars, init, npar, npad, nmonths, ld, unit_km3, part);
+    kge_pop_series_kernel<<<dim3(nb, 8), 256, 0, s>>>(part, d_slot0, nmonths, npad, series);
+    kge_pop_finish_kernel<<<nb, 64, 0, s>>>(series, d_obs, npar, npad, nmonths, d_ed, d_series);
+    XAN_CUDA_CHECK(cudaGetLastError());
+    // The host tables are read by the copies above: wait before they go out of scope.
+    XAN_CUDA_CHECK(cudaFreeAsync(d_chunks, s));
+    XAN_CUDA_CHECK(cudaFreeAsync(d_slot0, s));
+    XAN_CUDA_CHECK(cudaFreeAsync(snap, s));
+    XAN_CUDA_CHECK(cudaFreeAsync(init, s));
+    XAN_CUDA_CHECK(cudaFreeAsync(part, s));
+    XAN_CUDA_CHECK(cudaFreeAsync(series, s));
+    XAN_CUDA_CHECK(cudaStreamSynchronize(s));
+    return XAN_OK;
+}
+
 int xan_abcd_kge_batch(const xan_abcd_plan *pl, const int *h_basins, int nb, int npar, const double *d_pet,
                        const double *d_precip, const double *d_tmin, const double *d_area, const double *d_pars,
                        const double *d_obs, int nmonths, int spinup, int ld, int unit_km3, double *d_ed,
@@ -551,6 +765,19 @@ int xan_abcd_kge_batch(const xan_abcd_plan *pl, const int *h_basins, int nb, int
     XAN_REQUIRE(spinup <= nmonths, "xan_abcd_kge_batch: spinup (%d) exceeds the %d months of forcing", spinup,
                 nmonths);
     cudaStream_t s = (cudaStream_t)stream;
+    for (int i = 0; i < nb; ++i) {
+        XAN_REQUIRE(h_basins[i] >= 0 && h_basins[i] < pl->n_basins, "xan_abcd_kge_batch: basin row %d out of range",
+                    h_basins[i]);
+        XAN_REQUIRE(pl->h_offsets[h_basins[i] + 1] > pl->h_offsets[h_basins[i]],
+                    "xan_abcd_kge_batch: basin row %d has no cells", h_basins[i]);
+    }
+    {
+        const char *env = getenv("XANTHOS_KGE_LAYOUT");   // "block" forces the block-per-(candidate, basin) kernel
+        const bool force_block = env && !strcmp(env, "block"), force_pop = env && !strcmp(env, "population");
+        if (!force_block && (npar >= 16 || force_pop))
+            return kge_population(pl, h_basins, nb, npar, d_pet, d_precip, d_tmin, d_area, d_pars, d_obs, nmonths,
+                                  spinup, ld, unit_km3, d_ed, d_series, s);
+    }
     // schedule big basins first (longest-processing-time order)
     std::vector<int> slots(nb);
     std::iota(slots.begin(), slots.end(), 0);
@@ -576,7 +803,7 @@ int xan_abcd_kge_batch(const xan_abcd_plan *pl, const int *h_basins, int nb, int
     XAN_REQUIRE(smem <= 227 * 1024, "xan_abcd_kge_batch: basin with %d cells x %d months needs %zu B of shared memory",
                 max_cells, nmonths, smem);
     int *d_meta = nullptr;
-    XAN_CUDA_CHECK(cudaMallocAsync(&d_meta, sizeof(int) * 2 * nb, s));
+    XAN_CUDA_CHECK(scratch_alloc(&d_meta, sizeof(int) * 2 * nb, s));
     XAN_CUDA_CHECK(cudaMemcpyAsync(d_meta, h_meta.data(), sizeof(int) * 2 * nb, cudaMemcpyHostToDevice, s));
     dim3 grid(npar, nb);
     if (d_tmin) {

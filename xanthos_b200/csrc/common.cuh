@@ -12,6 +12,12 @@
 namespace xan {
 
 void set_error(const char *fmt, ...);
+// cudaMallocAsync from the device's default pool, configured to keep freed memory cached (core.cu)
+cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t s);
+template <typename T>
+inline cudaError_t scratch_alloc(T **p, size_t bytes, cudaStream_t s) {
+    return scratch_alloc(reinterpret_cast<void **>(p), bytes, s);
+}
 
 #define XAN_CUDA_CHECK(expr)                                                                  \
     do {                                                                                      \

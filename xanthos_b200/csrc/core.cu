@@ -14,6 +14,27 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+// Stream-ordered scratch memory.  The default memory pool of a device returns its memory to the driver
+// at every synchronisation (release threshold 0), so a 3 GB scratch buffer would be cudaMalloc'ed and
+// freed on every call (tens of milliseconds).  The threshold is raised once per device; scratch then
+// stays cached in the pool between calls.
+cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t s) {
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (configured_dev != dev) {
+        cudaMemPool_t pool;
+        e = cudaDeviceGetDefaultMemPool(&pool, dev);
+        if (e != cudaSuccess) return e;
+        unsigned long long keep = ~0ull;
+        e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess) return e;
+        configured_dev = dev;
+    }
+    return cudaMallocAsync(p, bytes, s);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Transposes.  The reference keeps every field as [ncell][nmonths] (data_load.py:288-340); the
 // kernels of this library want [nmonths][ld] so that a warp reads 32 consecutive cells of one

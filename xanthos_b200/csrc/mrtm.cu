@@ -1076,11 +1076,11 @@ static int launch_warp(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, cudaS
     a.sleep_ns = es ? std::max(0, atoi(es)) : 100;
     double2 *ring = nullptr;
     const size_t ring_elems = (size_t)std::max(pl->n_edges, 1) * a.ring * ntmax * NM;
-    XAN_CUDA_CHECK(cudaMallocAsync(&ring, sizeof(double2) * ring_elems, s));
+    XAN_CUDA_CHECK(scratch_alloc(&ring, sizeof(double2) * ring_elems, s));
     XAN_CUDA_CHECK(cudaMemsetAsync(pl->d_progress, 0, sizeof(int) * pl->n_warps, s));
     a.ring_buf = ring;
     a.dbg = nullptr;
-    if (getenv("XANTHOS_MRTM_DEBUG")) XAN_CUDA_CHECK(cudaMallocAsync(&a.dbg, sizeof(long long) * 6 * pl->n_warps, s));
+    if (getenv("XANTHOS_MRTM_DEBUG")) XAN_CUDA_CHECK(scratch_alloc(&a.dbg, sizeof(long long) * 6 * pl->n_warps, s));
     void *kargs[] = {(void *)&a};
     // cooperative launch = all blocks co-resident (no grid.sync is used)
     XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)mrtm_warp_kernel<NM>, dim3(blocks), dim3(pl->block_threads), kargs,
@@ -1122,7 +1122,7 @@ static int route_grid(xan_mrtm_plan *pl, const double *d_runoff, const double *d
     g.ld = ld;
     g.dt = dt;
     double *work = nullptr;
-    XAN_CUDA_CHECK(cudaMallocAsync(&work, sizeof(double) * 6 * (size_t)pl->ncell, s));
+    XAN_CUDA_CHECK(scratch_alloc(&work, sizeof(double) * 6 * (size_t)pl->ncell, s));
     g.S = work;
     g.Favg = work + pl->ncell;
     g.D = work + 2 * (size_t)pl->ncell;
@@ -1168,7 +1168,7 @@ int xan_mrtm_route_batch(xan_mrtm_plan *pl, int n_members, const double *const *
     XAN_CUDA_CHECK(cudaGetDevice(&dev));
     XAN_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int *d_ndays = nullptr;
-    XAN_CUDA_CHECK(cudaMallocAsync(&d_ndays, sizeof(int) * nmonths, s));
+    XAN_CUDA_CHECK(scratch_alloc(&d_ndays, sizeof(int) * nmonths, s));
     XAN_CUDA_CHECK(cudaMemcpyAsync(d_ndays, h_ndays, sizeof(int) * nmonths, cudaMemcpyHostToDevice, s));
 
     const char *env_nm = getenv("XANTHOS_MRTM_MEMBERS");

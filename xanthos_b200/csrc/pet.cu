@@ -354,7 +354,7 @@ int xan_hs_pet(const double *d_tas, const double *d_tmax, const double *d_tmin, 
                 nmonths, ld);
     cudaStream_t s = (cudaStream_t)stream;
     double *ra_tab = nullptr;
-    XAN_CUDA_CHECK(cudaMallocAsync(&ra_tab, sizeof(double) * 12 * (size_t)ncell, s));
+    XAN_CUDA_CHECK(scratch_alloc(&ra_tab, sizeof(double) * 12 * (size_t)ncell, s));
     hs_ra_table_kernel<<<dim3(ceil_div(ncell, 128), 12), 128, 0, s>>>(d_lat_deg, ra_tab, ncell);
     hs_pet_kernel<<<dim3(ceil_div(ncell, 256), nmonths / 12), 256, 0, s>>>(d_tas, d_tmax, d_tmin, ra_tab,
                                                                           d_pet, ncell, ld, start_year);
@@ -370,7 +370,7 @@ int xan_thornthwaite_pet(const double *d_tas, const double *d_lat_rad, double *d
                 "xan_thornthwaite_pet: bad shape ncell=%d nmonths=%d ld=%d", ncell, nmonths, ld);
     cudaStream_t s = (cudaStream_t)stream;
     double *L_tab = nullptr;
-    XAN_CUDA_CHECK(cudaMallocAsync(&L_tab, sizeof(double) * 24 * (size_t)ncell, s));
+    XAN_CUDA_CHECK(scratch_alloc(&L_tab, sizeof(double) * 24 * (size_t)ncell, s));
     tw_daylight_kernel<<<ceil_div(ncell, 128), 128, 0, s>>>(d_lat_rad, L_tab, ncell);
     const int nyears = nmonths / 12;
     tw_pet_kernel<<<dim3(ceil_div(ncell, 256), nyears), 256, 0, s>>>(d_tas, L_tab, d_pet, ncell, ld,
@@ -438,7 +438,7 @@ int xan_pm_pet(const double *d_tair, const double *d_tmin, const double *d_rhs, 
         }
         h_tab->lc_index[y] = (unsigned char)h_lc_index[y];
     }
-    XAN_CUDA_CHECK(cudaMallocAsync(&d_tab, sizeof(PmTab), s));
+    XAN_CUDA_CHECK(scratch_alloc(&d_tab, sizeof(PmTab), s));
     XAN_CUDA_CHECK(cudaMemcpyAsync(d_tab, h_tab, sizeof(PmTab), cudaMemcpyHostToDevice, s));
     const char *exact = getenv("XANTHOS_PM_EXACT");
     if (exact && exact[0] == '1')

@@ -151,7 +151,7 @@ int xan_hargreaves_pet(const double *d_temp, const double *d_dtr, const double *
         h_tab[3 * m + 1] = h_dr[m];
         h_tab[3 * m + 2] = (double)h_days[m];
     }
-    XAN_CUDA_CHECK(cudaMallocAsync(&tab, sizeof(double) * 3 * (size_t)nmonths, s));
+    XAN_CUDA_CHECK(scratch_alloc(&tab, sizeof(double) * 3 * (size_t)nmonths, s));
     XAN_CUDA_CHECK(cudaMemcpyAsync(tab, h_tab, sizeof(double) * 3 * (size_t)nmonths, cudaMemcpyHostToDevice, s));
     hargreaves_pet_kernel<<<dim3(ceil_div(ncell, 256), nmonths), 256, 0, s>>>(d_temp, d_dtr, d_lat_rad, tab, d_pet,
                                                                              ncell, ld);
