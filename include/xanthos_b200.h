@@ -135,8 +135,11 @@ int xan_mrtm_upstream(const double *h_coords, const int64_t *h_dsid, int ncell, 
 
 /* Execution plan; replaces upstream_genmatrix (mrtm.py:194-230): from h_upid [ncell][9] it
  * builds the rows of UM = UP - I, checks that the flow graph is a forest, cuts large river trees
- * into pieces of at most 31 lanes and packs them into warps (lane 31 of every warp stays empty).  block_threads (multiple of 32,
- * <= 256) / chunk_substeps (sub-steps per hand-over between warps) <= 0 pick defaults.  Plan
+ * into pieces of at most 31 lanes and packs them into warps (lane 31 of every warp stays empty).
+ * block_threads (multiple of 32, <= 640; default 640 = 20 warps, one block per SM, 96 registers) /
+ * chunk_substeps (sub-steps per hand-over between warps) <= 0 pick defaults.  At launch the packed
+ * warps are assigned to SM sub-partitions by cost and loop variant (see mrtm_sched_kernel;
+ * XANTHOS_MRTM_SCHED=static binds packed warp w to grid warp w instead).  Plan
  * creation is host-side integer work and needs no device; the device tables are uploaded by the
  * first xan_mrtm_route call. */
 typedef struct xan_mrtm_plan xan_mrtm_plan;

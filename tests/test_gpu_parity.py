@@ -178,7 +178,9 @@ def test_mrtm_streamrouting_single_month():
 @pytest.mark.parametrize("kw,lanes", [(dict(block_threads=32, chunk_substeps=64), 0),
                                       (dict(block_threads=64, chunk_substeps=7), 12),
                                       (dict(block_threads=256, chunk_substeps=1), 20),
-                                      (dict(block_threads=128, chunk_substeps=300), 9)])
+                                      (dict(block_threads=128, chunk_substeps=300), 9),
+                                      (dict(block_threads=512, chunk_substeps=64), 14),
+                                      (dict(block_threads=640, chunk_substeps=64), 10)])
 def test_mrtm_cut_trees_match_oracle(kw, lanes, monkeypatch):
     """River trees much larger than a warp: exercises the cut-edge pipeline between warps."""
     if lanes:

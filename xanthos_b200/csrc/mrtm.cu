@@ -57,6 +57,7 @@ struct xan_mrtm_plan {
     int *d_edge_prod = nullptr;         // [n_edges] producing warp
     int *d_edge_cons = nullptr;         // [n_edges] consuming warp
     int *d_progress = nullptr;          // [n_warps] chunks completed (reset per run)
+    int *d_edge_cell = nullptr;         // [n_edges] cell whose flow the edge carries
     bool on_device = false;
 };
 
@@ -177,7 +178,7 @@ static int build_rows(xan_mrtm_plan *pl, const int64_t *upid) {
 // host: partition of the forest into warp-sized pieces
 // =============================================================================================
 struct Packing {
-    std::vector<int> lane_cell, lane_gedge, lane_oedge, edge_prod, edge_cons;
+    std::vector<int> lane_cell, lane_gedge, lane_oedge, edge_prod, edge_cons, edge_cell;
     std::vector<uint2> lane_src;
     std::vector<unsigned> lane_meta;
     int n_warps = 0, n_edges = 0, n_levels = 0, G = 0;
@@ -378,6 +379,7 @@ static bool build_packing(xan_mrtm_plan *pl, int lanes, Packing &pk) {
             const int e = (int)pk.edge_prod.size();
             pk.edge_prod.push_back(wp);
             pk.edge_cons.push_back(wc);
+            pk.edge_cell.push_back(v);
             if (next_lane[wc] >= 32) return false;
             const int gl = next_lane[wc]++;
             ghost_lane[v] = gl;
@@ -449,6 +451,7 @@ struct WarpArgs {
     double *chs[NM_MAX], *avg[NM_MAX], *instream[NM_MAX];
     int n_warps, G, ntmax, nmonths, spinup, ld, ring, sleep_ns, sb;
     double dt;
+    const int *sched;        // [grid warps] packed warp run by each grid warp (mrtm_sched_kernel); null = identity
     long long *dbg;          // optional [n_warps][6]: cycles total, hand-over wait, staging wait, sub-step loops, redo count, SM id
 };
 
@@ -652,13 +655,85 @@ __device__ __forceinline__ void run_block_nt(bool has_ghost, bool has_out, LaneS
         run_block<NT, NM, false, false>(L, gsl, is_ghost, out, lane_out, len, dt, dtinv, lastFp, n_redo);
 }
 
-template <int NM>
-__global__ void __launch_bounds__(256, 2) mrtm_warp_kernel(const WarpArgs a) {
+
+// ---------------------------------------------------------------------------------------------
+// Placement-aware work assignment.  The run ends when the slowest chain of packed warps ends, and the
+// slow ones are known before the launch: a warp that holds a cell with dt V / L > 1 (or a ghost lane fed
+// by such a cell) repeats the balance with F' at every other sub-step (that cell empties, refills,
+// empties ...) and needs ~1.7x the instructions of the others.  With packed warp w bound to grid warp
+// w, up to 7 of them met on one SM and 3 in one SM sub-partition, where they share one issue port.
+// A block is 16 warps = one SM (1 block per SM by registers), warp i of a block runs in sub-partition
+// i & 3, so the table assign[grid warp] -> packed warp decides who shares an issue port:
+//   * the expensive warps go one per sub-partition, spread over all SMs, in slot 0 of their sub-partition;
+//   * the others are sorted by loop variant (row length NT, ghost lanes, cut-edge output) and fill the
+//     sub-partitions in runs of consecutive entries, so that the warps of a sub-partition execute the
+//     same copy of the sub-step loop (instruction cache) - the cheapest variants beside the expensive warps.
+// The arithmetic of a packed warp does not depend on where it runs: results are bit-identical.
+// One block, thread = packed warp; ranks by counting (n_warps <= 148 x 16 because all warps are co-resident).
+// ---------------------------------------------------------------------------------------------
+__global__ void mrtm_sched_kernel(const int *lane_cell, const int *lane_gedge, const int *lane_oedge,
+                                  const unsigned *lane_meta, const int *edge_cell, const double *flow_dist,
+                                  const double *velocity, double dt, int n_warps, int n_blocks, int wpb, int group,
+                                  int *assign) {
+    extern __shared__ int s_key[];   // [n_warps]
+    for (int i = threadIdx.x; i < n_blocks * wpb; i += blockDim.x) assign[i] = -1;
+    for (int w = threadIdx.x; w < n_warps; w += blockDim.x) {
+        bool expensive = false, ghost = false, out = false;
+        int nt = 1;
+        for (int l = 0; l < 32; ++l) {
+            const size_t g = (size_t)w * 32 + l;
+            int c = lane_cell[g];
+            const int e = lane_gedge[g];
+            if (c >= 0) nt = max(nt, (int)(lane_meta[g] & 0xf));
+            if (e >= 0) {
+                c = edge_cell[e];
+                ghost = true;
+            }
+            out = out || lane_oedge[g] >= 0;
+            if (c >= 0) expensive = expensive || (velocity[c] / flow_dist[c]) * dt > 1.0;
+        }
+        const int variant = group ? (nt * 4 + (ghost ? 2 : 0) + (out ? 1 : 0)) : 0;
+        s_key[w] = (expensive ? 0 : 1 << 16) | variant;
+    }
+    __syncthreads();
+    const int S = wpb / 4, B = n_blocks;
+    for (int w = threadIdx.x; w < n_warps; w += blockDim.x) {
+        const int key = s_key[w];
+        int r = 0, nE = 0;
+        for (int v = 0; v < n_warps; ++v) {
+            const int kv = s_key[v];
+            r += (kv < key || (kv == key && v < w)) ? 1 : 0;
+            nE += (kv < (1 << 16)) ? 1 : 0;
+        }
+        const int nEp = min(nE, 4 * B);
+        // companions of an expensive warp: as few as the grid allows (spare slots stay beside the expensive warps)
+        int c = S - 1;
+        while (c > 0 && nEp * (c - 1) + (4 * B - nEp) * S >= n_warps - nEp) --c;
+        int q, blk, pos;
+        if (r < nEp) {
+            q = r / B; blk = r % B; pos = 0;
+        } else {
+            const int j = r - nEp, cap1 = c * nEp;
+            if (j < cap1) {
+                const int k = j / c;
+                q = k / B; blk = k % B; pos = 1 + j % c;
+            } else {
+                const int jj = j - cap1, t = nEp + jj / S;
+                q = t / B; blk = t % B; pos = jj % S;
+            }
+        }
+        assign[blk * wpb + q + 4 * pos] = w;
+    }
+}
+
+template <int NM, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) mrtm_warp_kernel(const WarpArgs a) {
     extern __shared__ double smem[];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int w = blockIdx.x * wpb + wib;
-    if (w >= a.n_warps) return;   // no block-level barrier is used below
+    int w = blockIdx.x * wpb + wib;
+    if (a.sched) w = a.sched[w];
+    if (w < 0 || w >= a.n_warps) return;   // no block-level barrier is used below
     const int SB = a.sb;                                               // sub-steps of ghost series staged at a time
     const int SBP = SB + 1;                                            // + 1: the look-ahead reads one entry past a block
     const int GS = a.G + 1;                                            // + 1: an all-zero series for the lanes without ghost
@@ -822,7 +897,9 @@ __global__ void __launch_bounds__(256, 2) mrtm_warp_kernel(const WarpArgs a) {
         a.dbg[6 * w + 2] = cyc_stage;
         a.dbg[6 * w + 3] = cyc_loop;
         a.dbg[6 * w + 4] = n_redo;
-        a.dbg[6 * w + 5] = smid;
+        unsigned wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        a.dbg[6 * w + 5] = smid * 4 + (wid & 3);   // SM sub-partition
     }
 }
 
@@ -915,6 +992,7 @@ static void free_device(xan_mrtm_plan *pl) {
     cudaFree(pl->d_edge_prod);
     cudaFree(pl->d_edge_cons);
     cudaFree(pl->d_progress);
+    cudaFree(pl->d_edge_cell);
 }
 
 template <typename V>
@@ -934,7 +1012,8 @@ static int ensure_device(xan_mrtm_plan *pl) {
         ok = upload(pk.lane_cell, &pl->d_lane_cell) && upload(pk.lane_gedge, &pl->d_lane_gedge) &&
              upload(pk.lane_oedge, &pl->d_lane_oedge) && upload(pk.lane_src, &pl->d_lane_src) &&
              upload(pk.lane_meta, &pl->d_lane_meta) && upload(pk.edge_prod, &pl->d_edge_prod) &&
-             upload(pk.edge_cons, &pl->d_edge_cons) && upload(zeros, &pl->d_progress);
+             upload(pk.edge_cons, &pl->d_edge_cons) && upload(zeros, &pl->d_progress) &&
+             upload(pk.edge_cell, &pl->d_edge_cell);
     }
     if (!ok) {
         set_error("mrtm plan: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -973,15 +1052,15 @@ xan_mrtm_plan *xan_mrtm_plan_create(const int64_t *h_upid, int ncell, int block_
     }
     const char *env_t = getenv("XANTHOS_MRTM_THREADS"), *env_c = getenv("XANTHOS_MRTM_CHUNK"),
                *env_l = getenv("XANTHOS_MRTM_LANES");
-    pl->block_threads = (block_threads > 0) ? block_threads : (env_t ? atoi(env_t) : 128);
+    pl->block_threads = (block_threads > 0) ? block_threads : (env_t ? atoi(env_t) : 640);
     pl->chunk = (chunk_substeps > 0) ? chunk_substeps : (env_c ? atoi(env_c) : 64);
     // lanes a warp may occupy (tests use small values); 31 keeps lane 31 empty, which the shuffle
     // exchange uses as its constant-zero source
     const int lanes = env_l ? atoi(env_l) : 31;
     pl->lanes = lanes;
-    if (pl->block_threads % 32 != 0 || pl->block_threads < 32 || pl->block_threads > 256 || pl->chunk < 1 ||
+    if (pl->block_threads % 32 != 0 || pl->block_threads < 32 || pl->block_threads > 640 || pl->chunk < 1 ||
         pl->chunk > 1024 || lanes < 9 || lanes > 31) {
-        set_error("xan_mrtm_plan_create: block_threads must be a multiple of 32 in 32..256, chunk_substeps in "
+        set_error("xan_mrtm_plan_create: block_threads must be a multiple of 32 in 32..640, chunk_substeps in "
                   "1..1024 (XANTHOS_MRTM_LANES in 9..31)");
         delete pl;
         return nullptr;
@@ -1051,40 +1130,54 @@ int xan_mrtm_plan_info(const xan_mrtm_plan *pl, int *info) {
 
 // Launch the warp kernel for `nm` (1..NM_MAX) members.  Returns XAN_OK, or XAN_E_INVALID when the
 // blocks cannot all be resident (the caller may then fall back to the grid kernel).
-template <int NM>
-static int launch_warp(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, cudaStream_t s) {
-    const int wpb = pl->block_threads / 32;
-    const int blocks = ceil_div(pl->n_warps, wpb);
-    XAN_CUDA_CHECK(cudaFuncSetAttribute(mrtm_warp_kernel<NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+template <int NM, int MAXT>
+static int launch_warp_t(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, int threads, cudaStream_t s) {
+    const int wpb = threads / 32;
+    int blocks = ceil_div(pl->n_warps, wpb);
+    auto kernel = mrtm_warp_kernel<NM, MAXT>;
+    XAN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int per_sm = 0;
     size_t smem = 0;
     for (int sb : {32, 16, 8}) {   // shrink the staging blocks until every warp fits on the device
         a.sb = sb;
         smem = sizeof(double) * (size_t)wpb * (2 * ((size_t)pl->G + 1) * (sb + 1) * NM * 2);
         if (smem > 200 * 1024) continue;
-        XAN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mrtm_warp_kernel<NM>, pl->block_threads, smem));
+        XAN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
         if (per_sm * sms >= blocks) break;
     }
     if (per_sm * sms < blocks) {
         // the cut-edge pipeline needs every warp resident at the same time
         set_error("mrtm warp kernel: %d blocks of %d threads (%zu B smem, %d members) cannot be co-resident "
-                  "(%d per SM x %d SMs)", blocks, pl->block_threads, smem, NM, per_sm, sms);
+                  "(%d per SM x %d SMs)", blocks, threads, smem, NM, per_sm, sms);
         return XAN_E_INVALID;
     }
     const char *er = getenv("XANTHOS_MRTM_RING"), *es = getenv("XANTHOS_MRTM_SLEEP_NS");
     a.ring = er ? std::max(1, atoi(er)) : RING_DEFAULT;
     a.sleep_ns = es ? std::max(0, atoi(es)) : 100;
+
     double2 *ring = nullptr;
     const size_t ring_elems = (size_t)std::max(pl->n_edges, 1) * a.ring * ntmax * NM;
     XAN_CUDA_CHECK(scratch_alloc(&ring, sizeof(double2) * ring_elems, s));
     XAN_CUDA_CHECK(cudaMemsetAsync(pl->d_progress, 0, sizeof(int) * pl->n_warps, s));
     a.ring_buf = ring;
     a.dbg = nullptr;
+    a.sched = nullptr;
+    int *d_sched = nullptr;
+    const char *esch = getenv("XANTHOS_MRTM_SCHED");   // static | spread (no variant grouping) | grouped (default)
+    if (!(esch && !strcmp(esch, "static")) && wpb % 4 == 0 && pl->n_warps <= 12288) {
+        // one block per SM on every SM: the slots the packed warps do not need stay empty beside the expensive warps
+        if (per_sm == 1 && wpb >= 16) blocks = std::max(blocks, sms);
+        XAN_CUDA_CHECK(scratch_alloc(&d_sched, sizeof(int) * (size_t)blocks * wpb, s));
+        mrtm_sched_kernel<<<1, 1024, sizeof(int) * pl->n_warps, s>>>(
+            a.lane_cell, a.lane_gedge, a.lane_oedge, a.lane_meta, pl->d_edge_cell, a.flow_dist, a.velocity, a.dt,
+            pl->n_warps, blocks, wpb, (esch && !strcmp(esch, "spread")) ? 0 : 1, d_sched);
+        XAN_CUDA_CHECK(cudaGetLastError());
+        a.sched = d_sched;
+    }
     if (getenv("XANTHOS_MRTM_DEBUG")) XAN_CUDA_CHECK(scratch_alloc(&a.dbg, sizeof(long long) * 6 * pl->n_warps, s));
     void *kargs[] = {(void *)&a};
     // cooperative launch = all blocks co-resident (no grid.sync is used)
-    XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)mrtm_warp_kernel<NM>, dim3(blocks), dim3(pl->block_threads), kargs,
-                                               smem, s));
+    XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kernel, dim3(blocks), dim3(threads), kargs, smem, s));
     if (a.dbg) {
         std::vector<long long> h(6 * (size_t)pl->n_warps);
         XAN_CUDA_CHECK(cudaMemcpyAsync(h.data(), a.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, s));
@@ -1098,8 +1191,18 @@ static int launch_warp(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, cudaS
         }
         XAN_CUDA_CHECK(cudaFreeAsync(a.dbg, s));
     }
+    if (d_sched) XAN_CUDA_CHECK(cudaFreeAsync(d_sched, s));
     XAN_CUDA_CHECK(cudaFreeAsync(ring, s));
     return XAN_OK;
+}
+
+template <int NM>
+static int launch_warp(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, cudaStream_t s) {
+    // the register budget follows the block size: up to 512 threads -> 128 registers, 640 -> 96 (one member per pass only)
+    if constexpr (NM == 1) {
+        if (pl->block_threads > 512) return launch_warp_t<NM, 640>(pl, a, ntmax, sms, pl->block_threads, s);
+    }
+    return launch_warp_t<NM, 512>(pl, a, ntmax, sms, std::min(pl->block_threads, 512), s);
 }
 
 static int route_grid(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_dist, const double *d_velocity,
