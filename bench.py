@@ -362,22 +362,22 @@ def run_ours(args, rank, world_size, local_rank):
     # DRAM traffic per launch from the committed ncu --set full capture of the same workload (profiles/)
     traffic = {}
     try:
-        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+        with open(os.path.join(ROOT, 'profiles', 'r01b_traffic.json')) as f:
             tk = json.load(f)['kernels']
         if (ncell, nmonths) == (NCELL, NMONTHS):
             traffic = {'pm_pet_kernel': tk['pm_pet_fast_kernel']['dram_bytes_per_launch'],
                        'abcd_spinup+reinit+sim': tk['abcd_spinup_kernel<1>']['dram_bytes_per_launch']
                        + tk['abcd_sim_kernel<1>']['dram_bytes_per_launch'],
-                       'mrtm_warp_kernel': tk['mrtm_warp_kernel<1>']['dram_bytes_per_launch']}
+                       'mrtm_warp_kernel': tk['mrtm_warp_kernel<1, 640>']['dram_bytes_per_launch']}
     except Exception:
         traffic = {}
     dom = max(per_kernel, key=lambda k: per_kernel[k]['ms'])
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': per_kernel[dom]['gbs'], 'peak': peaks['hbm_gbs'],
                 'unit': 'GB/s', 'frac': per_kernel[dom]['frac_hbm'], 'traffic': traffic.get(dom),
-                'traffic_source': 'profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)',
+                'traffic_source': 'profiles/r01b_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)',
                 'algorithmic_bytes': per_kernel[dom]['alg_bytes'], 'peak_source': peak_src,
                 'share_of_step': per_kernel[dom]['ms'] / sum(v['ms'] for v in per_kernel.values()),
-                'note': 'dominant kernel is latency/FP64 bound, not HBM bound; see DESIGN.md',
+                'note': 'dominant kernel is bound by the latency of its sequential sub-step recurrence and by issue slots, not by HBM; see DESIGN.md',
                 'kernels': {k: {'ms': round(v['ms'], 4), 'achieved_gbs': round(v['gbs'], 2),
                                 'frac_hbm': round(v['frac_hbm'], 5), 'algorithmic_bytes': v['alg_bytes'],
                                 'traffic': traffic.get(k)} for k, v in per_kernel.items()}}

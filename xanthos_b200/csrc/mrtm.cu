@@ -58,6 +58,13 @@ struct xan_mrtm_plan {
     int *d_edge_cons = nullptr;         // [n_edges] consuming warp
     int *d_progress = nullptr;          // [n_warps] chunks completed (reset per run)
     int *d_edge_cell = nullptr;         // [n_edges] cell whose flow the edge carries
+    struct SchedKey {
+        const double *flow_dist, *velocity;
+        double dt;
+        int blocks, wpb, group;
+    };
+    int *d_sched = nullptr;             // [grid warps] packed warp run by each grid warp (mrtm_sched_kernel), cached
+    SchedKey sched_key{};
     bool on_device = false;
 };
 
@@ -993,6 +1000,7 @@ static void free_device(xan_mrtm_plan *pl) {
     cudaFree(pl->d_edge_cons);
     cudaFree(pl->d_progress);
     cudaFree(pl->d_edge_cell);
+    if (pl->d_sched) cudaFree(pl->d_sched);
 }
 
 template <typename V>
@@ -1162,17 +1170,28 @@ static int launch_warp_t(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, int
     a.ring_buf = ring;
     a.dbg = nullptr;
     a.sched = nullptr;
-    int *d_sched = nullptr;
     const char *esch = getenv("XANTHOS_MRTM_SCHED");   // static | spread (no variant grouping) | grouped (default)
     if (!(esch && !strcmp(esch, "static")) && wpb % 4 == 0 && pl->n_warps <= 12288) {
         // one block per SM on every SM: the slots the packed warps do not need stay empty beside the expensive warps
         if (per_sm == 1 && wpb >= 16) blocks = std::max(blocks, sms);
-        XAN_CUDA_CHECK(scratch_alloc(&d_sched, sizeof(int) * (size_t)blocks * wpb, s));
-        mrtm_sched_kernel<<<1, 1024, sizeof(int) * pl->n_warps, s>>>(
-            a.lane_cell, a.lane_gedge, a.lane_oedge, a.lane_meta, pl->d_edge_cell, a.flow_dist, a.velocity, a.dt,
-            pl->n_warps, blocks, wpb, (esch && !strcmp(esch, "spread")) ? 0 : 1, d_sched);
-        XAN_CUDA_CHECK(cudaGetLastError());
-        a.sched = d_sched;
+        // The table depends on the topology and on which cells have dt V / L > 1; it is kept with the plan and
+        // rebuilt when the static arrays, dt or the launch geometry change (a stale table costs time, never results).
+        const int group = (esch && !strcmp(esch, "spread")) ? 0 : 1;
+        const xan_mrtm_plan::SchedKey key{a.flow_dist, a.velocity, a.dt, blocks, wpb, group};
+        const xan_mrtm_plan::SchedKey &old = pl->sched_key;
+        if (!pl->d_sched || old.flow_dist != key.flow_dist || old.velocity != key.velocity || old.dt != key.dt ||
+            old.blocks != key.blocks || old.wpb != key.wpb || old.group != key.group) {
+            // the previous table may still be read by a kernel in flight on another stream: stream-ordered free
+            if (pl->d_sched) XAN_CUDA_CHECK(cudaFreeAsync(pl->d_sched, s));
+            pl->d_sched = nullptr;
+            XAN_CUDA_CHECK(scratch_alloc(&pl->d_sched, sizeof(int) * (size_t)blocks * wpb, s));
+            mrtm_sched_kernel<<<1, 1024, sizeof(int) * pl->n_warps, s>>>(
+                a.lane_cell, a.lane_gedge, a.lane_oedge, a.lane_meta, pl->d_edge_cell, a.flow_dist, a.velocity, a.dt,
+                pl->n_warps, blocks, wpb, group, pl->d_sched);
+            XAN_CUDA_CHECK(cudaGetLastError());
+            pl->sched_key = key;
+        }
+        a.sched = pl->d_sched;
     }
     if (getenv("XANTHOS_MRTM_DEBUG")) XAN_CUDA_CHECK(scratch_alloc(&a.dbg, sizeof(long long) * 6 * pl->n_warps, s));
     void *kargs[] = {(void *)&a};
@@ -1191,7 +1210,6 @@ static int launch_warp_t(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, int
         }
         XAN_CUDA_CHECK(cudaFreeAsync(a.dbg, s));
     }
-    if (d_sched) XAN_CUDA_CHECK(cudaFreeAsync(d_sched, s));
     XAN_CUDA_CHECK(cudaFreeAsync(ring, s));
     return XAN_OK;
 }
