@@ -338,6 +338,53 @@ def run_ours(args, rank, world_size, local_rank):
                          'distances D2H inside the timing; forcing resident'}
         del ev, pet_f
 
+    # ---- post-processing scans on the resident runoff: drought thresholds + statistics,
+    # basin aggregation.  Device time per call, algorithmic bytes, and the numpy port beside it (rank 0, N = 1).
+    postproc = None
+    if not args.no_calib:
+        from xanthos_b200.drought import drought_stats as dr
+        from xanthos_b200.diagnostics import time_series as tsm
+        qf = device_step()[1]['q']                                  # Field [nmonths][ld]
+        thr = dr.getthresh_device(qf.t, ncell, 12)
+
+        def ev_ms(fn, reps=5):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        ms_thr = ev_ms(lambda: dr.getthresh_device(qf.t, ncell, 12))
+        ms_sid = ev_ms(lambda: dr.droughtstats_device(qf.t, ncell, thr))
+        ms_grp = ev_ms(lambda: tsm.group_sum_device(world.basin_ids, qf.t))
+        cmf = float(ncell) * nmonths
+        postproc = {'drought_stats': {'ms': ms_sid, 'algorithmic_bytes': 32 * cmf,
+                                      'achieved_gbs': 32 * cmf / (ms_sid * 1e-3) / 1e9},
+                    'drought_thresholds': {'ms': ms_thr, 'algorithmic_bytes': 8 * cmf + 8 * 12 * ncell,
+                                           'achieved_gbs': (8 * cmf + 96 * ncell) / (ms_thr * 1e-3) / 1e9},
+                    'basin_group_sum': {'ms': ms_grp, 'algorithmic_bytes': 8 * cmf,
+                                        'achieved_gbs': 8 * cmf / (ms_grp * 1e-3) / 1e9,
+                                        'note': 'includes the host-side group plan and its upload'},
+                    'cell_months_per_s': cmf / ((ms_thr + ms_sid + ms_grp) * 1e-3)}
+        if world_size == 1 and not args.no_cpu_baseline:
+            from oracle import postproc as opp
+            qh = qf.t[:, :ncell].cpu().numpy()                      # [ntime, ngrid]
+            t0 = time.perf_counter()
+            thr_h = opp.getthresh(qh, 12)
+            opp.droughtstats(qh, thr_h)
+            t1 = time.perf_counter()
+            sub = slice(0, min(ncell, 4000))                        # the reference's double loop is O(ncell x ntime) Python
+            opp.aggregation_map(np.asarray(world.basin_ids)[sub], np.ascontiguousarray(qh.T[sub]))
+            t2 = time.perf_counter()
+            t_cpu = (t1 - t0) + (t2 - t1) * ncell / (sub.stop - sub.start)
+            postproc['cpu_port'] = {'cell_months_per_s': cmf / t_cpu, 'cores': 1,
+                                    'sample': 'thresholds + statistics on all cells; aggregation on %d cells, '
+                                              'extrapolated linearly' % (sub.stop - sub.start)}
+        del qf, thr
+
     cm = float(ncell) * nmonths
     ms_step = dev_ms / args.steps
     value = world_size * cm / (ms_step * 1e-3)
@@ -402,6 +449,10 @@ def run_ours(args, rank, world_size, local_rank):
     }
     if calib is not None:
         line['calib'] = calib
+    if postproc is not None:
+        for k in ('drought_stats', 'drought_thresholds', 'basin_group_sum'):
+            postproc[k]['frac_hbm'] = postproc[k]['achieved_gbs'] / peaks['hbm_gbs']
+        line['postproc'] = postproc
     if world_size == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(world, pm, ab, end_yr, budget_s=args.cpu_budget)
         if calib is not None:

@@ -214,6 +214,30 @@ int xan_agg_to_year(const double *d_src, double *d_dst, int ncell, int nmonths, 
 int xan_basin_sum(const xan_abcd_plan *plan, const double *d_src, const double *d_w,
                   int nmonths, int ld, double *d_out, void *stream);
 
+/* ---- post-processing scans on the resident fields -------------- */
+/* DroughtStats.droughtstats (xanthos/drought/drought_stats.py:85-148): d_hydro [nmonths][ld],
+ * d_thresh [nthresh][ld_thresh] (row t % nthresh applies to month t) -> severity, intensity,
+ * duration [nmonths][ld].  Bit-identical to the numpy loop. */
+int xan_drought_stats(const double *d_hydro, const double *d_thresh, int ncell, int nmonths, int ld,
+                      int nthresh, int ld_thresh, double *d_severity, double *d_intensity,
+                      double *d_duration, void *stream);
+/* DroughtStats.getthresh (drought_stats.py:150-171): numpy.percentile(..., method "linear") over the
+ * ntime / nper samples of every (period, cell); the caller passes numpy's virtual index
+ * ((n - 1) q, split into floor and fraction).  d_out [nper][ld_out]. */
+int xan_drought_thresholds(const double *d_hist, int ncell, int ntime, int ld, int nper,
+                           int prev_index, double gamma, double *d_out, int ld_out, void *stream);
+/* Aggregation_Map (xanthos/diagnostics/time_series.py:126-138) / basin aggregation of
+ * AccessibleWater (xanthos/accessible/accessible.py:41-51): out[g][t] = sum over the cells of group g
+ * in ascending cell index of the non-NaN src[t][cell].  d_order = cells sorted (stable) by group,
+ * d_offsets [ngroups + 1] = group boundaries in d_order; cells with id <= 0 are left out by the
+ * caller.  d_out is [ngroups][ntime] (the reference's orientation). */
+int xan_group_sum(const double *d_src, const int *d_order, const int *d_offsets, int ngroups,
+                  int ntime, int ld, double *d_out, void *stream);
+/* accessible.py:34-39: dst[y][c] = numpy.sum(src[12 y .. 12 y + 11][c]) * scale[c] (scale may be
+ * NULL); a trailing partial year is dropped like int(nmonths / 12). */
+int xan_year_sum_scaled(const double *d_src, const double *d_scale, int ncell, int nmonths, int ld,
+                        double *d_dst, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

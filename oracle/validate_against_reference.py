@@ -222,6 +222,81 @@ def oracle_calibration(case, ref_out):
                                         ref_out['cal_obs']) for c in ref_out['cal_cand']])
 
 
+# ---- post-processing scans ------------------------------------------------------
+def build_postproc_case(ncell=211, n_groups=9, start_yr=1971, end_yr=2001, seed=41):
+    """Runoff-like [ncell, nmonths] field with NaN cells, all-zero cells and dry spells; group ids with 0 (= no
+    group); basin tables of the accessible-water chain."""
+    rng = np.random.default_rng(seed)
+    nmonths = (end_yr - start_yr + 1) * 12
+    season = 1.0 + 0.6 * np.sin(2 * np.pi * (np.arange(nmonths) % 12) / 12.0)
+    hydro = np.abs(rng.normal(50.0, 40.0, (ncell, nmonths))) * season
+    hydro[7, :] = 0.0                                   # threshold 0 -> (th - h) / th = nan / inf branches
+    hydro[9, 250:290] = 0.0                             # a long drought after the reference period
+    hydro[2, 5] = np.nan                                # NaN in the reference period of one (period, cell)
+    hydro[11, :] = np.nan
+    ids = rng.integers(0, n_groups + 1, ncell)
+    ids[:n_groups] = np.arange(1, n_groups + 1)         # every group occurs
+    ids[3 + n_groups] = 0
+    return dict(ncell=ncell, nmonths=nmonths, start_yr=start_yr, end_yr=end_yr, hydro=hydro, ids=ids,
+                area=rng.uniform(500.0, 3000.0, ncell), bfi=rng.uniform(0.1, 0.9, n_groups),
+                res_capacity=rng.uniform(0.0, 50.0, (n_groups, 1)), thr_start=start_yr + 4, thr_end=start_yr + 19,
+                hist_end=start_yr + 19, gcam_start=start_yr + 4, gcam_end=end_yr - 1, gcam_step=5, window=9,
+                env_flow=0.1)
+
+
+def run_reference_postproc(case):
+    """The reference's own drought / aggregation / accessible-water functions on the case."""
+    ref_loader.load()
+    import xanthos.drought.drought_stats as ds
+    import xanthos.accessible.accessible as acc
+    import xanthos.diagnostics.time_series as ts
+    from types import SimpleNamespace
+    h = case['hydro'].T                                  # [ntime, ngrid] as DroughtStats.__init__ passes it
+    out = {}
+    for nper in (1, 12):
+        st = SimpleNamespace(threshold_start_year=case['thr_start'], threshold_end_year=case['thr_end'],
+                             StartYear=case['start_yr'], threshold_nper=nper)
+        thr = ds.DroughtStats.calculate_thresholds(h, st)
+        out['thr%d' % nper] = thr
+        with np.errstate(all='ignore'):
+            S, I, D = ds.DroughtStats.droughtstats(None, h, thr)
+        out['sev%d' % nper], out['int%d' % nper], out['dur%d' % nper] = S, I, D
+    out['aggmap'] = ts.Aggregation_Map(case['ids'], case['hydro'])
+    s = SimpleNamespace(StartYear=case['start_yr'], EndYear=case['end_yr'], GCAM_StartYear=case['gcam_start'],
+                        GCAM_EndYear=case['gcam_end'], GCAM_YearStep=case['gcam_step'])
+    ny = int(case['nmonths'] / 12)
+    q = np.zeros((case['ncell'], ny))
+    for i in range(ny):                                  # accessible.py:34-39
+        q[:, i] = np.sum(case['hydro'][:, i * 12:(i + 1) * 12], axis=1) * (case['area'] / 1e6)
+    mr = ts.Aggregation_Map(case['ids'], q)              # same double loop as accessible.py:41-51
+    out['basin_annual'] = mr
+    qs = acc.RollingWindowFilter(mr, case['window'])
+    qg = acc.QInGCAMYears(qs, s)
+    bflow = np.transpose(np.transpose(qg) * case['bfi'])
+    hey = list(range(case['start_yr'], case['end_yr'] + 1)).index(case['hist_end'])
+    edf = case['env_flow'] * np.mean(mr[:, :(hey + 1)], axis=1)
+    out['accessible'] = acc.accessible_water(qg, bflow, edf, case['res_capacity'])
+    return out
+
+
+def run_oracle_postproc(case):
+    from . import postproc as P
+    h = case['hydro'].T
+    out = {}
+    for nper in (1, 12):
+        thr = P.calculate_thresholds(h, case['start_yr'], case['thr_start'], case['thr_end'], nper)
+        out['thr%d' % nper] = thr
+        out['sev%d' % nper], out['int%d' % nper], out['dur%d' % nper] = P.droughtstats(h, thr)
+    out['aggmap'] = P.aggregation_map(case['ids'], case['hydro'])
+    mr = P.aggregation_map(case['ids'], P.yearly_km3(case['hydro'], case['area']))
+    out['basin_annual'] = mr
+    out['accessible'] = P.accessible_water_chain(
+        mr, case['start_yr'], case['end_yr'], case['hist_end'],
+        list(range(case['gcam_start'], case['gcam_end'] + 1, case['gcam_step'])), case['window'], case['bfi'],
+        case['res_capacity'], case['env_flow'])
+    return out
+
+
 def compare(ref_out, ora_out, verbose=True):
     """Return {name: (bitwise_equal, max_rel_err)}."""
     res = {}
@@ -265,6 +340,13 @@ def main():
         for k in sorted(r):
             bit = np.array_equal(np.asarray(r[k]), np.asarray(o[k]), equal_nan=True)
             print("  stepwise {:18s} bitwise={}".format(k, bit))
+            ok &= bit
+    for kw in (dict(), dict(ncell=97, n_groups=5, start_yr=2006, end_yr=2050, seed=43)):
+        case = build_postproc_case(**kw)
+        r, o = run_reference_postproc(case), run_oracle_postproc(case)
+        for k in sorted(r):
+            bit = np.array_equal(np.asarray(r[k]), np.asarray(o[k]), equal_nan=True)
+            print("  postproc {:18s} bitwise={}".format(k, bit))
             ok &= bit
     print("ORACLE PINNED" if ok else "ORACLE MISMATCH")
     return 0 if ok else 1

@@ -9,7 +9,9 @@ Each fixture is a compressed .npz holding every input array of a parity case
 run_pmpet, hargreaves_samani.execute, thornthwaite.execute, abcd_execute
 (jobs=1, jobs=-1, no-snow), downstream / upstream / upstream_genmatrix,
 streamrouting driven like Components.calculate_routing, and objective_kge; case_c holds the
-step-wise path (hargreaves.calculate_pet, calc_sinusoidal_factor, gwam.runoffgen with its spin-up pass).
+step-wise path (hargreaves.calculate_pet, calc_sinusoidal_factor, gwam.runoffgen with its spin-up pass);
+case_d the post-processing scans (DroughtStats.calculate_thresholds / droughtstats, Aggregation_Map, the
+accessible-water chain).
 """
 
 import os
@@ -22,7 +24,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle import ref_loader  # noqa: E402
 from oracle.validate_against_reference import (build_case, run_reference, build_stepwise_case,  # noqa: E402
-                                               run_reference_stepwise)
+                                               run_reference_stepwise, build_postproc_case, run_reference_postproc)
 
 CASES = {
     # 3 years around the leap year 2000, spin-up = whole period
@@ -52,6 +54,14 @@ def main():
     path = os.path.join(HERE, 'case_c.npz')
     np.savez_compressed(path, **blob)
     print('case_c', '->', path, '{:.2f} MB'.format(os.path.getsize(path) / 1e6))
+    # post-processing scans (drought statistics, Aggregation_Map, accessible water), 1971-2001
+    case = build_postproc_case()
+    out = run_reference_postproc(case)
+    blob = {'in_' + k: np.asarray(v) for k, v in case.items()}
+    blob.update({'ref_' + k: np.asarray(v) for k, v in out.items()})
+    path = os.path.join(HERE, 'case_d.npz')
+    np.savez_compressed(path, **blob)
+    print('case_d', '->', path, '{:.2f} MB'.format(os.path.getsize(path) / 1e6))
 
 
 if __name__ == '__main__':

@@ -34,6 +34,18 @@ def test_stepwise_oracle_matches_golden_bitwise():
         assert bitwise_equal(v, ref[k]), k
 
 
+def test_postproc_oracle_matches_golden_bitwise():
+    """Drought statistics, Aggregation_Map and the accessible-water chain (tests/golden/case_d.npz, produced by the
+    reference's own functions)."""
+    from oracle.validate_against_reference import run_oracle_postproc
+    case, ref = load_golden("case_d")
+    out = run_oracle_postproc(case)
+    assert set(out) == set(ref)
+    for k, v in out.items():
+        assert bitwise_equal(v, ref[k]), k
+    assert np.isnan(ref['thr12']).any() and (ref['dur12'].max() > 12)      # the edge cases are really in the fixture
+
+
 def test_upstream_fast_equals_loop():
     case, ref = load_golden("case_a")
     a = omrtm.upstream_fast(case['coords'], ref['dsid'], case['nrow'], case['ncol'])

@@ -9,8 +9,9 @@ host arrays (as the reference's do) and leaves a device copy resident, so the ne
 from HBM.  Routing runs the reference's two month loops (components.py:273-294) as ONE kernel
 launch (`routing_mod.route`).
 
-Post-processing methods (drought, accessible water, hydropower, diagnostics, plots) are outside
-the hot path and are logged no-ops here.
+Post-processing: drought statistics, accessible water and the aggregated time series run on the
+resident fields; hydropower and the diagnostics against external data
+sets are outside the scope and are logged no-ops.
 """
 
 import logging
@@ -23,6 +24,9 @@ from .utils import general as helper
 from .calibrate import calibrate_abcd as calib_mod
 from .data_writer.out_writer import OutWriter
 from .data_reader.data_load import DataLoader
+from .drought.drought_stats import DroughtStats
+from .accessible.accessible import AccessibleWater
+from .diagnostics.time_series import TimeSeriesPlot
 
 pet_mod = None
 runoff_mod = None
@@ -253,10 +257,20 @@ class Components:
             logging.warning("---%s is not part of xanthos_b200 (post-processing, out of scope); skipped", name)
 
     def drought(self):
-        self._skipped(self.s.CalculateDroughtStats, 'Drought Statistics')
+        """Drought statistics on the resident fields (components.py:391-400)."""
+        if self.s.CalculateDroughtStats:
+            logging.info("---Start Drought Statistics:")
+            t0 = time.time()
+            DroughtStats(self.s, self.Q, self.Sav)
+            logging.info("---Drought Statistics has finished successfully: %s seconds ------" % (time.time() - t0))
 
     def accessible_water(self):
-        self._skipped(self.s.CalculateAccessibleWater, 'Accessible Water')
+        """Accessible water per basin (components.py:402-410)."""
+        if self.s.CalculateAccessibleWater:
+            logging.info("---Start Accessible Water:")
+            t0 = time.time()
+            AccessibleWater(self.s, self.data, self.Q)
+            logging.info("---Accessible Water has finished successfully: %s seconds ------" % (time.time() - t0))
 
     def hydropower_potential(self):
         self._skipped(self.s.CalculateHydropowerPotential, 'Hydropower Potential')
@@ -268,7 +282,12 @@ class Components:
         self._skipped(self.s.PerformDiagnostics, 'Diagnostics')
 
     def plots(self):
-        self._skipped(self.s.CreateTimeSeriesPlot, 'Time Series Plots')
+        """Aggregated series of components.py:476-484 (written as .csv; no matplotlib here)."""
+        if self.s.CreateTimeSeriesPlot:
+            logging.info("---Creating Time Series Plots:")
+            t0 = time.time()
+            TimeSeriesPlot(self.s, getattr(self, 'q', self.Q), getattr(self, 'ac', self.Avg_ChFlow), self.data)
+            logging.info("---Time Series have finished successfully: %s seconds ------" % (time.time() - t0))
 
     def output_simulation(self):
         """Write outputs (components.py:441-474)."""

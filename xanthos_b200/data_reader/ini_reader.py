@@ -88,6 +88,13 @@ class ConfigReader:
         elif routing_config:
             routing_config = False
         calibration_config = c.get('Calibrate', False)
+        drought_config = c.get('Drought', False)                       # ini_reader.py:85-88
+        acc_water_config = c.get('AccessibleWater', False)              # ini_reader.py:90-94
+        if acc_water_config and 'AccWatDir' in p:
+            self.AccWatDir = os.path.join(self.InputFolder, p['AccWatDir'])
+        elif acc_water_config:
+            acc_water_config = False
+        timeseries_config = c.get('TimeSeriesPlot', False)
 
         # project level settings (ini_reader.py:117-139)
         self.ncell = int(p.get('ncell', 67420))
@@ -126,8 +133,14 @@ class ConfigReader:
 
         self.configure_reference_data(ref)
 
-        for flag, name in ((self.PerformDiagnostics, 'Diagnostics'), (self.CreateTimeSeriesPlot, 'TimeSeriesPlot'),
-                           (self.CalculateDroughtStats, 'Drought'), (self.CalculateAccessibleWater, 'AccessibleWater'),
+        if drought_config and self.CalculateDroughtStats:
+            self.configure_drought_stats(drought_config)
+        if acc_water_config and self.CalculateAccessibleWater:
+            self.configure_acc_water(acc_water_config)
+        if timeseries_config and self.CreateTimeSeriesPlot:
+            self.configure_timeseries_plot(timeseries_config)
+
+        for flag, name in ((self.PerformDiagnostics, 'Diagnostics'),
                            (self.CalculateHydropowerPotential, 'HydropowerPotential'),
                            (self.CalculateHydropowerActual, 'HydropowerActual')):
             if flag:
@@ -306,6 +319,47 @@ class ConfigReader:
             self.CountryNames = os.path.join(self.Reference, 'country-names.csv')
         else:
             logging.warning('No reference data selected for use.')
+
+    def configure_drought_stats(self, drought_config):
+        """ini_reader.py:460-471."""
+        self.drought_var = drought_config['drought_var']
+        self.drought_thresholds = drought_config.get('drought_thresholds')  # optional
+        if self.drought_thresholds is None:
+            self.threshold_nper = int(drought_config['threshold_nper'])
+            self.threshold_start_year = int(drought_config['threshold_start_year'])
+            self.threshold_end_year = int(drought_config['threshold_end_year'])
+            if (self.StartYear > self.threshold_start_year) or (self.EndYear < self.threshold_end_year):
+                raise ValidationException("Drought threshold year range is outside the output year range.")
+
+    def configure_acc_water(self, acc_water_config):
+        """ini_reader.py:473-486."""
+        self.ResCapacityFile = os.path.join(self.AccWatDir, acc_water_config['ResCapacityFile'])
+        self.BfiFile = os.path.join(self.AccWatDir, acc_water_config['BfiFile'])
+        self.HistEndYear = int(acc_water_config['HistEndYear'])
+        self.GCAM_StartYear = self.ck_year(int(acc_water_config['GCAM_StartYear']))
+        self.GCAM_EndYear = int(acc_water_config['GCAM_EndYear'])
+        self.GCAM_YearStep = int(acc_water_config['GCAM_YearStep'])
+        self.MovingMeanWindow = int(acc_water_config['MovingMeanWindow'])
+        self.Env_FlowPercent = float(acc_water_config['Env_FlowPercent'])
+        if (self.StartYear > self.GCAM_StartYear) or (self.EndYear < self.GCAM_EndYear):
+            raise ValidationException("Accessible water range of GCAM years are outside "
+                                      "the range of years in climate data.")
+
+    def configure_timeseries_plot(self, timeseries_config):
+        """ini_reader.py:443-458."""
+        self.TimeSeriesScale = int(timeseries_config['Scale'])
+        self.TimeSeriesMapID = 999
+        try:
+            self.TimeSeriesMapID = int(timeseries_config['MapID'])
+        except TypeError:
+            self.TimeSeriesMapID = list(map(int, timeseries_config['MapID']))
+
+    def ck_year(self, yr):
+        """ini_reader.py:545-551."""
+        if (yr < self.StartYear) or (yr > self.EndYear):
+            raise ValidationException("Accessible water year {0} is outside the range of years in the climate "
+                                      "data ({1}-{2}).".format(yr, self.StartYear, self.EndYear))
+        return yr
 
     def configure_calibration(self, calibration_config):
         """ini_reader.py:504-519."""

@@ -75,12 +75,16 @@ class OutWriter:
             filename = os.path.join(self.out_folder, '{}_{}_{}'.format(var, unit, self.proj_name))
             self.write_data(filename, var, self.outputs[i], self.time_steps)
 
-    def write_data(self, filename, var, data, col_names=None):
+    def write_data(self, filename, var, data, col_names=None, index_base=1):
+        """index_base: first value of the id column (grid-cell outputs are 1-based, out_writer.py:123; the drought
+        module hands over a fresh DataFrame whose index starts at 0, drought_stats.py:60-63)."""
         if self.out_format == FORMAT_NPY:
             np.save(filename + '.npy', data)
         else:
+            if col_names is None:
+                col_names = [str(k) for k in range(data.shape[1])]
             header = 'id,' + ','.join(col_names)
-            ids = np.arange(1, data.shape[0] + 1)[:, None]
+            ids = np.arange(index_base, data.shape[0] + index_base)[:, None]
             np.savetxt(filename + '.csv', np.hstack([ids, data]), delimiter=',', header=header, comments='',
                        fmt=['%d'] + ['%.17g'] * data.shape[1])
 

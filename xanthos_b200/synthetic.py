@@ -408,11 +408,15 @@ def calibration_obs(basin_series, seed=4):
 # example project on disk (same file layout as the reference's example data)
 # --------------------------------------------------------------------------
 def write_example(root, world, start_yr, end_yr, pet='pm', routing=True, seed=1, runoff_spinup=None,
-                  routing_spinup=None, calibrate=False, output_vars='q,avgchflow', project='synthetic'):
+                  routing_spinup=None, calibrate=False, output_vars='q,avgchflow', project='synthetic',
+                  postproc=None):
     """
     Write a synthetic project under `root` in the file formats the loader reads
     (xanthos/data_reader/ini_reader.py:428-435, data_load.py:47-72, 92-135, 200-211) and return the
-    path of its .ini file plus the dict of in-memory inputs.
+    path of its .ini file plus the dict of in-memory inputs.  `postproc`: optional dict that switches the
+    post-processing modules on, e.g. {'drought': {'drought_var': 'q', 'threshold_nper': 12, 'threshold_start_year': ..,
+    'threshold_end_year': ..}, 'accessible_water': {'HistEndYear': .., 'GCAM_StartYear': .., 'GCAM_EndYear': ..,
+    'GCAM_YearStep': .., 'MovingMeanWindow': .., 'Env_FlowPercent': ..}} (ini_reader.py:460-486).
     """
     import os
     n, m = world.ncell, (end_yr - start_yr + 1) * 12
@@ -520,9 +524,27 @@ def write_example(root, world, start_yr, end_yr, pet='pm', routing=True, seed=1,
         'HistFlag = True', 'n_basins = {}'.format(world.n_basins), 'StartYear = {}'.format(start_yr),
         'EndYear = {}'.format(end_yr), 'output_vars = ' + output_vars, 'OutputFormat = 4', 'OutputUnit = 0',
         'OutputInYear = 0', 'AggregateRunoffBasin = 1', 'AggregateRunoffCountry = 0', 'AggregateRunoffGCAMRegion = 0',
-        'PerformDiagnostics = 0', 'CreateTimeSeriesPlot = 0', 'CalculateDroughtStats = 0',
-        'CalculateAccessibleWater = 0', 'CalculateHydropowerPotential = 0', 'CalculateHydropowerActual = 0',
+        'PerformDiagnostics = 0', 'CreateTimeSeriesPlot = 0',
+        'CalculateDroughtStats = {}'.format(int('drought' in (postproc or {}))),
+        'CalculateAccessibleWater = {}'.format(int('accessible_water' in (postproc or {}))),
+        'CalculateHydropowerPotential = 0', 'CalculateHydropowerActual = 0',
         'Calibrate = {}'.format(int(calibrate))]
+    if postproc and 'drought' in postproc:
+        lines += ['[Drought]'] + ['{} = {}'.format(k, v) for k, v in postproc['drought'].items()]
+    if postproc and 'accessible_water' in postproc:
+        adir = os.path.join(inp, 'accessible_water')
+        os.makedirs(adir, exist_ok=True)
+        rng = np.random.default_rng(seed + 77)
+        data['res_capacity'] = rng.uniform(0.0, 50.0, world.n_basins)
+        data['bfi'] = rng.uniform(0.1, 0.9, world.n_basins)
+        np.savetxt(os.path.join(adir, 'total_reservoir_storage_capacity_BM3.csv'), data['res_capacity'], fmt='%.17g')
+        with open(os.path.join(adir, 'bfi_per_basin.csv'), 'w') as f:
+            f.write('basin_id,bfi_avg\n')
+            for b in range(world.n_basins):
+                f.write('{},{:.17g}\n'.format(b + 1, data['bfi'][b]))
+        project_lines.append('AccWatDir = accessible_water')
+        lines += ['[AccessibleWater]', 'ResCapacityFile = total_reservoir_storage_capacity_BM3.csv',
+                  'BfiFile = bfi_per_basin.csv'] + ['{} = {}'.format(k, v) for k, v in postproc['accessible_water'].items()]
     if calibrate:
         lines += ['[Calibrate]', 'set_calibrate = 0', 'observed = ' + os.path.join(root, 'input', 'obs.csv'),
                   'obs_unit = km3_per_mth', 'calib_out_dir = ' + os.path.join(root, 'output', 'calib'),
