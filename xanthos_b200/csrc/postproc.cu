@@ -20,6 +20,8 @@ namespace xan {
 // Quirk kept: month 0 uses threshold row 0 and intensity == severity there (drought_stats.py:121-123);
 // later months use row t % K (:130).
 // ---------------------------------------------------------------------------------------------
+constexpr int DS_BATCH = 8;   // months loaded ahead of the scan (the scan itself is a dependent chain per cell)
+
 __global__ void __launch_bounds__(128)
     drought_stats_kernel(const double *__restrict__ hydro, const double *__restrict__ thresh, int ncell, int nmonths,
                          int ld, int ld_t, int nthresh, double *__restrict__ S, double *__restrict__ I,
@@ -27,23 +29,34 @@ __global__ void __launch_bounds__(128)
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncell) return;
     double s = 0.0, d = 0.0;
-    for (int t = 0; t < nmonths; ++t) {
-        const double h = ldg_stream(hydro + (size_t)t * ld + c);
-        const double th = thresh[(size_t)(t % nthresh) * ld_t + c];
-        const bool dry = h < th;                                  // false for NaN, like numpy
-        double it;
-        if (t == 0) {
-            d = dry ? 1.0 : 0.0;
-            s = dry ? (th - h) / th : 0.0;
-            it = s;
-        } else {
-            d = dry ? d + 1.0 : 0.0;
-            s = dry ? s + (th - h) / th : 0.0;
-            it = dry ? s / d : 0.0;
+    for (int t0 = 0; t0 < nmonths; t0 += DS_BATCH) {
+        double h[DS_BATCH], th[DS_BATCH];
+#pragma unroll
+        for (int k = 0; k < DS_BATCH; ++k) {                      // all loads of the batch in flight together
+            const int t = min(t0 + k, nmonths - 1);
+            h[k] = ldg_stream(hydro + (size_t)t * ld + c);
+            th[k] = thresh[(size_t)(t % nthresh) * ld_t + c];
         }
-        stg_stream(S + (size_t)t * ld + c, s);
-        stg_stream(I + (size_t)t * ld + c, it);
-        stg_stream(D + (size_t)t * ld + c, d);
+#pragma unroll
+        for (int k = 0; k < DS_BATCH; ++k) {
+            const int t = t0 + k;
+            if (t >= nmonths) break;
+            const bool dry = h[k] < th[k];                          // false for NaN, like numpy
+            const double deficit = (th[k] - h[k]) / th[k];          // off the chain: depends on the inputs only
+            double it;
+            if (t == 0) {
+                d = dry ? 1.0 : 0.0;
+                s = dry ? deficit : 0.0;
+                it = s;
+            } else {
+                d = dry ? d + 1.0 : 0.0;
+                s = dry ? s + deficit : 0.0;
+                it = dry ? s / d : 0.0;
+            }
+            stg_stream(S + (size_t)t * ld + c, s);
+            stg_stream(I + (size_t)t * ld + c, it);
+            stg_stream(D + (size_t)t * ld + c, d);
+        }
     }
 }
 
