@@ -681,7 +681,7 @@ __device__ __forceinline__ void run_block_nt(bool has_ghost, bool has_out, LaneS
 __global__ void mrtm_sched_kernel(const int *lane_cell, const int *lane_gedge, const int *lane_oedge,
                                   const unsigned *lane_meta, const int *edge_cell, const double *flow_dist,
                                   const double *velocity, double dt, int n_warps, int n_blocks, int wpb, int group,
-                                  int *assign) {
+                                  int exp_per_sp, int *assign) {
     extern __shared__ int s_key[];   // [n_warps]
     for (int i = threadIdx.x; i < n_blocks * wpb; i += blockDim.x) assign[i] = -1;
     for (int w = threadIdx.x; w < n_warps; w += blockDim.x) {
@@ -699,7 +699,7 @@ __global__ void mrtm_sched_kernel(const int *lane_cell, const int *lane_gedge, c
             out = out || lane_oedge[g] >= 0;
             if (c >= 0) expensive = expensive || (velocity[c] / flow_dist[c]) * dt > 1.0;
         }
-        const int variant = group ? (nt * 4 + (ghost ? 2 : 0) + (out ? 1 : 0)) : 0;
+        const int variant = (group & 1) ? (nt * 4 + (ghost ? 2 : 0) + (out ? 1 : 0)) : 0;
         s_key[w] = (expensive ? 0 : 1 << 16) | variant;
     }
     __syncthreads();
@@ -712,23 +712,29 @@ __global__ void mrtm_sched_kernel(const int *lane_cell, const int *lane_gedge, c
             r += (kv < key || (kv == key && v < w)) ? 1 : 0;
             nE += (kv < (1 << 16)) ? 1 : 0;
         }
-        const int nEp = min(nE, 4 * B);
-        // companions of an expensive warp: as few as the grid allows (spare slots stay beside the expensive warps)
-        int c = S - 1;
-        while (c > 0 && nEp * (c - 1) + (4 * B - nEp) * S >= n_warps - nEp) --c;
-        int q, blk, pos;
-        if (r < nEp) {
-            q = r / B; blk = r % B; pos = 0;
+        // EP expensive warps share a sub-partition (slots 0 .. EP - 1); they get as few companions as the grid allows
+        // (the spare slots of the grid stay beside them); sub-partition k is (block k % B, quarter k / B): spread over SMs
+        const int EP = max(1, min(exp_per_sp, S));
+        const int nEx = min(nE, EP * 4 * B);              // expensive warps placed as such (the rest counts as cheap)
+        const int nEsp = (nEx + EP - 1) / EP;             // sub-partitions they occupy
+        // slot sequence: A = the EP expensive slots of the first nEsp sub-partitions, B = c companion slots beside
+        // them, C = the other sub-partitions; the warp of rank r (expensive first, then by loop variant) takes slot r
+        const int nA = nEsp * EP;
+        int c = S - EP;
+        while (c > 0 && nA + nEsp * (c - 1) + (4 * B - nEsp) * S >= n_warps) --c;
+        int k, pos;
+        if (r < nA) {
+            k = r / EP; pos = r % EP;
         } else {
-            const int j = r - nEp, cap1 = c * nEp;
+            const int j = r - nA, cap1 = c * nEsp;
             if (j < cap1) {
-                const int k = j / c;
-                q = k / B; blk = k % B; pos = 1 + j % c;
+                k = j / c; pos = EP + j % c;
             } else {
-                const int jj = j - cap1, t = nEp + jj / S;
-                q = t / B; blk = t % B; pos = jj % S;
+                const int jj = j - cap1;
+                k = nEsp + jj / S; pos = jj % S;
             }
         }
+        const int q = k / B, blk = k % B;
         assign[blk * wpb + q + 4 * pos] = w;
     }
 }
@@ -1176,7 +1182,9 @@ static int launch_warp_t(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, int
         if (per_sm == 1 && wpb >= 16) blocks = std::max(blocks, sms);
         // The table depends on the topology and on which cells have dt V / L > 1; it is kept with the plan and
         // rebuilt when the static arrays, dt or the launch geometry change (a stale table costs time, never results).
-        const int group = (esch && !strcmp(esch, "spread")) ? 0 : 1;
+        const char *eep = getenv("XANTHOS_MRTM_EXP_PER_SP");
+        const int exp_per_sp = eep ? std::max(1, atoi(eep)) : 1;
+        const int group = ((esch && !strcmp(esch, "spread")) ? 0 : 1) | (exp_per_sp << 8);
         const xan_mrtm_plan::SchedKey key{a.flow_dist, a.velocity, a.dt, blocks, wpb, group};
         const xan_mrtm_plan::SchedKey &old = pl->sched_key;
         if (!pl->d_sched || old.flow_dist != key.flow_dist || old.velocity != key.velocity || old.dt != key.dt ||
@@ -1187,7 +1195,7 @@ static int launch_warp_t(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, int
             XAN_CUDA_CHECK(scratch_alloc(&pl->d_sched, sizeof(int) * (size_t)blocks * wpb, s));
             mrtm_sched_kernel<<<1, 1024, sizeof(int) * pl->n_warps, s>>>(
                 a.lane_cell, a.lane_gedge, a.lane_oedge, a.lane_meta, pl->d_edge_cell, a.flow_dist, a.velocity, a.dt,
-                pl->n_warps, blocks, wpb, group, pl->d_sched);
+                pl->n_warps, blocks, wpb, group, exp_per_sp, pl->d_sched);
             XAN_CUDA_CHECK(cudaGetLastError());
             pl->sched_key = key;
         }
