@@ -599,6 +599,24 @@ def run_reference(args, rank, world_size):
     print(json.dumps(line), flush=True)
 
 
+def _bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the CPUs next to its GPU, so that its pinned host buffers are allocated on that NUMA node and
+    the per-step H2D / D2H copies of the end-to-end leg do not cross the socket link (best effort)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        ideal = {64 * i + b for i, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = ideal & allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -620,6 +638,8 @@ def main():
         run_reference(args, rank, world_size)
         return
     if world_size > 1:
+        os.environ['NCCL_DEBUG'] = os.environ.get('XANTHOS_NCCL_DEBUG', 'WARN')    # stdout carries ONE JSON line
+        _bind_to_gpu_numa_node(local_rank)
         import torch
         import torch.distributed as dist
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')

@@ -671,17 +671,19 @@ __device__ __forceinline__ void run_block_nt(bool has_ghost, bool has_out, LaneS
 // w, up to 7 of them met on one SM and 3 in one SM sub-partition, where they share one issue port.
 // A block is 16 warps = one SM (1 block per SM by registers), warp i of a block runs in sub-partition
 // i & 3, so the table assign[grid warp] -> packed warp decides who shares an issue port:
-//   * the expensive warps go one per sub-partition, spread over all SMs, in slot 0 of their sub-partition;
-//   * the others are sorted by loop variant (row length NT, ghost lanes, cut-edge output) and fill the
-//     sub-partitions in runs of consecutive entries, so that the warps of a sub-partition execute the
-//     same copy of the sub-step loop (instruction cache) - the cheapest variants beside the expensive warps.
+//   * the expensive warps go two per sub-partition and sub-partition by sub-partition onto whole SMs (8 per SM,
+//     ~40 SMs here) with no other warp beside them: what slows them is the SM-wide shuffle (LSU) pipe and the issue
+//     ports they would share with 15-18 cheap warps (XANTHOS_MRTM_EXP_PER_SP / XANTHOS_MRTM_PACK_SM change this);
+//   * the others are sorted by loop variant (row length NT, ghost lanes, cut-edge output) and fill the remaining
+//     sub-partitions in runs of consecutive entries, so that the warps of a sub-partition execute the same copy of
+//     the sub-step loop (6 KB L0 instruction cache); the spare slots of the grid stay beside the expensive warps.
 // The arithmetic of a packed warp does not depend on where it runs: results are bit-identical.
 // One block, thread = packed warp; ranks by counting (n_warps <= 148 x 16 because all warps are co-resident).
 // ---------------------------------------------------------------------------------------------
 __global__ void mrtm_sched_kernel(const int *lane_cell, const int *lane_gedge, const int *lane_oedge,
                                   const unsigned *lane_meta, const int *edge_cell, const double *flow_dist,
                                   const double *velocity, double dt, int n_warps, int n_blocks, int wpb, int group,
-                                  int exp_per_sp, int *assign) {
+                                  int exp_per_sp, int pack_sm, int *assign) {
     extern __shared__ int s_key[];   // [n_warps]
     for (int i = threadIdx.x; i < n_blocks * wpb; i += blockDim.x) assign[i] = -1;
     for (int w = threadIdx.x; w < n_warps; w += blockDim.x) {
@@ -734,7 +736,8 @@ __global__ void mrtm_sched_kernel(const int *lane_cell, const int *lane_gedge, c
                 k = nEsp + jj / S; pos = jj % S;
             }
         }
-        const int q = k / B, blk = k % B;
+        // sub-partition k -> (block, quarter): spread over the SMs (quarter-major), or SM by SM (pack_sm)
+        const int q = pack_sm ? k % 4 : k / B, blk = pack_sm ? k / 4 : k % B;
         assign[blk * wpb + q + 4 * pos] = w;
     }
 }
@@ -1183,8 +1186,10 @@ static int launch_warp_t(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, int
         // The table depends on the topology and on which cells have dt V / L > 1; it is kept with the plan and
         // rebuilt when the static arrays, dt or the launch geometry change (a stale table costs time, never results).
         const char *eep = getenv("XANTHOS_MRTM_EXP_PER_SP");
-        const int exp_per_sp = eep ? std::max(1, atoi(eep)) : 1;
-        const int group = ((esch && !strcmp(esch, "spread")) ? 0 : 1) | (exp_per_sp << 8);
+        const int exp_per_sp = eep ? std::max(1, atoi(eep)) : 2;
+        const char *epk = getenv("XANTHOS_MRTM_PACK_SM");
+        const int pack_sm = epk ? atoi(epk) : 1;
+        const int group = ((esch && !strcmp(esch, "spread")) ? 0 : 1) | (exp_per_sp << 8) | (pack_sm << 16);
         const xan_mrtm_plan::SchedKey key{a.flow_dist, a.velocity, a.dt, blocks, wpb, group};
         const xan_mrtm_plan::SchedKey &old = pl->sched_key;
         if (!pl->d_sched || old.flow_dist != key.flow_dist || old.velocity != key.velocity || old.dt != key.dt ||
@@ -1195,7 +1200,7 @@ static int launch_warp_t(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, int
             XAN_CUDA_CHECK(scratch_alloc(&pl->d_sched, sizeof(int) * (size_t)blocks * wpb, s));
             mrtm_sched_kernel<<<1, 1024, sizeof(int) * pl->n_warps, s>>>(
                 a.lane_cell, a.lane_gedge, a.lane_oedge, a.lane_meta, pl->d_edge_cell, a.flow_dist, a.velocity, a.dt,
-                pl->n_warps, blocks, wpb, group, exp_per_sp, pl->d_sched);
+                pl->n_warps, blocks, wpb, group, exp_per_sp, pack_sm, pl->d_sched);
             XAN_CUDA_CHECK(cudaGetLastError());
             pl->sched_key = key;
         }
