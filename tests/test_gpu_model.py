@@ -306,3 +306,24 @@ def test_full_size_properties():
         is_up[upid[sel, k] - 1] = True
     outflow = float((avg[~is_up] * secs[None, :]).sum())                       # everything else leaves the system
     assert abs(inflow - outflow - float(chs[:, -1].sum())) / inflow < 1e-10
+
+
+def test_npy_forcing_is_read_into_pinned_memory(tmp_path):
+    """SURVEY section 8 row f2: big float64 .npy inputs land in pinned host buffers (and are equal to np.load);
+    small or non-float64 files take the numpy path."""
+    import torch
+    from xanthos_b200.data_reader.data_load import load_npy_pinned, DataLoader
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=(3000, 400))
+    a[5, 7] = np.nan
+    np.save(tmp_path / 'big.npy', a)
+    b = DataLoader.load_data(str(tmp_path / 'big.npy'))
+    assert bitwise_equal(a, b) and torch.from_numpy(b).is_pinned()
+    np.save(tmp_path / 'small.npy', a[:10])
+    assert bitwise_equal(load_npy_pinned(str(tmp_path / 'small.npy')), a[:10])
+    np.save(tmp_path / 'ints.npy', np.arange(2_000_000).reshape(1000, 2000))
+    assert np.array_equal(load_npy_pinned(str(tmp_path / 'ints.npy')), np.arange(2_000_000).reshape(1000, 2000))
+    with open(tmp_path / 'cut.npy', 'wb') as f:
+        f.write(open(tmp_path / 'big.npy', 'rb').read()[:100000])
+    with pytest.raises(Exception):
+        load_npy_pinned(str(tmp_path / 'cut.npy'))

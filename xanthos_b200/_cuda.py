@@ -152,6 +152,15 @@ def torch_cuda():
     return torch
 
 
+def device_available():
+    """True when a CUDA device is present (used only to choose pinned host buffers for file input)."""
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
+    except Exception:
+        return False
+
+
 def stream_ptr():
     torch = torch_cuda()
     return c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -13,7 +13,36 @@ import os
 
 import numpy as np
 
+from .. import _cuda as C
 from .._cuda import ValidationException  # noqa: F401  (same role as data_load.py:24)
+
+
+def load_npy_pinned(fn):
+    """
+    np.load for the big [ncell, nmonths] float64 forcing files, read straight into a pinned host buffer of the
+    recycling pool: the later upload then runs at PCIe speed instead of through the
+    driver's pageable staging copy.  Anything else (small arrays, other dtypes, Fortran order, no CUDA device)
+    goes through numpy.load.
+    """
+    try:
+        with open(fn, 'rb') as f:
+            major, _ = np.lib.format.read_magic(f)
+            shape, fortran, dtype = (np.lib.format.read_array_header_1_0(f) if major == 1
+                                     else np.lib.format.read_array_header_2_0(f))
+            big = len(shape) == 2 and dtype == np.dtype('<f8') and not fortran and int(np.prod(shape)) >= (1 << 20)
+            if big and C.device_available():
+                arr = C.host_pool.as_array(C.host_pool.acquire(shape))
+                view = memoryview(arr.reshape(-1)).cast('B')
+                got = 0
+                while got < len(view):
+                    k = f.readinto(view[got:])
+                    if not k:
+                        raise IOError("Error: File {} is truncated".format(fn))
+                    got += k
+                return arr
+    except (ValueError, OSError, AttributeError):
+        pass
+    return np.load(fn)
 
 
 class DataLoader:
@@ -172,7 +201,7 @@ class DataLoader:
         if not os.path.isfile(fn):
             raise IOError("Error: File does not exist:", fn)
         if fn.endswith('.npy'):
-            return np.load(fn)
+            return load_npy_pinned(fn)
         if fn.endswith('.txt'):
             try:
                 return np.genfromtxt(fn, delimiter=" ", skip_header=header_num, filling_values="0")
