@@ -2,18 +2,20 @@
 // -fmad=false: the routing results are BIT-IDENTICAL to the reference's scipy-CSR formulation.
 //
 // Host side  : integer topology (downstream / upstream / UM = UP - I), forest check, partition of
-//              every river tree into "pieces" of at most 32 lanes, levels, packing of pieces into warps.
+//              every river tree into "pieces" of at most 31 lanes, levels, packing of pieces into warps.
 // Device side:
 //   * mrtm_warp_kernel - warp-level dataflow, NO block- or grid-wide barrier anywhere in the time
-//     loop.  One warp owns one or more pieces (<= 32 cells + ghost lanes).  Channel storage S lives
-//     in a register of the owning lane for the whole run; the flows F of the warp's cells are
-//     exchanged through 512 B of shared memory with __syncwarp, and the reference's sparse
-//     "UM.dot(F)" is a <= 9-term gather from that buffer in ascending column order.  Water only
-//     moves downstream, so a cut edge between two pieces is a one-way dependency: the upstream
-//     warp runs ahead and streams the (F, F') series of its outlet cell into a small ring buffer
-//     in global memory (L2 resident), chunk by chunk; the downstream warp follows one chunk behind
-//     (acquire/release progress counters, back-pressure through the same counters).  The depth of
-//     the piece tree only adds a start-up lag of one chunk per level.
+//     loop.  One warp owns one or more pieces (<= 31 cells + ghost lanes, lane 31 stays empty).  Channel
+//     storage S lives in a register of the owning lane for the whole run; the flows F of the warp's cells
+//     never leave the register file: the reference's sparse "UM.dot(F)" is a gather of <= 9 row terms with
+//     64-bit shuffles in ascending column order (um_row).  Water only moves downstream, so a cut edge
+//     between two pieces is a one-way dependency: the upstream warp runs ahead and streams the (F, F')
+//     series of its outlet cell into a small ring buffer in global memory (L2 resident), month by month;
+//     the downstream warp follows one month behind and stages the series into shared memory with cp.async
+//     (acquire/release progress counters, back-pressure through the same counters).  The depth of the
+//     piece tree only adds a start-up lag of one month per level.
+//   * mrtm_sched_kernel - decides, once per plan, which packed warp runs on which SM sub-partition
+//     (expensive warps on SMs of their own, the others grouped by loop variant).
 //   * mrtm_grid_kernel - general fallback for graphs that are not forests: cooperative launch,
 //     two grid-wide syncs per sub-step, state in global memory.
 #include "common.cuh"
