@@ -327,3 +327,55 @@ def test_npy_forcing_is_read_into_pinned_memory(tmp_path):
         f.write(open(tmp_path / 'big.npy', 'rb').read()[:100000])
     with pytest.raises(Exception):
         load_npy_pinned(str(tmp_path / 'cut.npy'))
+
+
+def test_full_size_config2_hs_abcd_and_config3_hourly_routing():
+    """BASELINE.json configs[1] (Hargreaves-Samani PET + ABCD, no routing, 67,420 cells x 1,140 months, 2006-2100) and
+    configs[2] (routing only, hourly sub-steps) at full size: oracle on a sample of cells, and size-independent
+    properties (cells are independent in PET; a basin re-run reproduces its rows; warp kernel == grid kernel)."""
+    from types import SimpleNamespace
+    from xanthos_b200 import synthetic, _cuda as C
+    from xanthos_b200.pet import hargreaves_samani as hs
+    from xanthos_b200.runoff import abcd
+    from xanthos_b200.routing import mrtm
+    from xanthos_b200.utils.general import set_month_arrays
+    from oracle import pet as opet
+    w = synthetic.make_world(seed=0)
+    sy, ey = 2006, 2100
+    m = (ey - sy + 1) * 12
+    assert m == 1140
+    d = synthetic.hs_inputs(w, sy, ey, seed=2)
+    cfg = SimpleNamespace(StartYear=sy, EndYear=ey)
+    pet = hs.execute(cfg, SimpleNamespace(coords=w.coords, **d))
+    assert pet.shape == (w.ncell, m)
+    sample = np.random.default_rng(0).choice(w.ncell, 700, replace=False)
+    want = opet.hs_pet(d['hs_tas'][sample], d['hs_tmax'][sample], d['hs_tmin'][sample], w.coords[sample, 2], sy, ey)
+    assert max_rel(pet[sample], want, floor=1e-6) < RTOL
+    cold = d['hs_tas'] < 0
+    assert (pet[cold] == 0).all() and (pet[~cold & ~np.isnan(d['hs_tas'])] >= 0).all()          # hargreaves_samani.py:60
+    assert np.array_equal(np.isnan(pet), np.isnan(d['hs_tas']))
+    part = hs.execute(cfg, SimpleNamespace(coords=w.coords[sample], hs_tas=d['hs_tas'][sample],
+                                           hs_tmax=d['hs_tmax'][sample], hs_tmin=d['hs_tmin'][sample]))
+    assert bitwise_equal(part, pet[sample])                                                      # cells are independent
+    del part, want
+    ab = synthetic.abcd_inputs(w, m, seed=2, with_pet=False)
+    tmin = np.nan_to_num(ab['tmin'])
+    petz = np.nan_to_num(pet)
+    _, aet, q, sav = abcd.abcd_execute(w.n_basins, w.basin_ids, petz, ab['precip'], tmin, ab['pars'], m, 120, -1)
+    ok = ~np.isnan(ab['precip']).any(axis=1)
+    assert q.shape == (w.ncell, m) and np.isfinite(q[ok]).all() and (q[ok] >= 0).all()
+    assert (aet[ok] >= 0).all() and (aet[ok] <= petz[ok] + 1e-12).all()
+    b = 101
+    idx = np.where(w.basin_ids == b)[0]
+    _, aet_b, q_b, _ = abcd.abcd_execute(1, np.full(len(idx), b), petz[idx], ab['precip'][idx], tmin[idx], ab['pars'],
+                                         m, 120, -1)
+    assert bitwise_equal(q_b, q[idx]) and bitwise_equal(aet_b, aet[idx])
+    # configs[2]: hourly sub-steps (dt = 3600 s) on the full river network, warp kernel == grid kernel bit for bit
+    s = w.settings()
+    um = mrtm.upstream_genmatrix(mrtm.upstream(w.coords, mrtm.downstream(w.coords, w.flow_dir, s), s))
+    nd = set_month_arrays(m, sy, ey)[:, 2]
+    qq = np.ascontiguousarray(np.nan_to_num(q[:, :6]))
+    a = mrtm.route(um, qq, w.flow_dist, w.velocity, w.area, nd[:6], 3600.0, 2, method=C.MRTM_TREE)
+    g = mrtm.route(um, qq, w.flow_dist, w.velocity, w.area, nd[:6], 3600.0, 2, method=C.MRTM_GRID)
+    for x, y in zip(a, g):
+        assert bitwise_equal(x, y)
