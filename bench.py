@@ -409,7 +409,7 @@ def run_ours(args, rank, world_size, local_rank):
     # DRAM traffic per launch from the committed ncu --set full capture of the same workload (profiles/)
     traffic = {}
     try:
-        with open(os.path.join(ROOT, 'profiles', 'r01b_traffic.json')) as f:
+        with open(os.path.join(ROOT, 'profiles', 'r01c_traffic.json')) as f:
             tk = json.load(f)['kernels']
         if (ncell, nmonths) == (NCELL, NMONTHS):
             traffic = {'pm_pet_kernel': tk['pm_pet_fast_kernel']['dram_bytes_per_launch'],
@@ -421,7 +421,7 @@ def run_ours(args, rank, world_size, local_rank):
     dom = max(per_kernel, key=lambda k: per_kernel[k]['ms'])
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': per_kernel[dom]['gbs'], 'peak': peaks['hbm_gbs'],
                 'unit': 'GB/s', 'frac': per_kernel[dom]['frac_hbm'], 'traffic': traffic.get(dom),
-                'traffic_source': 'profiles/r01b_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)',
+                'traffic_source': 'profiles/r01c_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)',
                 'algorithmic_bytes': per_kernel[dom]['alg_bytes'], 'peak_source': peak_src,
                 'share_of_step': per_kernel[dom]['ms'] / sum(v['ms'] for v in per_kernel.values()),
                 'note': 'dominant kernel is bound by the latency of its sequential sub-step recurrence and by issue slots, not by HBM; see DESIGN.md',
