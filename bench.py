@@ -336,6 +336,30 @@ def run_ours(args, rank, world_size, local_rank):
                  / (max(cal_ms, cal_wall) / cal_steps * 1e-3),
                  'note': 'xan_abcd_kge_batch through BasinEvaluator.evaluate: parameters and observations H2D, '
                          'distances D2H inside the timing; forcing resident'}
+        # whole differential-evolution loop (objective + generation logic), device driver against host driver
+        gens = 12
+        robs_de = obs
+
+        def de_loop(driver):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if driver == 'device':
+                r = cal.differential_evolution_device(ev, bnums, robs_de, cal.BOUNDS_SNOW, popsize=13, maxiter=gens,
+                                                      tol=0.0, seed=4)
+            else:
+                r = cal.differential_evolution_batched(lambda x, idx: ev.evaluate(bnums[idx], x, robs_de[idx]),
+                                                       len(bnums), cal.BOUNDS_SNOW, popsize=13, maxiter=gens, tol=0.0,
+                                                       seed=4)
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0), int(r['nfev'].sum())
+        de_loop('device')
+        t_dev, nf_dev = de_loop('device')
+        t_host, nf_host = de_loop('host')
+        calib['de_loop'] = {'generations': gens, 'population': 65,
+                            'device_driver_param_sets_per_s': world_size * nf_dev / t_dev,
+                            'host_driver_param_sets_per_s': world_size * nf_host / t_host,
+                            'note': 'Latin-hypercube initialisation + %d generations for all basins; device driver = '
+                                    'xan_de_trial / xan_abcd_kge_batch / xan_de_select without host round trips' % gens}
         del ev, pet_f
 
     # ---- post-processing scans on the resident runoff: drought thresholds + statistics,

@@ -238,6 +238,32 @@ int xan_group_sum(const double *d_src, const int *d_order, const int *d_offsets,
 int xan_year_sum_scaled(const double *d_src, const double *d_scale, int ncell, int nmonths, int ld,
                         double *d_dst, void *stream);
 
+/* ---- differential evolution on the device ----------------------- */
+/* The generation logic of scipy.optimize.differential_evolution as calibrate_abcd.py:103-110 uses
+ * it (best1bin, Latin-hypercube init, dither, binomial crossover with one forced gene, out-of-bounds
+ * genes redrawn, deferred updating, convergence std(E) <= atol + tol |mean(E)|) for many independent
+ * problems in lock step.  d_pop [n_problems][pop_size][n_dims] holds scaled vectors in [0, 1],
+ * d_energy [n_problems][pop_size]; d_active [n_active] lists the problems a call works on (trial
+ * arrays are compact: [n_active][pop_size][...]).  Random numbers are Philox4x32-10 keyed by `seed`
+ * and indexed by (generation, problem, member): reproducible for any launch geometry.
+ *   xan_de_init    Latin hypercube
+ *   xan_de_trial   trial vectors of generation `generation` (>= 1): scaled (d_trial_x) and in parameter
+ *                  units lo + x * span with n_par_cols >= n_dims columns, the extra ones 0 (d_trial_par -
+ *                  what xan_abcd_kge_batch takes)
+ *   xan_de_select  keep trial where its energy <= the member's (NaN = +inf), then the convergence test:
+ *                  d_converged[problem] = generation at which it first held (-1: already at
+ *                  initialisation; 0: not yet); converged problems are frozen.  d_trial_x == NULL:
+ *                  only the test. */
+int xan_de_init(double *d_pop, int n_problems, int pop_size, int n_dims, unsigned long long seed,
+                void *stream);
+int xan_de_trial(const double *d_pop, const double *d_energy, const int *d_active, int n_active,
+                 int pop_size, int n_dims, int n_par_cols, const double *d_lo, const double *d_span,
+                 unsigned long long seed, int generation, double mutation_lo, double mutation_hi,
+                 double recombination, double *d_trial_x, double *d_trial_par, void *stream);
+int xan_de_select(double *d_pop, double *d_energy, const int *d_active, int n_active, int pop_size,
+                  int n_dims, const double *d_trial_x, const double *d_trial_energy, double tol,
+                  double atol, int generation, int *d_converged, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -379,3 +379,75 @@ def test_full_size_config2_hs_abcd_and_config3_hourly_routing():
     g = mrtm.route(um, qq, w.flow_dist, w.velocity, w.area, nd[:6], 3600.0, 2, method=C.MRTM_GRID)
     for x, y in zip(a, g):
         assert bitwise_equal(x, y)
+
+
+def test_device_differential_evolution_kernels_and_drivers():
+    """the DE generation logic on the device.  Kernel invariants (Latin hypercube, trial
+    vectors in [0, 1], best1bin structure, deferred selection, frozen converged problems), reproducibility, and the
+    device driver against the numpy driver on the same calibration problem."""
+    import ctypes
+    import torch
+    from xanthos_b200 import synthetic, _cuda as C
+    from xanthos_b200.calibrate import calibrate_abcd as cal
+    lib = C.lib()
+    n, S, D = 7, 50, 5
+    dev = dict(dtype=torch.float64, device='cuda')
+    pop = torch.empty((n, S, D), **dev)
+    C.check(lib.xan_de_init(C.ptr(pop), n, S, D, 12345, C.stream_ptr()))
+    p = pop.cpu().numpy()
+    assert (p >= 0).all() and (p < 1).all()
+    strata = np.sort(np.floor(p * S).astype(int), axis=1)                      # every stratum exactly once per dimension
+    assert (strata == np.arange(S)[None, :, None]).all()
+    pop2 = torch.empty_like(pop)
+    C.check(lib.xan_de_init(C.ptr(pop2), n, S, D, 12345, C.stream_ptr()))
+    assert torch.equal(pop, pop2)
+    # one generation on a known energy landscape
+    E = ((pop - 0.3) ** 2).sum(dim=2).contiguous()
+    act = torch.arange(n, dtype=torch.int32, device='cuda')
+    lo = torch.tensor([1e-4] * D, **dev)
+    span = torch.tensor([0.9998, 7.9998, 0.9998, 0.9998, 0.9998], **dev)
+    tx = torch.empty((n, S, D), **dev)
+    tp = torch.empty((n, S, 5), **dev)
+    C.check(lib.xan_de_trial(C.ptr(pop), C.ptr(E), C.ptr(act), n, S, D, 5, C.ptr(lo), C.ptr(span), 99, 1, 0.5, 1.0, 0.7,
+                             C.ptr(tx), C.ptr(tp), C.stream_ptr()))
+    t = tx.cpu().numpy()
+    assert (t >= 0).all() and (t <= 1).all()
+    assert np.allclose(tp.cpu().numpy(), lo.cpu().numpy() + t * span.cpu().numpy(), rtol=1e-15)
+    same = (t == p)                                                            # genes taken over from the parent
+    assert (~same).any(axis=2).all()                                           # at least one mutant gene per member
+    frac = 1 - same.mean()
+    assert 0.6 < frac < 0.9                                                    # ~ CR + (1 - CR) / D = 0.76
+    Et = ((tx - 0.3) ** 2).sum(dim=2).contiguous()
+    conv = torch.zeros(n, dtype=torch.int32, device='cuda')
+    conv[3] = 5                                                                # problem 3 has already converged: frozen
+    E0, P0 = E.clone(), pop.clone()
+    C.check(lib.xan_de_select(C.ptr(pop), C.ptr(E), C.ptr(act), n, S, D, C.ptr(tx), C.ptr(Et), 0.01, 0.0, 1, C.ptr(conv),
+                              C.stream_ptr()))
+    better = (Et <= E0)
+    better[3] = False
+    assert torch.equal(E, torch.where(better, Et, E0))
+    assert torch.equal(pop, torch.where(better[:, :, None], tx, P0))
+    assert conv.cpu().tolist()[3] == 5 and all(c == 0 for i, c in enumerate(conv.cpu().tolist()) if i != 3)
+    flat = torch.full((n, S), 2.0, **dev)                                      # equal energies: std = 0 -> converged
+    C.check(lib.xan_de_select(C.ptr(pop), C.ptr(flat), C.ptr(act), n, S, D, None, None, 0.01, 0.0, 7, C.ptr(conv),
+                              C.stream_ptr()))
+    assert conv.cpu().tolist() == [7, 7, 7, 5, 7, 7, 7]
+
+    # drivers: device against numpy on a small calibration problem with a known optimum
+    w = synthetic.make_world(24, 48, 320, 5, seed=41)
+    m = 48
+    ab = synthetic.abcd_inputs(w, m, seed=7)
+    tmin = np.nan_to_num(ab['tmin'])
+    ev = cal.BasinEvaluator(w.basin_ids, w.area, ab['precip'], ab['pet'], tmin, m, m, 'km3_per_mth')
+    bn = np.arange(1, w.n_basins + 1)
+    _, series = ev.evaluate(bn, ab['pars'][:, None, :], np.ones((w.n_basins, m)), want_series=True)
+    robs = series[:, 0, :]                                                     # noise-free: KGE = 1 at the truth
+    kw = dict(popsize=10, maxiter=120, tol=0.01, seed=11)
+    rd = cal.differential_evolution_device(ev, bn, robs, cal.BOUNDS_SNOW, **kw)
+    rd2 = cal.differential_evolution_device(ev, bn, robs, cal.BOUNDS_SNOW, check_every=9, **kw)
+    assert np.array_equal(rd['x'], rd2['x']) and np.array_equal(rd['fun'], rd2['fun']) and np.array_equal(rd['nit'], rd2['nit'])
+    rh = cal.differential_evolution_batched(lambda x, idx: ev.evaluate(bn[idx], x, robs[idx]), len(bn), cal.BOUNDS_SNOW, **kw)
+    assert (rd['fun'] < 0.05).all() and (rh['fun'] < 0.05).all(), (rd['fun'], rh['fun'])
+    ed = ev.evaluate(bn, rd['x'][:, None, :], robs)[:, 0]
+    assert np.allclose(ed, rd['fun'], rtol=1e-9, atol=1e-12)                   # reported energy = objective at the result
+    assert (rd['nfev'] == 50 * (1 + rd['nit'])).all() and (rd['nit'] <= 120).all()

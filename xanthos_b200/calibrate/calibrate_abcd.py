@@ -8,10 +8,12 @@ files, :20-131), `basin_runoff` (:134-173), `objective_kge` (:176-213), `process
 What changes is WHERE the objective is evaluated: one CUDA launch (`xan_abcd_kge_batch`) runs the
 full spin-up + simulation + basin aggregation + KGE distance for every (basin, candidate) pair of a
 differential-evolution generation, instead of one `ABCD.emulate()` per candidate.  The DE driver
-stays on the host and follows scipy.optimize.differential_evolution's defaults as used by the
-reference (best1bin, Latin-hypercube init, dither in [0.5, 1), recombination 0.7, tol 0.01,
-popsize 15 x n_params, maxiter 1000, no polish) with *deferred* updating, so that a whole
-generation is one batch; all basins of a call are advanced together.
+follows scipy.optimize.differential_evolution's defaults as used by the reference (best1bin,
+Latin-hypercube init, dither in [0.5, 1), recombination 0.7, tol 0.01, popsize 15 x n_params,
+maxiter 1000, no polish) with *deferred* updating, so that a whole generation is one batch; all
+basins of a call are advanced together.  Two drivers with the same semantics:
+`differential_evolution_device` (default; population and generation logic on the device, csrc/de.cu)
+and `differential_evolution_batched` (numpy, one host round trip per generation).
 
 Only the runoff target (`set_calibrate = 0`) is supported: the streamflow branch of the
 reference (:164-173) is broken.
@@ -60,19 +62,26 @@ class BasinEvaluator:
         nb, npar, k = pars.shape
         if k == 4:
             pars = np.concatenate([pars, np.zeros((nb, npar, 1))], axis=2)
-        rows, rp = C.as_c(np.asarray(basin_nums, dtype=np.int64) - 1, np.int32)
         d_pars = torch.from_numpy(np.ascontiguousarray(pars)).cuda()
         d_obs = torch.from_numpy(np.ascontiguousarray(obs, dtype=np.float64)).cuda()
-        d_ed = torch.empty((nb, npar), dtype=torch.float64, device='cuda')
         d_series = torch.empty((nb, npar, self.n_months), dtype=torch.float64, device='cuda') if want_series else None
+        ed = self.evaluate_device(basin_nums, d_pars, d_obs, d_series).cpu().numpy()
+        if want_series:
+            return ed, d_series.cpu().numpy()
+        return ed
+
+    def evaluate_device(self, basin_nums, d_pars, d_obs, d_series=None):
+        """The same with parameters [nb, P, 5] and observations [nb, n_months] already on the device (cuda tensors);
+        returns the KGE distances as a cuda tensor [nb, P].  Nothing is synchronised."""
+        torch = self._torch
+        nb, npar = int(d_pars.shape[0]), int(d_pars.shape[1])
+        rows, rp = C.as_c(np.asarray(basin_nums, dtype=np.int64) - 1, np.int32)
+        d_ed = torch.empty((nb, npar), dtype=torch.float64, device='cuda')
         C.check(C.lib().xan_abcd_kge_batch(self.plan._plan, rp, nb, npar, C.ptr(self.pet.t), C.ptr(self.precip.t),
                                            C.ptr(self.tmin.t if self.tmin is not None else None), C.ptr(self.area),
                                            C.ptr(d_pars), C.ptr(d_obs), self.n_months, self.spinup, self.pet.ld,
                                            self.unit_km3, C.ptr(d_ed), C.ptr(d_series), C.stream_ptr()))
-        ed = d_ed.cpu().numpy()
-        if want_series:
-            return ed, d_series.cpu().numpy()
-        return ed
+        return d_ed
 
 
 def differential_evolution_batched(evaluate, n_problems, bounds, popsize=15, maxiter=1000, tol=0.01, atol=0.0,
@@ -156,13 +165,79 @@ def differential_evolution_batched(evaluate, n_problems, bounds, popsize=15, max
     return dict(x=lo + pop[np.arange(n), b] * span, fun=E[np.arange(n), b], nit=nit, nfev=nfev)
 
 
+def differential_evolution_device(ev, basin_nums, robs, bounds, popsize=15, maxiter=1000, tol=0.01, atol=0.0,
+                                  mutation=(0.5, 1.0), recombination=0.7, seed=None, check_every=4):
+    """
+    The same solver with population, energies and generation logic on the device (xan_de_init / xan_de_trial /
+    xan_de_select, csrc/de.cu): a generation is trial kernel -> objective kernels -> selection kernel, and the host
+    only reads the convergence flags every `check_every` generations to drop finished basins from the batch (a
+    converged basin is frozen on the device at once, so the result does not depend on `check_every`).
+    ev: BasinEvaluator; robs [n, n_months].  Returns dict(x [n, D], fun [n], nit [n], nfev [n]).
+    """
+    torch = C.torch_cuda()
+    lib = C.lib()
+    bounds = np.asarray(bounds, dtype=float)
+    D = bounds.shape[0]
+    S = max(5, popsize * D)
+    n = len(basin_nums)
+    bn = np.asarray(basin_nums)
+    seed = int(np.random.SeedSequence(seed).generate_state(2, dtype=np.uint32).astype(np.uint64) @ np.array([1, 1 << 32], dtype=np.uint64))
+    dev = dict(dtype=torch.float64, device='cuda')
+    d_lo = torch.tensor(bounds[:, 0], **dev)
+    d_span = torch.tensor(bounds[:, 1] - bounds[:, 0], **dev)
+    d_obs = torch.from_numpy(np.ascontiguousarray(robs, dtype=np.float64)).cuda()
+    pop = torch.empty((n, S, D), **dev)
+    conv = torch.zeros(n, dtype=torch.int32, device='cuda')
+    C.check(lib.xan_de_init(C.ptr(pop), n, S, D, seed, C.stream_ptr()))
+    pars0 = torch.zeros((n, S, 5), **dev)
+    pars0[:, :, :D] = d_lo + pop * d_span
+    E = ev.evaluate_device(bn, pars0, d_obs)
+    act_h = np.arange(n, dtype=np.int32)
+    act = torch.from_numpy(act_h).cuda()
+    C.check(lib.xan_de_select(C.ptr(pop), C.ptr(E), C.ptr(act), n, S, D, None, None, float(tol), float(atol), 0,
+                              C.ptr(conv), C.stream_ptr()))
+    nfev = np.full(n, S)
+    nit = np.zeros(n, dtype=int)
+
+    def refresh_active():
+        c = conv.cpu().numpy()
+        return np.nonzero(c == 0)[0].astype(np.int32), c
+    act_h, c_h = refresh_active()
+    obs_a = d_obs
+    it = 0
+    while it < maxiter and len(act_h):
+        na = len(act_h)
+        act = torch.from_numpy(act_h).cuda()
+        obs_a = d_obs.index_select(0, act.long()) if na < n else d_obs
+        trial_x = torch.empty((na, S, D), **dev)
+        trial_p = torch.empty((na, S, 5), **dev)
+        for _ in range(min(check_every, maxiter - it)):
+            it += 1
+            C.check(lib.xan_de_trial(C.ptr(pop), C.ptr(E), C.ptr(act), na, S, D, 5, C.ptr(d_lo), C.ptr(d_span), seed, it,
+                                     float(mutation[0]), float(mutation[1]), float(recombination), C.ptr(trial_x),
+                                     C.ptr(trial_p), C.stream_ptr()))
+            Et = ev.evaluate_device(bn[act_h], trial_p, obs_a)
+            C.check(lib.xan_de_select(C.ptr(pop), C.ptr(E), C.ptr(act), na, S, D, C.ptr(trial_x), C.ptr(Et), float(tol),
+                                      float(atol), it, C.ptr(conv), C.stream_ptr()))
+        prev = act_h
+        act_h, c_h = refresh_active()
+        done_gen = np.where(c_h[prev] > 0, c_h[prev], it)          # generation at which each problem stopped
+        nit[prev] = done_gen
+        nfev[prev] = S * (1 + done_gen)
+    E_h = E.cpu().numpy()
+    pop_h = pop.cpu().numpy()
+    b = np.argmin(np.where(np.isnan(E_h), np.inf, E_h), axis=1)
+    return dict(x=bounds[:, 0] + pop_h[np.arange(n), b] * (bounds[:, 1] - bounds[:, 0]), fun=E_h[np.arange(n), b],
+                nit=nit, nfev=nfev)
+
+
 def _basin_obs(obs, basin_num, n_months):
     """Observed series of a basin (calibrate_abcd.py:88)."""
     return np.asarray(obs)[np.where(np.asarray(obs)[:, 0] == basin_num)][:n_months, 1]
 
 
 def calibrate_basins(basin_nums, basin_ids, basin_areas, precip, pet, obs, tmin, n_months, runoff_spinup, obs_unit,
-                     popsize=15, maxiter=1000, tol=0.01, seed=None, evaluator=None):
+                     popsize=15, maxiter=1000, tol=0.01, seed=None, evaluator=None, driver='device'):
     """
     Differential evolution for several basins at once.  Returns (pars [nb, 4 or 5], kge [nb], info).
     """
@@ -171,8 +246,11 @@ def calibrate_basins(basin_nums, basin_ids, basin_areas, precip, pet, obs, tmin,
     robs = np.stack([_basin_obs(obs, b, n_months) for b in basin_nums])
     bounds = BOUNDS_SNOW[:4] if ev.nosnow else BOUNDS_SNOW
     bn = np.asarray(basin_nums)
-    res = differential_evolution_batched(lambda x, idx: ev.evaluate(bn[idx], x, robs[idx]), len(basin_nums), bounds,
-                                         popsize=popsize, maxiter=maxiter, tol=tol, seed=seed)
+    if driver == 'host':       # numpy generation logic, one host round trip per generation
+        res = differential_evolution_batched(lambda x, idx: ev.evaluate(bn[idx], x, robs[idx]), len(basin_nums), bounds,
+                                             popsize=popsize, maxiter=maxiter, tol=tol, seed=seed)
+    else:
+        res = differential_evolution_device(ev, bn, robs, bounds, popsize=popsize, maxiter=maxiter, tol=tol, seed=seed)
     return res['x'], 1 - res['fun'], res
 
 
