@@ -662,7 +662,11 @@ def main():
         run_reference(args, rank, world_size)
         return
     if world_size > 1:
-        os.environ['NCCL_DEBUG'] = os.environ.get('XANTHOS_NCCL_DEBUG', 'WARN')    # stdout carries ONE JSON line
+        # stdout carries ONE JSON line: NCCL prints its version banner there at the VERSION and WARN levels
+        if 'XANTHOS_NCCL_DEBUG' in os.environ:
+            os.environ['NCCL_DEBUG'] = os.environ['XANTHOS_NCCL_DEBUG']
+        else:
+            os.environ.pop('NCCL_DEBUG', None)
         _bind_to_gpu_numa_node(local_rank)
         import torch
         import torch.distributed as dist
