@@ -391,7 +391,7 @@ def run_ours(args, rank, world_size, local_rank):
                                            'achieved_gbs': (8 * cmf + 96 * ncell) / (ms_thr * 1e-3) / 1e9},
                     'basin_group_sum': {'ms': ms_grp, 'algorithmic_bytes': 8 * cmf,
                                         'achieved_gbs': 8 * cmf / (ms_grp * 1e-3) / 1e9,
-                                        'note': 'includes the host-side group plan and its upload'},
+                                        'note': 'group plan (cells sorted by basin) cached on the device'},
                     'cell_months_per_s': cmf / ((ms_thr + ms_sid + ms_grp) * 1e-3)}
         if world_size == 1 and not args.no_cpu_baseline:
             from oracle import postproc as opp

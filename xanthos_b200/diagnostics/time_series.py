@@ -26,15 +26,31 @@ def group_plan(id_map):
     return order.astype(np.int32), offsets.astype(np.int32), nb
 
 
+_plans = {}   # id map (bytes digest) -> (device order, device offsets, NB): maps are few (basin, country, region)
+
+
+def _device_plan(id_map):
+    import hashlib
+    torch = C.torch_cuda()
+    ids = np.ascontiguousarray(np.asarray(id_map).astype(np.int64).reshape(-1))
+    key = (ids.shape[0], hashlib.blake2b(ids.tobytes(), digest_size=16).digest(), torch.cuda.current_device())
+    hit = _plans.get(key)
+    if hit is None:
+        order, offsets, nb = group_plan(ids)
+        hit = (torch.from_numpy(order).cuda(), torch.from_numpy(offsets).cuda(), nb)
+        if len(_plans) >= 16:
+            _plans.clear()
+        _plans[key] = hit
+    return hit
+
+
 def group_sum_device(id_map, t, ntime=None):
     """t: cuda tensor [ntime, ld] (time-major) -> cuda tensor [NB, ntime]."""
     torch = C.torch_cuda()
-    order, offsets, nb = group_plan(id_map)
+    d_order, d_off, nb = _device_plan(id_map)
     if nb < 1:
         raise C.ValidationException("Aggregation_Map: the id map has no positive id")
     ntime = int(t.shape[0]) if ntime is None else ntime
-    d_order = torch.from_numpy(order).cuda()
-    d_off = torch.from_numpy(offsets).cuda()
     out = torch.empty((nb, ntime), dtype=torch.float64, device='cuda')
     C.check(C.lib().xan_group_sum(C.ptr(t), C.ptr(d_order), C.ptr(d_off), nb, ntime, int(t.shape[1]), C.ptr(out),
                                   C.stream_ptr()))
