@@ -18,7 +18,9 @@ from .. import _cuda as C
 def group_plan(id_map):
     """Cells sorted (stable) by group id, ids <= 0 left out -> (order int32 [n_used], offsets int32 [NB + 1], NB)."""
     ids = np.asarray(id_map).astype(np.int64).reshape(-1)
-    nb = int(ids.max())
+    nb = int(ids.max()) if ids.size else 0
+    if nb < 1:
+        return np.zeros(0, dtype=np.int32), np.zeros(1, dtype=np.int32), 0
     used = np.nonzero(ids > 0)[0]
     order = used[np.argsort(ids[used], kind='stable')]
     counts = np.bincount(ids[used], minlength=nb + 1)[1:]
