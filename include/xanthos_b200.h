@@ -136,9 +136,10 @@ int xan_mrtm_upstream(const double *h_coords, const int64_t *h_dsid, int ncell, 
 /* Execution plan; replaces upstream_genmatrix (mrtm.py:194-230): from h_upid [ncell][9] it
  * builds the rows of UM = UP - I, checks that the flow graph is a forest, cuts large river trees
  * into pieces of at most 31 lanes and packs them into warps (lane 31 of every warp stays empty).
- * block_threads (multiple of 32, <= 640; default 640 = 20 warps, one block per SM, 96 registers) /
- * chunk_substeps (sub-steps per hand-over between warps) <= 0 pick defaults.  At launch the packed
- * warps are assigned to SM sub-partitions by cost and loop variant (see mrtm_sched_kernel;
+ * block_threads: multiple of 32, <= 640; <= 0 picks the default 640 (20 warps, one block per SM,
+ * 96 registers).  chunk_substeps: kept for ABI stability (1..1024, <= 0 = default) and otherwise
+ * unused - warps hand their cut-edge series over once per month.  At launch the packed warps are
+ * assigned to SM sub-partitions by cost and loop variant (see mrtm_sched_kernel;
  * XANTHOS_MRTM_SCHED=static binds packed warp w to grid warp w instead).  Plan
  * creation is host-side integer work and needs no device; the device tables are uploaded by the
  * first xan_mrtm_route call. */
@@ -151,7 +152,7 @@ int xan_mrtm_plan_um_nnz(const xan_mrtm_plan *plan);
 int xan_mrtm_plan_um(const xan_mrtm_plan *plan, int64_t *h_indptr, int64_t *h_indices,
                      int64_t *h_data);
 /* info[0]=is_forest info[1]=n_components info[2]=max_component info[3]=n_warps
- * info[4]=n_cut_edges info[5]=n_levels info[6]=block_threads info[7]=chunk_substeps */
+ * info[4]=n_cut_edges info[5]=n_levels info[6]=block_threads info[7]=max ghost lanes of a warp */
 int xan_mrtm_plan_info(const xan_mrtm_plan *plan, int *info8);
 /* diagnostic export of the warp-kernel packing: lane_cell [n_warps * 32] (cell index or -1),
  * edge_prod / edge_cons [n_cut_edges] (warp indices).  Any pointer may be NULL. */
