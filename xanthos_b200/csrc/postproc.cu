@@ -112,7 +112,17 @@ __global__ void __launch_bounds__(128)
     if (t >= ntime) return;
     const double *row = src + (size_t)t * ld;
     double acc = 0.0;
-    for (int k = offsets[g]; k < offsets[g + 1]; ++k) {
+    const int end = offsets[g + 1];
+    int k = offsets[g];
+    for (; k + 8 <= end; k += 8) {          // 8 loads in flight, the additions stay in cell order
+        double x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = row[order[k + j]];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (!isnan(x[j])) acc = acc + x[j];
+    }
+    for (; k < end; ++k) {
         const double x = row[order[k]];
         if (!isnan(x)) acc = acc + x;
     }
