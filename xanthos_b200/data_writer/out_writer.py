@@ -8,7 +8,8 @@ aggregates (:250-265).  Formats: csv (1) and npy (4); NetCDF / MATLAB / parquet 
 to csv with a warning (file-format breadth is out of scope).
 
 When the array handed in is the one a CUDA stage returned, its device copy is still resident and
-the yearly aggregation runs on the device (xan_agg_to_year).
+the yearly aggregation (xan_agg_to_year) and the basin / country / region sums (xan_group_sum) run on the
+device.
 """
 
 import logging
@@ -97,9 +98,16 @@ class OutWriter:
                 continue
             ids = np.asarray(ids).astype(int)
             nid = int(ids.max())
-            out = np.zeros((nid, data.shape[1]))
-            for k in range(data.shape[1]):
-                out[:, k] = np.bincount(ids, weights=np.nan_to_num(data[:, k]), minlength=nid + 1)[1:]
+            f = C.resident(data)
+            if f is not None:
+                # the array a CUDA stage returned: summed where it lies in HBM (xan_group_sum, NaN skipped)
+                from ..diagnostics.time_series import group_sum_device
+                out = group_sum_device(ids, f.t).cpu().numpy()
+            else:
+                out = np.zeros((nid, data.shape[1]))
+                for k in range(data.shape[1]):
+                    out[:, k] = np.bincount(ids, weights=np.where(np.isnan(data[:, k]), 0.0, data[:, k]),
+                                            minlength=nid + 1)[1:]
             fn = os.path.join(self.out_folder, '{}_{}_{}'.format(name, self.out_unit_str, self.proj_name))
             header = 'id,' + ','.join(self.time_steps)
             np.savetxt(fn + '.csv', np.hstack([np.arange(1, nid + 1)[:, None], out]), delimiter=',', header=header,
