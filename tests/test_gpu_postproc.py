@@ -141,3 +141,7 @@ def test_run_model_with_drought_and_accessible_water(tmp_path):
     want = P.accessible_water_chain(mr, sy, ey, 2006, [2002, 2007, 2012], 5, data['bfi'], data['res_capacity'], 0.1)
     assert list(ac['id']) == list(range(1, w.n_basins + 1)) and list(ac.columns[2:]) == ['2002', '2007', '2012']
     assert np.allclose(ac.iloc[:, 2:].values, want, rtol=1e-12, atol=0)
+    # the basin aggregate OutWriter writes (AggregateRunoffBasin = 1) comes from the resident runoff (xan_group_sum)
+    agg = np.loadtxt(os.path.join(out, 'Basin_runoff_mmpermonth_synthetic.csv'), delimiter=',', skiprows=1)
+    assert np.array_equal(agg[:, 0], np.arange(1, w.n_basins + 1))
+    assert bitwise_equal(agg[:, 1:], P.aggregation_map(w.basin_ids, res.Q))
