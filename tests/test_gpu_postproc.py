@@ -35,6 +35,8 @@ def test_drought_thresholds_and_stats_match_reference_bitwise(nper):
     assert bitwise_equal(DroughtStats.getthresh(h[:11], 1), P.getthresh(h[:11], 1))
     with pytest.raises(ValueError):
         DroughtStats.getthresh(h[:13], 12)
+    if nper == 1:      # one period over the whole record: 372 samples per cell (the local-memory path of the kernel)
+        assert bitwise_equal(DroughtStats.getthresh(h, 1), P.getthresh(h, 1))
 
 
 def test_drought_module_from_resident_field_writes_reference_files(tmp_path):

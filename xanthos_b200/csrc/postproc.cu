@@ -61,37 +61,45 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Quantile thresholds.  thread = (cell, period): the nyear values hist[y * nper + p][cell] are sorted in
-// local memory (insertion sort; nyear is a few dozen) and numpy's "linear" rule is applied with the
+// Quantile thresholds.  thread = (cell, period): the nyear values hist[y * nper + p][cell] are sorted by
+// insertion (nyear is a few dozen) and numpy's "linear" rule is applied with the
 // virtual index (prev, gamma) computed on the host exactly as numpy does.  A NaN anywhere in the sample
 // gives NaN (numpy sorts NaN last and then tests the last element).
 // ---------------------------------------------------------------------------------------------
-constexpr int MAX_YEARS = 256;
+constexpr int MAX_YEARS = 1024;   // samples per (period, cell): 85 years of monthly data with a single period
+constexpr int THR_BLOCK = 128;
+constexpr int THR_SMEM_YEARS = 96;   // up to this many samples per thread the sort runs in shared memory
 
-__global__ void __launch_bounds__(128)
+// SMEM = true: the samples of a thread live in shared memory as v[y * THR_BLOCK + thread] (conflict-free); a
+// thread-private array in local memory costs 2 KB per thread of DRAM write-back (ncu: 447 MB for a 6.5 MB result).
+template <bool SMEM>
+__global__ void __launch_bounds__(THR_BLOCK)
     drought_thresholds_kernel(const double *__restrict__ hist, int ncell, int nyear, int nper, int ld, int prev,
                               double gamma, double *__restrict__ out, int ld_out) {
+    extern __shared__ double s_v[];
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int p = blockIdx.y;
     if (c >= ncell) return;
-    double v[MAX_YEARS];
+    double local_v[SMEM ? 1 : MAX_YEARS];
+    double *v = SMEM ? s_v + threadIdx.x : local_v;
+    const int st = SMEM ? THR_BLOCK : 1;
     bool has_nan = false;
     for (int y = 0; y < nyear; ++y) {
         const double x = hist[(size_t)(y * nper + p) * ld + c];
         has_nan = has_nan || isnan(x);
         int k = y;
-        while (k > 0 && v[k - 1] > x) {
-            v[k] = v[k - 1];
+        while (k > 0 && v[(k - 1) * st] > x) {
+            v[k * st] = v[(k - 1) * st];
             --k;
         }
-        v[k] = x;
+        v[k * st] = x;
     }
     double r;
     if (has_nan) {
         r = nan("");
     } else {
         const int nxt = min(prev + 1, nyear - 1);
-        const double a = v[prev], b = v[nxt];
+        const double a = v[prev * st], b = v[nxt * st];
         const double diff = b - a;
         r = (gamma >= 0.5) ? b - diff * (1.0 - gamma) : a + diff * gamma;   // numpy _lerp
     }
@@ -170,9 +178,17 @@ int xan_drought_thresholds(const double *d_hist, int ncell, int ntime, int ld, i
                 MAX_YEARS);
     XAN_REQUIRE(prev_index >= 0 && prev_index < nyear && gamma >= 0.0 && gamma <= 1.0,
                 "xan_drought_thresholds: bad virtual index %d + %g for %d samples", prev_index, gamma, nyear);
-    dim3 grid(ceil_div(ncell, 128), nper);
-    drought_thresholds_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(d_hist, ncell, nyear, nper, ld, prev_index, gamma,
-                                                                      d_out, ld_out);
+    dim3 grid(ceil_div(ncell, THR_BLOCK), nper);
+    if (nyear <= THR_SMEM_YEARS) {
+        const size_t smem = sizeof(double) * THR_BLOCK * (size_t)nyear;
+        XAN_CUDA_CHECK(cudaFuncSetAttribute(drought_thresholds_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(sizeof(double) * THR_BLOCK * THR_SMEM_YEARS)));
+        drought_thresholds_kernel<true><<<grid, THR_BLOCK, smem, (cudaStream_t)stream>>>(d_hist, ncell, nyear, nper, ld,
+                                                                                          prev_index, gamma, d_out, ld_out);
+    } else {
+        drought_thresholds_kernel<false><<<grid, THR_BLOCK, 0, (cudaStream_t)stream>>>(d_hist, ncell, nyear, nper, ld,
+                                                                                        prev_index, gamma, d_out, ld_out);
+    }
     XAN_CUDA_CHECK(cudaGetLastError());
     return XAN_OK;
 }
