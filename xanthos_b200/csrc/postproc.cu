@@ -120,18 +120,31 @@ __global__ void __launch_bounds__(128)
     if (t >= ntime) return;
     const double *row = src + (size_t)t * ld;
     double acc = 0.0;
+    // The additions are a dependent chain in cell order (bit-exactness), so the time of the kernel is the largest group
+    // times the latency per cell: GB loads are kept in flight and the indices of the next batch are fetched while the
+    // values of this one arrive.
+    constexpr int GB = 16;
     const int end = offsets[g + 1];
     int k = offsets[g];
-    for (; k + 8 <= end; k += 8) {          // 8 loads in flight, the additions stay in cell order
-        double x[8];
+    if (k >= end) {          // a group without cells
+        out[(size_t)g * ntime + t] = 0.0;
+        return;
+    }
+    int idx[GB];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = row[order[k + j]];
+    for (int j = 0; j < GB; ++j) idx[j] = order[min(k + j, end - 1)];
+    for (; k + GB <= end; k += GB) {
+        double x[GB];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < GB; ++j) x[j] = row[idx[j]];
+#pragma unroll
+        for (int j = 0; j < GB; ++j) idx[j] = order[min(k + GB + j, end - 1)];
+#pragma unroll
+        for (int j = 0; j < GB; ++j)
             if (!isnan(x[j])) acc = acc + x[j];
     }
-    for (; k < end; ++k) {
-        const double x = row[order[k]];
+    for (int j = 0; k + j < end; ++j) {      // tail: its indices are already in idx[]
+        const double x = row[idx[j]];
         if (!isnan(x)) acc = acc + x;
     }
     out[(size_t)g * ntime + t] = acc;   // [group][time], the reference's orientation
