@@ -15,6 +15,10 @@ streamflow [360 x 235] of every member are all-gathered over NCCL at the end of 
   value : cell-months/s with the forcing already resident in HBM (month-major fields), device time
   e2e   : same metric through the reference-facing plug-in calls (run_pmpet / abcd_execute /
           route) with pinned HOST buffers in and host ndarrays out; H2D and D2H inside the timing
+  roofline, cpu_baseline, clocks, gpu_launches : as the measurement contract asks
+  calib    : param-sets/s of one differential-evolution generation (235 basins x 64 candidates) and of a whole
+             DE loop with the device and the numpy driver
+  postproc : drought thresholds / statistics and basin sums on the step's resident runoff, numpy port beside it
 """
 
 import argparse
