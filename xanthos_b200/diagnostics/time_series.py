@@ -31,14 +31,9 @@ def group_plan(id_map):
 _plans = {}   # id map (bytes digest) -> (device order, device offsets, NB): maps are few (basin, country, region)
 
 
-_last = [None, None]   # (the id-map object seen last, its plan): the same array is usually aggregated several times
-
-
 def _device_plan(id_map):
     import hashlib
     torch = C.torch_cuda()
-    if _last[0] is id_map and isinstance(id_map, np.ndarray) and not id_map.flags.writeable:
-        return _last[1]
     ids = np.ascontiguousarray(np.asarray(id_map).astype(np.int64).reshape(-1))
     key = (ids.shape[0], hashlib.blake2b(ids.tobytes(), digest_size=16).digest(), torch.cuda.current_device())
     hit = _plans.get(key)
@@ -48,7 +43,6 @@ def _device_plan(id_map):
         if len(_plans) >= 16:
             _plans.clear()
         _plans[key] = hit
-    _last[0], _last[1] = id_map, hit
     return hit
 
 
