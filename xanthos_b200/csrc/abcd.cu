@@ -423,13 +423,15 @@ __global__ void __launch_bounds__(KGE_NT)
 // Calibration objective, population layout (used when a generation has >= 16 candidates).
 // lane = candidate parameter set, warp = a chunk of KC cells of one basin.  The 32 candidates of a
 // warp read the SAME forcing (one broadcast load serves 32 evaluations), every lane keeps the state of
-// its KC cells in registers for the whole pass (KC independent recurrences per thread = ILP), and no
-// shared memory or barrier is used.  Per chunk and candidate the spin-up pass leaves 12 partial
-// (sum, count) values for the basin re-initialisation and the simulation pass one partial basin sum per
-// month; two small kernels add the chunks of a basin in index order (deterministic) and finish the KGE.
-//   kge_pop_spinup_kernel -> kge_pop_reinit_kernel -> kge_pop_sim_kernel -> kge_pop_series_kernel -> kge_pop_finish_kernel
+// its KC cells in registers for the whole pass (KC independent recurrences per thread = ILP).  Per chunk
+// and candidate the spin-up pass leaves 12 partial (sum, count) values for the basin re-initialisation;
+// the simulation pass adds the monthly partial basin sums of the KQ chunks of a block in shared memory (one
+// barrier per month) and leaves one value per block, month and candidate; two small kernels add the blocks
+// of a basin in index order (deterministic) and finish the KGE.
+//   kge_pop_pass<.., false> -> kge_pop_reinit_kernel -> kge_pop_pass<.., true> -> kge_pop_series_kernel -> kge_pop_finish_kernel
 // ---------------------------------------------------------------------------------------------
 constexpr int KC = 4;   // cells per warp-chunk
+constexpr int KQ = 4;   // chunks (warps) per block
 
 struct KgeChunk {
     int slot;    // caller's basin slot
@@ -444,12 +446,15 @@ __global__ void __launch_bounds__(128)
                         const int *__restrict__ order, const KgeChunk *__restrict__ chunks, int nchunks,
                         const double *__restrict__ pars, const double *__restrict__ init /* [nb][npar][2], SIM */,
                         int npar, int npad, int nsteps, int ld, int unit_km3,
-                        double *__restrict__ out /* SIM: [nchunks][nsteps][npad]; else [nchunks][12][npad] */) {
-    const int lane = threadIdx.x & 31;
-    const int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                        double *__restrict__ out /* SIM: [nchunks / KQ][nsteps][npad]; else [nchunks][12][npad] */) {
+    // block = 4 consecutive chunks of ONE basin (the host pads every basin to a multiple of 4 chunks; a padding chunk
+    // has n == 0) for one group of 32 candidates: the four partial basin sums of a month are added in chunk order in
+    // shared memory, so only one value per (4 chunks, month, candidate) goes to global memory.
+    __shared__ double s_acc[2][KQ][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ngroups = npad >> 5;
-    if (unit >= nchunks * ngroups) return;
-    const int ch = unit / ngroups, grp = unit - ch * ngroups;
+    const int quad = blockIdx.x / ngroups, grp = blockIdx.x - quad * ngroups;
+    const int ch = quad * KQ + warp;
     const KgeChunk c = chunks[ch];
     const int p = grp * 32 + lane;
     const int pp = min(p, npar - 1);                       // padding lanes repeat the last candidate
@@ -458,13 +463,13 @@ __global__ void __launch_bounds__(128)
     double sn[KC], sw[KC], g[KC];
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
-        cell[k] = order[c.beg + min(k, c.n - 1)];          // short chunks repeat their last cell (masked below)
+        cell[k] = order[c.beg + max(min(k, c.n - 1), 0)];  // short / padding chunks repeat a cell (masked below)
         sn[k] = 0.0;
         sw[k] = SIM ? init[((size_t)c.slot * npar + pp) * 2] : SW_INIT;
         g[k] = SIM ? init[((size_t)c.slot * npar + pp) * 2 + 1] : GW_INIT;
     }
     const int s1 = nsteps - 25, s2 = nsteps - 13, s3 = nsteps - 1;   // Decembers -25, -13, -1 (abcd.py:255)
-    double *o = out + (size_t)ch * (SIM ? nsteps : 12) * npad + p;
+    double *o = SIM ? out + (size_t)quad * nsteps * npad + p : out + (size_t)ch * 12 * npad + p;
     for (int i = 0; i < nsteps; ++i) {
         const size_t off = (size_t)i * ld;
         double e[KC], pr[KC], t[KC];
@@ -485,7 +490,11 @@ __global__ void __launch_bounds__(128)
             }
         }
         if (SIM) {
-            o[(size_t)i * npad] = acc;
+            s_acc[i & 1][warp][lane] = acc;
+            __syncthreads();       // one barrier per month: the two buffers alternate
+            if (warp == 0)
+                o[(size_t)i * npad] = ((s_acc[i & 1][0][lane] + s_acc[i & 1][1][lane]) + s_acc[i & 1][2][lane]) +
+                                      s_acc[i & 1][3][lane];
         } else if (i == s1 || i == s2 || i == s3) {
             const int which = (i == s3) ? 0 : (i == s2) ? 1 : 2;
             double ssw = 0.0, nsw = 0.0, sg = 0.0, ng = 0.0;
@@ -530,12 +539,12 @@ __global__ void __launch_bounds__(64)
     }
 }
 
-// series[slot][m][p] = sum over the chunks of the slot (index order) of part[chunk][m][p]
+// series[slot][m][p] = sum over the 4-chunk blocks of the slot (index order) of part[block][m][p]
 __global__ void __launch_bounds__(256)
     kge_pop_series_kernel(const double *__restrict__ part, const int *__restrict__ slot_chunk0, int nmonths, int npad,
                           double *__restrict__ series /* [nb][nmonths][npad] */) {
     const int slot = blockIdx.x;
-    const int c0 = slot_chunk0[slot], c1 = slot_chunk0[slot + 1];
+    const int c0 = slot_chunk0[slot] / KQ, c1 = slot_chunk0[slot + 1] / KQ;
     const int total = nmonths * npad;
     for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < total; idx += gridDim.y * blockDim.x) {
         double a = 0.0;
@@ -707,6 +716,7 @@ static int kge_population(const xan_abcd_plan *pl, const int *h_basins, int nb, 
         const int beg = pl->h_offsets[h_basins[i]], end = pl->h_offsets[h_basins[i] + 1];
         slot_chunk0[i] = (int)chunks.size();
         for (int b = beg; b < end; b += KC) chunks.push_back(KgeChunk{i, b, std::min(KC, end - b)});
+        while (chunks.size() % KQ) chunks.push_back(KgeChunk{i, beg, 0});   // padding chunks: no cell counts
     }
     slot_chunk0[nb] = (int)chunks.size();
     const int nch = (int)chunks.size();
@@ -717,12 +727,11 @@ static int kge_population(const xan_abcd_plan *pl, const int *h_basins, int nb, 
     XAN_CUDA_CHECK(scratch_alloc(&d_slot0, sizeof(int) * (nb + 1), s));
     XAN_CUDA_CHECK(scratch_alloc(&snap, sizeof(double) * 12 * (size_t)nch * npad, s));
     XAN_CUDA_CHECK(scratch_alloc(&init, sizeof(double) * 2 * (size_t)nb * npar, s));
-    XAN_CUDA_CHECK(scratch_alloc(&part, sizeof(double) * (size_t)nch * nmonths * npad, s));
+    XAN_CUDA_CHECK(scratch_alloc(&part, sizeof(double) * (size_t)(nch / KQ) * nmonths * npad, s));
     XAN_CUDA_CHECK(scratch_alloc(&series, sizeof(double) * (size_t)nb * nmonths * npad, s));
     XAN_CUDA_CHECK(cudaMemcpyAsync(d_chunks, chunks.data(), sizeof(KgeChunk) * nch, cudaMemcpyHostToDevice, s));
     XAN_CUDA_CHECK(cudaMemcpyAsync(d_slot0, slot_chunk0.data(), sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, s));
-    const int units = nch * (npad / 32);
-    const int grid = ceil_div(units, 4);
+    const int grid = (nch / KQ) * (npad / 32);
     if (d_tmin)
         kge_pop_pass_kernel<true, false><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, d_area, pl->d_order, d_chunks, nch,
                                                               d_pars, nullptr, npar, npad, spinup, ld, unit_km3, snap);
@@ -739,14 +748,13 @@ static int kge_population(const xan_abcd_plan *pl, const int *h_basins, int nb, 
     kge_pop_series_kernel<<<dim3(nb, 8), 256, 0, s>>>(part, d_slot0, nmonths, npad, series);
     kge_pop_finish_kernel<<<nb, 64, 0, s>>>(series, d_obs, npar, npad, nmonths, d_ed, d_series);
     XAN_CUDA_CHECK(cudaGetLastError());
-    // The host tables are read by the copies above: wait before they go out of scope.
+    // (the host tables are pageable: cudaMemcpyAsync has staged them before it returned)
     XAN_CUDA_CHECK(cudaFreeAsync(d_chunks, s));
     XAN_CUDA_CHECK(cudaFreeAsync(d_slot0, s));
     XAN_CUDA_CHECK(cudaFreeAsync(snap, s));
     XAN_CUDA_CHECK(cudaFreeAsync(init, s));
     XAN_CUDA_CHECK(cudaFreeAsync(part, s));
     XAN_CUDA_CHECK(cudaFreeAsync(series, s));
-    XAN_CUDA_CHECK(cudaStreamSynchronize(s));
     return XAN_OK;
 }
 
