@@ -515,24 +515,34 @@ __global__ void __launch_bounds__(128)
 
 // set_vals with every cell of the basin in one group (calibrate_abcd.py:143): mean over the three Decembers
 // of the nanmean over cells.  thread = (slot, candidate); chunks of the slot are added in index order.
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(256)
     kge_pop_reinit_kernel(const double *__restrict__ snap /* [nchunks][12][npad] */, const int *__restrict__ slot_chunk0,
                           int npar, int npad, double *__restrict__ init /* [nb][npar][2] */) {
+    extern __shared__ double s_acc[];   // [12][npad]
     const int slot = blockIdx.x;
     const int c0 = slot_chunk0[slot], c1 = slot_chunk0[slot + 1];
-    for (int p = threadIdx.x; p < npar; p += blockDim.x) {
-        double acc[12];
+    const int total = 12 * npad;
+    // thread = (snapshot value j, candidate p): the chunks are added in index order, 8 loads in flight
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        double acc = 0.0;
+        int c = c0;
+        for (; c + 8 <= c1; c += 8) {
+            double x[8];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) acc[j] = 0.0;
-        for (int c = c0; c < c1; ++c) {
+            for (int k = 0; k < 8; ++k) x[k] = snap[(size_t)(c + k) * total + idx];
 #pragma unroll
-            for (int j = 0; j < 12; ++j) acc[j] += snap[((size_t)c * 12 + j) * npad + p];
+            for (int k = 0; k < 8; ++k) acc += x[k];
         }
+        for (; c < c1; ++c) acc += snap[(size_t)c * total + idx];
+        s_acc[idx] = acc;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < npar; p += blockDim.x) {
         double m_sw = 0.0, m_g = 0.0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            m_sw = m_sw + acc[k] / acc[3 + k];             // nanmean; 0/0 -> NaN like numpy
-            m_g = m_g + acc[6 + k] / acc[9 + k];
+            m_sw = m_sw + s_acc[k * npad + p] / s_acc[(3 + k) * npad + p];       // nanmean; 0/0 -> NaN like numpy
+            m_g = m_g + s_acc[(6 + k) * npad + p] / s_acc[(9 + k) * npad + p];
         }
         init[((size_t)slot * npar + p) * 2] = m_sw / 3.0;
         init[((size_t)slot * npar + p) * 2 + 1] = m_g / 3.0;
@@ -710,6 +720,7 @@ static int kge_population(const xan_abcd_plan *pl, const int *h_basins, int nb, 
                           const double *d_obs, int nmonths, int spinup, int ld, int unit_km3, double *d_ed,
                           double *d_series, cudaStream_t s) {
     const int npad = (npar + 31) / 32 * 32;
+    XAN_REQUIRE(npad <= 512, "xan_abcd_kge_batch: at most 512 parameter sets per basin and call (got %d)", npar);
     std::vector<KgeChunk> chunks;
     std::vector<int> slot_chunk0(nb + 1, 0);
     for (int i = 0; i < nb; ++i) {
@@ -738,7 +749,7 @@ static int kge_population(const xan_abcd_plan *pl, const int *h_basins, int nb, 
     else
         kge_pop_pass_kernel<false, false><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, d_area, pl->d_order, d_chunks, nch,
                                                                d_pars, nullptr, npar, npad, spinup, ld, unit_km3, snap);
-    kge_pop_reinit_kernel<<<nb, 64, 0, s>>>(snap, d_slot0, npar, npad, init);
+    kge_pop_reinit_kernel<<<nb, 256, sizeof(double) * 12 * npad, s>>>(snap, d_slot0, npar, npad, init);
     if (d_tmin)
         kge_pop_pass_kernel<true, true><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, d_area, pl->d_order, d_chunks, nch,
                                                              d_pars, init, npar, npad, nmonths, ld, unit_km3, part);
