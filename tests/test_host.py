@@ -245,3 +245,38 @@ def test_two_rank_gather_with_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all('ok' in o for o in outs), outs
+
+
+@pytest.mark.parametrize("fmt,ext", [(0, 'nc'), (1, 'csv'), (2, 'mat'), (3, 'parquet'), (4, 'npy')])
+def test_out_writer_formats_round_trip(tmp_path, fmt, ext):
+    """OutWriter file formats (out_writer.py:159-235) and the matching DataLoader.load_data readers (data_load.py:343-390);
+    host-only code, no device needed for arrays that are not resident."""
+    from types import SimpleNamespace
+    from xanthos_b200.data_writer.out_writer import OutWriter
+    from xanthos_b200.data_reader.data_load import DataLoader
+    a = np.random.default_rng(fmt).random((40, 24)) * 100
+    s = SimpleNamespace(output_vars=['q', 'avgchflow'], ProjectName='p', OutputFolder=str(tmp_path), OutputFormat=fmt,
+                        OutputUnit=1, OutputUnitStr='km3permonth', OutputInYear=1, StartYear=2001, EndYear=2002)
+    area = np.linspace(1000.0, 3000.0, 40)
+    OutWriter(s, area, {'q': a.copy(), 'avgchflow': a.copy()}).write()
+    want_q = a.reshape(40, 2, 12).sum(axis=2) * (area / 1e6)[:, None]          # yearly sum, mm -> km3
+    want_f = a.reshape(40, 2, 12).mean(axis=2)                                  # streamflow: yearly mean, no conversion
+    fq = os.path.join(str(tmp_path), 'q_km3permonth_p.' + ext)
+    ff = os.path.join(str(tmp_path), 'avgchflow_m3persec_p.' + ext)
+    assert os.path.isfile(fq) and os.path.isfile(ff)
+    if ext == 'nc':
+        got_q, got_f = DataLoader.load_data(fq, key='data'), DataLoader.load_data(ff, key='data')
+        assert got_q.dtype == np.float32 and np.allclose(got_q, want_q, rtol=1e-6) and np.allclose(got_f, want_f, rtol=1e-6)
+    elif ext == 'mat':
+        assert np.array_equal(DataLoader.load_data(fq, key='q'), want_q)
+        assert np.array_equal(DataLoader.load_data(ff, key='avgchflow'), want_f)
+    elif ext == 'npy':
+        assert np.array_equal(DataLoader.load_data(fq), want_q) and np.array_equal(DataLoader.load_data(ff), want_f)
+    elif ext == 'csv':
+        got = np.loadtxt(fq, delimiter=',', skiprows=1)
+        assert np.array_equal(got[:, 0], np.arange(1, 41)) and np.array_equal(got[:, 1:], want_q)
+        assert open(fq).readline().strip() == 'id,2001,2002'
+    else:
+        import pyarrow.parquet as pq
+        t = pq.read_table(fq).to_pandas()
+        assert list(t.columns) == ['id', '2001', '2002'] and np.array_equal(t.iloc[:, 1:].values, want_q)

@@ -210,9 +210,18 @@ class DataLoader:
                     return np.array(f.read().splitlines())
         if fn.endswith('.csv'):
             return np.genfromtxt(fn, delimiter=",", skip_header=header_num, filling_values="0")
-        if fn.endswith('.mat') or fn.endswith('.nc'):
-            raise RuntimeError("File {}: MATLAB / NetCDF inputs are not read by xanthos_b200; "
-                               "convert to .npy".format(fn))
+        if fn.endswith('.mat'):
+            import scipy.io as sio
+            return sio.loadmat(fn)[key]
+        if fn.endswith('.nc'):
+            # scipy.io.netcdf (the module the reference imports, data_load.py:376) is gone; the class remains
+            import scipy.io as sio
+            datagrp = sio.netcdf_file(fn, 'r', mmap=False)
+            data = datagrp.variables[key][:].copy()
+            datagrp.close()
+            if data.dtype.byteorder == ">":                       # little-endian only, like the reference (:383-385)
+                data = data.byteswap().view(data.dtype.newbyteorder('<'))
+            return data
         raise RuntimeError("File {} has unrecognized extension".format(fn))
 
     def load_routing_data(self, fn, rep_val=None):

@@ -4,8 +4,9 @@ Output staging - counterpart of xanthos/data_writer/out_writer.py (OutWriter).
 Kept: variable selection by `output_vars`, yearly aggregation (sum; mean for avgchflow, :103-112),
 mm -> km3 conversion (not for avgchflow, :114-115), file naming `<var>_<unit>_<ProjectName>.<ext>`
 (:119), 1-based cell index and YYYYMM / YYYY column names (:66-70, :123), basin / country / region
-aggregates (:250-265).  Formats: csv (1) and npy (4); NetCDF / MATLAB / parquet requests fall back
-to csv with a warning (file-format breadth is out of scope).
+aggregates (:250-265).  Formats (out_writer.py:159-235): NetCDF classic (0, `scipy.io.netcdf_file` - the
+`scipy.io.netcdf` module the reference imports no longer exists), csv (1), MATLAB (2), parquet (3, written with
+pyarrow when fastparquet is absent; one row group, gzip) and npy (4).
 
 When the array handed in is the one a CUDA stage returned, its device copy is still resident and
 the yearly aggregation (xan_agg_to_year) and the basin / country / region sums (xan_group_sum) run on the
@@ -55,9 +56,8 @@ class OutWriter:
             self.time_steps = [str(y) for y in years]
         else:
             self.time_steps = ['{}{:02}'.format(y, m) for y in years for m in range(1, NMONTHS + 1)]
-        if self.out_format not in (FORMAT_CSV, FORMAT_NPY):
-            logging.warning("Output format {} is not supported by xanthos_b200; writing output as .csv".format(
-                self.out_format))
+        if self.out_format not in (FORMAT_NETCDF, FORMAT_CSV, FORMAT_MAT, FORMAT_PARQUET, FORMAT_NPY):
+            logging.warning("Unknown output format {}; writing output as .csv".format(self.out_format))
             self.out_format = FORMAT_CSV
 
     def get(self, varstr):
@@ -81,6 +81,13 @@ class OutWriter:
         module hands over a fresh DataFrame whose index starts at 0, drought_stats.py:60-63)."""
         if self.out_format == FORMAT_NPY:
             np.save(filename + '.npy', data)
+        elif self.out_format == FORMAT_MAT:
+            import scipy.io as spio
+            spio.savemat(filename + '.mat', {var: np.asarray(data)})                  # out_writer.py:181-183
+        elif self.out_format == FORMAT_NETCDF:
+            self.save_netcdf(filename, np.asarray(data), var)
+        elif self.out_format == FORMAT_PARQUET:
+            self.save_parquet(filename, np.asarray(data), col_names, index_base)
         else:
             if col_names is None:
                 col_names = [str(k) for k in range(data.shape[1])]
@@ -88,6 +95,31 @@ class OutWriter:
             ids = np.arange(index_base, data.shape[0] + index_base)[:, None]
             np.savetxt(filename + '.csv', np.hstack([ids, data]), delimiter=',', header=header, comments='',
                        fmt=['%d'] + ['%.17g'] * data.shape[1])
+
+    def save_netcdf(self, filename, data, varstr):
+        """NetCDF classic, float32 variable 'data' over ('index', 'month' | 'year') (out_writer.py:198-223)."""
+        import scipy.io as spio
+        datagrp = spio.netcdf_file(filename + '.nc', 'w')
+        nrows, ncols = data.shape
+        tdim = 'year' if self.output_in_year else 'month'
+        datagrp.createDimension('index', nrows)
+        datagrp.createDimension(tdim, ncols)
+        griddata = datagrp.createVariable('data', 'f4', ('index', tdim))
+        griddata.units = self.out_unit_str
+        griddata.description = varstr + "_" + self.out_unit_str
+        griddata[:, :] = data[:, :].copy()
+        datagrp.close()
+
+    def save_parquet(self, filename, data, col_names=None, index_base=1):
+        """One gzip-compressed row group with the time steps as columns (out_writer.py:225-235; pyarrow instead of
+        fastparquet's hive layout)."""
+        import pyarrow as pa
+        import pyarrow.parquet as pq
+        if col_names is None:
+            col_names = [str(k) for k in range(data.shape[1])]
+        cols = {'id': np.arange(index_base, data.shape[0] + index_base)}
+        cols.update({str(c): np.ascontiguousarray(data[:, k]) for k, c in enumerate(col_names)})
+        pq.write_table(pa.table(cols), filename + '.parquet', compression='gzip', row_group_size=max(1, data.shape[0]))
 
     def write_aggregates(self, ref, data, basin, country, region):
         """Sum over basins / countries / regions (out_writer.py:250-265)."""
