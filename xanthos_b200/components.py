@@ -226,11 +226,6 @@ class Components:
             logging.info("\tRouting processed in {} seconds---".format(time.time() - t))
 
     def _simulation(self, run_pet, run_runoff, run_routing):
-        if run_runoff and self.s.runoff_module == 'abcd':
-            # start uploading the runoff forcing while PET computes
-            C.prefetch(self.data.precip)
-            C.prefetch(self.data.tmin)
-
         if run_pet:
             logging.info("\tProcessing PET...")
             t = time.time()
@@ -238,6 +233,13 @@ class Components:
             logging.info("\tPET processed in {} seconds---".format(time.time() - t))
         else:
             pet_out = self.calculate_pet()
+
+        if run_runoff and self.s.runoff_module == 'abcd':
+            # Upload the runoff forcing on the side stream while PET computes.  Queued AFTER the uploads of the PET
+            # module (the copy engine serves them in submission order): PET starts as soon as ITS forcing is there
+            # and runs under the upload of precipitation and minimum temperature, instead of behind it.
+            C.prefetch(self.data.precip)
+            C.prefetch(self.data.tmin)
 
         if run_runoff:
             logging.info("\tProcessing Runoff...")
