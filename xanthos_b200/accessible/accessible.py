@@ -34,81 +34,80 @@ def basin_annual_runoff_device(runoff, area, basin_ids):
 
 
 def AccessibleWater(settings, ref, runoff):
-    """Calculate accessible water per basin."""
-    bdf = ref.basin_names
-    rdf = pd.read_csv(settings.ResCapacityFile, header=None, names=['res_capacity'])
-    bfi = pd.read_csv(settings.BfiFile)['bfi_avg']
+    """Accessible water per basin and GCAM year; writes accessible_water_km3peryr_<name>.csv and returns the table."""
+    capacity = pd.read_csv(settings.ResCapacityFile, header=None, names=['res_capacity']).values      # (nb, 1)
+    bfi = pd.read_csv(settings.BfiFile)['bfi_avg'].values
 
-    Map_runoff = basin_annual_runoff_device(runoff, ref.area, ref.basin_ids).cpu().numpy()
+    annual = basin_annual_runoff_device(runoff, ref.area, ref.basin_ids).cpu().numpy()                # [nb, nyears]
+    q_gcam = QInGCAMYears(RollingWindowFilter(annual, settings.MovingMeanWindow), settings)
+    baseflow = (q_gcam.T * bfi).T                                                                      # accessible.py:57
 
-    qs = RollingWindowFilter(Map_runoff, settings.MovingMeanWindow)
-    q_gcam = QInGCAMYears(qs, settings)
-    bflow = np.transpose(np.transpose(q_gcam) * np.array(bfi))
-
+    # environmental flow requirement: a share of the mean annual runoff of the historical years (:60-73)
+    n_hist = annual.shape[1]
     if settings.StartYear > settings.HistEndYear:
         logging.warning('No historical data used in calculating Environmental Flow '
                         'Requirements (EFR) per basin for Accessible Water')
-        edf = settings.Env_FlowPercent * np.mean(Map_runoff, axis=1)
-    elif settings.EndYear <= settings.HistEndYear:
-        edf = settings.Env_FlowPercent * np.mean(Map_runoff, axis=1)
-    else:
-        hey = list(range(settings.StartYear, settings.EndYear + 1)).index(settings.HistEndYear)
-        edf = settings.Env_FlowPercent * np.mean(Map_runoff[:, :(hey + 1)], axis=1)
+    elif settings.EndYear > settings.HistEndYear:
+        n_hist = settings.HistEndYear - settings.StartYear + 1
+    efr = settings.Env_FlowPercent * np.mean(annual[:, :n_hist], axis=1)
 
-    ac = accessible_water(q_gcam, bflow, edf, rdf.values)
-    filename = os.path.join(settings.OutputFolder, 'accessible_water_km3peryr_{}.csv'.format(settings.OutputNameStr))
-    genGCAMOutput(filename, ac, bdf, settings)
+    ac = accessible_water(q_gcam, baseflow, efr, capacity)
+    genGCAMOutput(os.path.join(settings.OutputFolder, 'accessible_water_km3peryr_{}.csv'.format(settings.OutputNameStr)),
+                  ac, ref.basin_names, settings)
     return ac
 
 
 def RollingWindowFilter(data, window, Dimension=0):
-    """Centred moving average with shortened windows at both ends (accessible.py:78-103)."""
-    weights = np.repeat(1.0, window) / window
-    it = int((window - 1) / 2) + 1
+    """
+    Centred moving average of width `window` along the rows (Dimension = 0) or columns (1) of a 2-D array (or along
+    a 1-D array); the first and the last value are the plain means of the half window at that end (accessible.py:78-103).
+    numpy.convolve does the sums, as in the reference, so the values are bit-identical.
+    """
+    data = np.asarray(data, dtype=float)
+    kernel = np.full(window, 1.0 / window)
     if data.ndim == 1:
-        return np.convolve(data, weights, 'same')
-    sma = np.zeros(data.shape, dtype=float)
-    if Dimension == 1:
-        for i in range(data.shape[1]):
-            sma[:, i] = np.convolve(data[:, i], weights, 'same')
-            sma[0, i] = np.mean(data[:it, i])
-            sma[data.shape[0] - 1, i] = np.mean(data[data.shape[0] - it:, i])
-    elif Dimension == 0:
-        for i in range(data.shape[0]):
-            sma[i, :] = np.convolve(data[i, :], weights, 'same')
-            sma[i, 0] = np.mean(data[i, :it])
-            sma[i, data.shape[1] - 1] = np.mean(data[i, data.shape[1] - it:])
-    return sma
+        return np.convolve(data, kernel, 'same')
+    half = (window - 1) // 2 + 1
+    rows = data if Dimension == 0 else data.T
+    out = np.empty(rows.shape, dtype=float)
+    for k, series in enumerate(rows):
+        out[k] = np.convolve(series, kernel, 'same')
+        out[k, 0] = series[:half].mean()
+        out[k, -1] = series[len(series) - half:].mean()
+    return out if Dimension == 0 else out.T
+
+
+def _gcam_years(settings):
+    return list(range(settings.GCAM_StartYear, settings.GCAM_EndYear + 1, settings.GCAM_YearStep))
 
 
 def QInGCAMYears(qs, settings):
-    """Columns of the GCAM target years (accessible.py:106-116)."""
-    valid = list(range(settings.StartYear, settings.EndYear + 1))
-    gcam = list(range(settings.GCAM_StartYear, settings.GCAM_EndYear + 1, settings.GCAM_YearStep))
-    q_gcam = np.zeros((qs.shape[0], len(gcam)), dtype=float)
-    for i, y in enumerate(gcam):
-        q_gcam[:, i] = qs[:, valid.index(y)]
-    return q_gcam
+    """The columns of the GCAM target years out of the yearly table (accessible.py:106-116)."""
+    cols = [y - settings.StartYear for y in _gcam_years(settings)]
+    if min(cols) < 0 or max(cols) >= qs.shape[1]:
+        raise ValueError("GCAM year outside {}-{}".format(settings.StartYear, settings.EndYear))
+    return np.ascontiguousarray(qs[:, cols], dtype=float)
 
 
 def accessible_water(qtot, base, efr, res):
-    """min(qtot - efr, base - efr + res) clipped at 0 (accessible.py:119-129, broadcasting kept)."""
-    ac = np.zeros(qtot.shape, dtype=float)
-    for i in range(qtot.shape[1]):
-        a = qtot[:, i] - efr
-        b = base[:, i] - efr + res
-        c = np.min(np.vstack((a, b)), axis=0)
-        ac[:, i] = np.where(c < 0, 0, c)
-    return ac
+    """
+    min(total - EFR, baseflow - EFR + reservoir capacity), not below zero (accessible.py:119-129).  The reference adds
+    the (nb, 1) capacity column to an (nb,) vector, which broadcasts to every pair of basins before the minimum is
+    taken: the reservoir term of every basin is the SMALLEST capacity of all basins (x + r is monotone in r, so
+    min_k (x + r_k) == x + min_k r_k exactly).  A 1-D capacity vector is applied basin by basin.
+    """
+    res = np.asarray(res, dtype=float)
+    cap = res.min() if res.ndim == 2 else res.reshape(-1, 1)
+    a = qtot - efr[:, None]
+    b = (base - efr[:, None]) + cap
+    c = np.minimum(a, b)
+    return np.where(c < 0, 0.0, c)
 
 
 def genGCAMOutput(filename, data, bdf, settings):
-    """id, name and accessible water by GCAM year as .csv (accessible.py:132-146)."""
-    years = list(map(str, range(settings.GCAM_StartYear, settings.GCAM_EndYear + 1, settings.GCAM_YearStep)))
-    hdr = "id,name," + ",".join(years)
-    MapId = np.arange(1, len(bdf) + 1, 1, dtype=int).astype(str)
-    newdata = np.insert(data.astype(str), 0, bdf, axis=1)
-    Result = np.insert(newdata.astype(str), 0, MapId, axis=1)
-    df = pd.DataFrame(Result)
-    df.columns = hdr.split(',')
-    df.to_csv(filename, index=False)
+    """id, basin name and one column per GCAM year, values written as numpy prints them (accessible.py:132-146)."""
+    table = {'id': np.arange(1, len(bdf) + 1).astype(str), 'name': np.asarray(bdf).astype(str)}
+    text = np.asarray(data).astype(str)
+    for k, year in enumerate(_gcam_years(settings)):
+        table[str(year)] = text[:, k]
+    pd.DataFrame(table).to_csv(filename, index=False)
