@@ -4,6 +4,10 @@ Model interface - drop-in for xanthos/model.py (Xanthos, run_model; :21-132).
     from xanthos_b200 import Xanthos, run_model
     res = Xanthos('pm_abcd_mrtm.ini').execute(args={...})     # returns the Components object
     res.Q.shape == (ncell, nmonths)
+
+Same public surface as the reference class (`make_dir`, `init_log`, `stage`, `execute`, `cleanup`) and the same
+side effects: the output folder is created, every log record goes to stdout and to <OutputFolder>/logfile.log, and
+the handlers are detached again when the run ends.
 """
 
 import argparse
@@ -11,8 +15,10 @@ import logging
 import os
 import sys
 
-from .data_reader.ini_reader import ConfigReader
 from .configurations import ConfigRunner
+from .data_reader.ini_reader import ConfigReader
+
+LOG_FORMAT = '%(levelname)s: %(message)s'
 
 
 class Xanthos:
@@ -21,45 +27,49 @@ class Xanthos:
     def __init__(self, ini):
         self.ini = ini
         self.config = None
+        self._handlers = []
 
     @staticmethod
     def make_dir(pth):
-        if not os.path.exists(pth):
-            os.makedirs(pth)
+        os.makedirs(pth, exist_ok=True)
 
     def init_log(self):
-        """Project-wide logger to stdout and <OutputFolder>/logfile.log (model.py:46-69)."""
-        log_format = logging.Formatter('%(levelname)s: %(message)s')
-        logger = logging.getLogger()
-        logger.setLevel(logging.DEBUG)
-        c_handler = logging.StreamHandler(sys.stdout)
-        c_handler.setLevel(logging.DEBUG)
-        c_handler.setFormatter(log_format)
-        logger.addHandler(c_handler)
-        f_handler = logging.FileHandler(os.path.join(self.config.OutputFolder, 'logfile.log'))
-        f_handler.setFormatter(log_format)
-        logger.addHandler(f_handler)
+        """Root logger at DEBUG with a console and a file handler (model.py:46-69)."""
+        root = logging.getLogger()
+        root.setLevel(logging.DEBUG)
+        targets = (logging.StreamHandler(sys.stdout),
+                   logging.FileHandler(os.path.join(self.config.OutputFolder, 'logfile.log')))
+        for handler in targets:
+            handler.setLevel(logging.DEBUG)
+            handler.setFormatter(logging.Formatter(LOG_FORMAT))
+            root.addHandler(handler)
+            self._handlers.append(handler)
 
     def stage(self, mem_args):
+        """Parse the .ini, apply the in-memory overrides, create the output folder, start logging (model.py:71-80)."""
         self.config = ConfigReader(self.ini)
         self.config.update(mem_args)
         self.make_dir(self.config.OutputFolder)
         self.init_log()
 
-    def execute(self, args={}):
-        """Run the configuration; `args` overrides config attributes, e.g. with in-memory arrays (model.py:82-98)."""
-        self.stage(args)
-        self.config.log_info()
-        results = ConfigRunner(self.config).run()
-        self.cleanup()
-        return results
+    def execute(self, args=None):
+        """Run the configuration and return the Components object; `args` overrides config attributes, e.g. forcing
+        passed as in-memory arrays instead of file names (model.py:82-98)."""
+        self.stage(args or {})
+        try:
+            self.config.log_info()
+            return ConfigRunner(self.config).run()
+        finally:
+            self.cleanup()
 
     def cleanup(self):
+        """Close and detach every handler of the root logger, as the reference does (model.py:100-108)."""
         logging.info("End of {0}".format(self.config.ProjectName))
-        logger = logging.getLogger()
-        for handler in logger.handlers[:]:
+        root = logging.getLogger()
+        for handler in list(root.handlers):
             handler.close()
-            logger.removeHandler(handler)
+            root.removeHandler(handler)
+        self._handlers.clear()
 
 
 def run_model(config_file):
@@ -68,7 +78,6 @@ def run_model(config_file):
 
 
 if __name__ == "__main__":
-    parser = argparse.ArgumentParser()
-    parser.add_argument('config_file', type=str, help='Full path with file name to INI configuration file.')
-    a = parser.parse_args()
-    Xanthos(a.config_file).execute()
+    cli = argparse.ArgumentParser()
+    cli.add_argument('config_file', type=str, help='Full path with file name to INI configuration file.')
+    Xanthos(cli.parse_args().config_file).execute()
