@@ -1157,7 +1157,12 @@ static int launch_warp_t(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, int
     XAN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int per_sm = 0;
     size_t smem = 0;
-    for (int sb : {32, 16, 8}) {   // shrink the staging blocks until every warp fits on the device
+    const char *esb = getenv("XANTHOS_MRTM_SB");
+    // 50 sub-steps per staging block: 5 blocks per month at the reference's 3-hour step (224 - 248 sub-steps); every
+    // block costs a prologue (row decode, first gather, staging hand-shake): 45.3 ms with 32, 44.5 ms with 50
+    const int sb_first = esb ? std::max(8, std::min(64, atoi(esb))) : 50;
+    for (int sb : {sb_first, 32, 16, 8}) {   // shrink the staging blocks until every warp fits on the device
+        if (sb > sb_first) continue;
         a.sb = sb;
         smem = sizeof(double) * (size_t)wpb * (2 * ((size_t)pl->G + 1) * (sb + 1) * NM * 2);
         if (smem > 200 * 1024) continue;
