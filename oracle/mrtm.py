@@ -124,6 +124,21 @@ def gather_rows(upid):
     return cols, sign, cnt
 
 
+def csr_rows(upid):
+    """
+    The same operator as a scipy CSR matrix with int64 data and sorted indices - what the reference's
+    upstream_genmatrix returns after `.tocsr()` (mrtm.py:194-230).  scipy's csr_matvec accumulates a row from
+    0.0 in ascending column order, i.e. exactly `_um_dot`; ~10x faster than the numpy gather at 67,420 cells,
+    which is what makes full-size routing checks affordable.  Pass the result as `rows`.
+    """
+    import scipy.sparse as sparse
+    cols, sign, cnt = gather_rows(upid)
+    n = upid.shape[0]
+    mask = np.arange(9)[None, :] < cnt[:, None]
+    indptr = np.concatenate([[0], np.cumsum(cnt)])
+    return sparse.csr_matrix((sign[mask].astype(np.int64), cols[mask], indptr), shape=(n, n))
+
+
 def _um_dot(cols, sign, cnt, F):
     """Row-ordered accumulation from 0.0, like scipy's csr_matvec."""
     acc = np.zeros(F.shape[0])
@@ -137,7 +152,11 @@ def _um_dot(cols, sign, cnt, F):
 
 def streamrouting(L, S0, F0, ChV, q, area, nday, dt, rows):
     """One month of routing, mrtm.py:16-82.  `rows` = gather_rows(upid)."""
-    cols, sign, cnt = rows
+    if isinstance(rows, tuple):
+        cols, sign, cnt = rows
+        um_dot = lambda f: _um_dot(cols, sign, cnt, f)                         # noqa: E731
+    else:
+        um_dot = rows.dot                                                      # scipy CSR, as the reference
     nt = int(nday * 24 * 3600 / dt)                                            # :36
     S = np.copy(S0)
     F = np.copy(F0)
@@ -147,13 +166,13 @@ def streamrouting(L, S0, F0, ChV, q, area, nday, dt, rows):
     erl = (q * area) * (1e6 / 1e3) / (nday * 24 * 3600)                        # :45
     for _ in range(nt):
         F = S * tauinv                                                         # :50
-        dSdt = _um_dot(cols, sign, cnt, F) + erl                               # :51
+        dSdt = um_dot(F) + erl                                                 # :51
         Sx = (dSdt * dt) < (-S)                                                # :54
         if Sx.any():
             F[Sx] = dSdt[Sx] + F[Sx] + S[Sx] * dtinv                           # :60
             S[Sx] = 0                                                          # :63
             Sxn = np.logical_not(Sx)
-            d2 = _um_dot(cols, sign, cnt, F) + erl                             # :68
+            d2 = um_dot(F) + erl                                               # :68
             S[Sxn] += d2[Sxn] * dt
         else:
             S += (dSdt * dt)                                                   # :76

@@ -121,3 +121,26 @@ def accessible_water_chain(map_runoff, start_year, end_year, hist_end_year, gcam
         c = np.min(np.vstack((a, b)), axis=0)
         ac[:, i] = np.where(c < 0, 0, c)
     return ac
+
+
+def agg_to_year(arr, func='sum'):
+    """
+    OutWriter.agg_to_year (data_writer/out_writer.py:237-248): `df.groupby(np.arange(ncol) // 12, axis=1).agg(func)`.
+    The axis=1 form no longer exists in pandas 3; grouping the transposed frame is pandas' documented replacement
+    and keeps its semantics (NaN skipped: an all-NaN year sums to 0.0 and averages to NaN; Kahan summation).
+    """
+    import pandas as pd
+    df = pd.DataFrame(np.asarray(arr))
+    return df.T.groupby(np.arange(df.shape[1]) // 12).agg(func).T.values
+
+
+def agg_spatial(arr, id_map):
+    """
+    OutWriter.agg_spatial (out_writer.py:250-265) without the name join: `df.groupby('id').sum()` -> (ids present,
+    [n_ids, ntime]); NaN skipped.
+    """
+    import pandas as pd
+    df = pd.DataFrame(np.asarray(arr))
+    df['id'] = np.asarray(id_map)
+    g = df.groupby('id', as_index=False).sum()
+    return g['id'].values.astype(int), g.drop(columns='id').values

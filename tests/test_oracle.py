@@ -12,6 +12,7 @@ from oracle import pet as opet, mrtm as omrtm, abcd as oabcd
 from oracle import ref_loader
 from oracle.validate_against_reference import (run_oracle, oracle_calibration, build_case, run_reference, compare,
                                                run_oracle_stepwise, build_stepwise_case, run_reference_stepwise)
+from oracle.calendar_utils import set_month_arrays
 from util import load_golden, bitwise_equal
 
 
@@ -88,3 +89,48 @@ def test_oracle_matches_live_reference():
     r, o = run_reference_stepwise(sc), run_oracle_stepwise(sc)
     for k in r:
         assert bitwise_equal(r[k], o[k]), k
+
+
+def test_csr_operator_equals_gather_bitwise():
+    """oracle.mrtm.csr_rows (scipy CSR, what the reference multiplies with) and the numpy gather give the same
+    routing bit for bit, clamp events included - the CSR form is what the full-size GPU parity tests use."""
+    from xanthos_b200 import synthetic
+    w = synthetic.make_world(30, 60, 700, 9, seed=61)
+    dsid = omrtm.downstream(w.coords, w.flow_dir, w.nrow, w.ncol)
+    upid = omrtm.upstream_fast(w.coords, dsid, w.nrow, w.ncol)
+    q = synthetic.runoff_input(w, 5, seed=2)
+    nd = set_month_arrays(12, 1999, 1999)[:5, 2]
+    a = omrtm.route(q, w.flow_dist, w.velocity, w.area, nd, 10800, omrtm.gather_rows(upid), 2)
+    b = omrtm.route(q, w.flow_dist, w.velocity, w.area, nd, 10800, omrtm.csr_rows(upid), 2)
+    for x, y in zip(a, b):
+        assert bitwise_equal(x, y)
+    assert ((w.velocity / w.flow_dist) * 10800 > 1).any()          # the world has cells that empty (clamp branch)
+
+
+@pytest.mark.parametrize("seed,prob", [(12345, 0), (99, 3), (2 ** 40 + 7, 1)])
+def test_de_oracle_is_bitwise_scipy_deferred(seed, prob):
+    """SURVEY section 8 row f4 / parity of the third-party solver: scipy's own DifferentialEvolutionSolver
+    (best1bin, updating='deferred'), fed the Philox stream of the kernels in its own consumption order, produces the
+    trial vectors, the selection and the convergence decision of oracle.de bit for bit, out-of-bounds redraws included."""
+    from oracle import de
+    target = np.array([0.1, -0.2, 0.3, 0.0, -0.4])
+
+    def f(p):
+        x = np.asarray(p)
+        return float(np.sum((x - target) ** 2) + 0.1 * np.sum(np.cos(7 * x)))
+    gens = de.replay_against_scipy(f, 15, S=25, D=5, prob=prob, seed=seed)
+    assert len(gens) == 15
+    for g in gens:
+        assert g['trial_equal'] and g['pop_equal'] and g['energy_equal'] and g['converged_equal'] and g['best_at_row0'], g
+    assert sum(g['n_oob'] for g in gens) > 20            # the out-of-bounds branch was exercised
+    # a 4-dimensional problem (the no-snow parameter set) with the reference's population (15 x D)
+    gens = de.replay_against_scipy(lambda p: float(np.sum(np.asarray(p) ** 2)), 6, S=60, D=4, prob=0, seed=seed)
+    assert all(g['trial_equal'] and g['pop_equal'] and g['energy_equal'] for g in gens)
+
+
+def test_de_oracle_latin_hypercube():
+    from oracle import de
+    S, D = 50, 5
+    p = de.lhs_init(3, S, D, 777)
+    assert (p >= 0).all() and (p < 1).all()
+    assert (np.sort(np.floor(p * S).astype(int), axis=1) == np.arange(S)[None, :, None]).all()   # every stratum once

@@ -355,51 +355,73 @@ class async_host:
 def prefetch(host_array, nan_to_num=False):
     """
     Start uploading an input ([ncell, nmonths] host array) on a side stream so that the copy overlaps the
-    kernels of an earlier stage; `as_field(host_array)` later returns the device copy (and makes the compute stream
-    wait for it).
+    kernels of an earlier stage; the next `as_field(host_array)` returns the device copy (and makes the compute
+    stream wait for it).  The entry is TRANSIENT: it is consumed by that one `as_field` call, because the array
+    belongs to the caller, who is free to overwrite it afterwards (see `remember`).
     """
     torch = torch_cuda()
-    if host_array is None or isinstance(host_array, Field) or resident(host_array) is not None:
+    if host_array is None or isinstance(host_array, Field) or resident(host_array, peek=True) is not None:
         return
     cs = copy_stream('h2d')
     with torch.cuda.stream(cs):
         f = Field.from_host(host_array, nan_to_num=nan_to_num)
         ev = torch.cuda.Event()
         ev.record(cs)
-    _prefetched[id(host_array)] = ev
-    remember(host_array, f)
+    _register(host_array, f, transient=True, event=ev)
 
 
-_prefetched = {}
-
-
-# Device copies of arrays handed back to the caller, so that the next stage of
-# Components.simulation (PET -> runoff -> routing) finds its input already in HBM.
+# Device copies of host arrays, so that the next stage of Components.simulation (PET -> runoff -> routing) finds
+# its input already in HBM.  Coherence contract (the reference hands plain ndarrays around and its callees mutate
+# them, so a stale device copy must never be used silently):
+#   * arrays RETURNED by a CUDA stage (`remember`) are handed out READ-ONLY (`flags.writeable = False`): host and
+#     device copy cannot diverge.  `res.Q *= 2` raises "output array is read-only"; `q = res.Q * 2` / `res.Q.copy()`
+#     are new arrays and are uploaded when they are passed back in.  If an owner re-enables writing
+#     (`setflags(write=True)`, possible for arrays that own their memory) the entry is dropped at the next lookup.
+#   * arrays OWNED BY THE CALLER (`prefetch`) are trusted for exactly one lookup.
 _resident = {}
 
 
-def remember(host_array, field):
+def _register(host_array, field, transient=False, event=None):
     import weakref
     key = id(host_array)
-    _resident[key] = (weakref.ref(host_array, lambda _r, k=key: _resident.pop(k, None)), field)
+    _resident[key] = (weakref.ref(host_array, lambda _r, k=key: _resident.pop(k, None)), field, transient, event)
+
+
+def remember(host_array, field):
+    """Register `field` as the device copy of the array a stage returns; the array becomes read-only."""
+    try:
+        host_array.flags.writeable = False
+    except Exception:
+        return host_array               # cannot be protected -> not cached
+    _register(host_array, field)
     return host_array
 
 
-def resident(host_array):
-    hit = _resident.get(id(host_array))
-    if hit is not None and hit[0]() is host_array:
-        ev = _prefetched.pop(id(host_array), None)
-        if ev is not None:      # uploaded on the side stream: order the compute stream after it
-            f = hit[1]
-            torch_cuda().cuda.current_stream().wait_event(ev)
-            f.t.record_stream(torch_cuda().cuda.current_stream())
-        return hit[1]
-    return None
+def resident(host_array, peek=False):
+    """Device copy of `host_array` if it is still known to be identical to it, else None."""
+    key = id(host_array)
+    hit = _resident.get(key)
+    if hit is None or hit[0]() is not host_array:
+        return None
+    ref, f, transient, ev = hit
+    if not transient and getattr(getattr(host_array, 'flags', None), 'writeable', True):
+        _resident.pop(key, None)        # the owner made it writeable again: the copies may differ
+        return None
+    if peek:
+        return f
+    if transient:
+        _resident.pop(key, None)
+    if ev is not None:                  # uploaded on the side stream: order the compute stream after it
+        cur = torch_cuda().cuda.current_stream()
+        cur.wait_event(ev)
+        f.t.record_stream(cur)
+        if not transient:
+            _resident[key] = (ref, f, transient, None)
+    return f
 
 
 def forget_all():
     _resident.clear()
-    _prefetched.clear()
 
 
 def as_field(x, nan_to_num=False):

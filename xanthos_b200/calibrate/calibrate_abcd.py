@@ -75,6 +75,9 @@ class BasinEvaluator:
         returns the KGE distances as a cuda tensor [nb, P].  Nothing is synchronised."""
         torch = self._torch
         nb, npar = int(d_pars.shape[0]), int(d_pars.shape[1])
+        if tuple(d_obs.shape) != (nb, self.n_months) or len(basin_nums) != nb or int(d_pars.shape[2]) != 5:
+            raise C.ValidationException("objective: parameters {} / observations {} do not match {} basins x {} months"
+                                        .format(tuple(d_pars.shape), tuple(d_obs.shape), len(basin_nums), self.n_months))
         rows, rp = C.as_c(np.asarray(basin_nums, dtype=np.int64) - 1, np.int32)
         d_ed = torch.empty((nb, npar), dtype=torch.float64, device='cuda')
         C.check(C.lib().xan_abcd_kge_batch(self.plan._plan, rp, nb, npar, C.ptr(self.pet.t), C.ptr(self.precip.t),
@@ -243,7 +246,12 @@ def calibrate_basins(basin_nums, basin_ids, basin_areas, precip, pet, obs, tmin,
     """
     ev = evaluator or BasinEvaluator(basin_ids, basin_areas, precip, pet, tmin, n_months, runoff_spinup, obs_unit)
     basin_nums = [int(b) for b in basin_nums]
-    robs = np.stack([_basin_obs(obs, b, n_months) for b in basin_nums])
+    series = [_basin_obs(obs, b, n_months) for b in basin_nums]
+    short = [b for b, r in zip(basin_nums, series) if r.shape[0] != int(n_months)]
+    if short:       # the reference fails in np.corrcoef on the length mismatch (calibrate_abcd.py:200)
+        raise C.ValidationException("observations of basin(s) {} do not cover the {} simulated months".format(
+            short, int(n_months)))
+    robs = np.stack(series)
     bounds = BOUNDS_SNOW[:4] if ev.nosnow else BOUNDS_SNOW
     bn = np.asarray(basin_nums)
     if driver == 'host':       # numpy generation logic, one host round trip per generation

@@ -288,7 +288,8 @@ class Components:
         if self.s.CreateTimeSeriesPlot:
             logging.info("---Creating Time Series Plots:")
             t0 = time.time()
-            TimeSeriesPlot(self.s, getattr(self, 'q', self.Q), getattr(self, 'ac', self.Avg_ChFlow), self.data)
+            TimeSeriesPlot(self.s, self.q if self.q is not None else self.Q,
+                           self.ac if self.ac is not None else self.Avg_ChFlow, self.data)
             logging.info("---Time Series have finished successfully: %s seconds ------" % (time.time() - t0))
 
     def output_simulation(self):

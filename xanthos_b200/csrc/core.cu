@@ -85,16 +85,24 @@ __global__ void __launch_bounds__(TILE *TROWS)
     }
 }
 
-// OutWriter.agg_to_year (out_writer.py:237-248): sum (mean for avgchflow) of each block of 12 months.
+// OutWriter.agg_to_year (out_writer.py:237-248): sum (mean for avgchflow) of each block of 12 months, NaN skipped.
 __global__ void agg_to_year_kernel(const double *__restrict__ src, double *__restrict__ dst,
                                    int ncell, int nyears, int ld, int take_mean) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (c >= ncell || y >= nyears) return;
-    double acc = 0.0;
+    // pandas' groupby sum / mean skip NaN: an all-NaN year sums to 0.0 and averages to NaN
+    double v[12], acc = 0.0;
+    int cnt = 0;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) acc += ldg_stream(src + (size_t)(y * 12 + k) * ld + c);
-    if (take_mean) acc = acc / 12.0;
+    for (int k = 0; k < 12; ++k) v[k] = ldg_stream(src + (size_t)(y * 12 + k) * ld + c);
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+        if (!isnan(v[k])) {
+            acc += v[k];
+            ++cnt;
+        }
+    if (take_mean) acc = acc / (double)cnt;   // 0 / 0 = NaN
     dst[(size_t)y * ld + c] = acc;
 }
 

@@ -59,6 +59,8 @@ class DataLoader:
         self.basin_names = self._optional(s, 'BasinNames', lambda f: self.load_data(f))
         self.region_ids = self._optional(s, 'GCAMRegionIDs', lambda f: self.load_data(f, 1).astype(int))
         self.country_ids = self._optional(s, 'CountryIDs', lambda f: self.load_data(f, 1).astype(int))
+        self.region_names = self._optional(s, 'GCAMRegionNames', self.get_region_names)     # data_load.py:63
+        self.country_names = self._optional(s, 'CountryNames', self.get_country_names)      # data_load.py:69
         self.latitude = np.copy(self.coords[:, 2])
         self.lat_radians = np.radians(self.latitude)
 
@@ -166,6 +168,19 @@ class DataLoader:
             return self.load_data(self.s.ChStorageFile, 0, self.s.ChStorageVarName)[:, -1]
         except AttributeError:
             return np.zeros((self.s.ncell,), dtype=float)
+
+    @staticmethod
+    def get_country_names(fn):
+        """Second column of the headerless `index,name` file (data_load.py:275-279)."""
+        with open(fn, 'r') as f:
+            return np.array([ln.split(',')[1] for ln in f.read().splitlines() if ln.strip()])
+
+    @staticmethod
+    def get_region_names(fn):
+        """First column of the region name file below its header line (data_load.py:281-286)."""
+        with open(fn, 'r') as f:
+            f.readline()
+            return np.array([ln.split(',')[0] for ln in f.read().split('\n') if ln.strip()])
 
     def load_to_array(self, f, var_name=None, neg_to_zero=False, nan_to_num=False, warn_nan=False):
         """Load and validate a [ncell, nmonths] input (data_load.py:288-340)."""

@@ -33,9 +33,15 @@ def agg_to_year(arr, func='sum'):
         out = C.Field.empty(f.ncell, f.nmonths // NMONTHS, f.ld)
         C.check(C.lib().xan_agg_to_year(C.ptr(f.t), C.ptr(out.t), f.ncell, f.nmonths, f.ld, int(func == 'mean'),
                                         C.stream_ptr()))
-        return out.to_host()
-    a = np.asarray(arr).reshape(arr.shape[0], -1, NMONTHS)
-    return a.mean(axis=2) if func == 'mean' else a.sum(axis=2)
+        return C.remember(out.to_host(), out)
+    # arrays that did not come from a CUDA stage (host-side writer only); pandas' groupby skips NaN
+    a = np.asarray(arr)[:, :arr.shape[1] // NMONTHS * NMONTHS].reshape(arr.shape[0], -1, NMONTHS)
+    ok = ~np.isnan(a)
+    tot = np.where(ok, a, 0.0).sum(axis=2)
+    if func == 'mean':
+        with np.errstate(invalid='ignore', divide='ignore'):
+            return tot / ok.sum(axis=2)
+    return tot
 
 
 class OutWriter:

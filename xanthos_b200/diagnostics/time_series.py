@@ -72,8 +72,13 @@ def TimeSeriesPlot(settings, Q, Avg_ChFlow, ref):
     scales = {1: ['Basin'], 2: ['Country'], 3: ['GCAMRegion']}.get(settings.TimeSeriesScale,
                                                                     ['Basin', 'Country', 'GCAMRegion'])
     for scalestr in scales:
-        ids = {'Basin': ref.basin_ids, 'Country': ref.country_ids, 'GCAMRegion': ref.region_ids}[scalestr]
-        names = {'Basin': ref.basin_names, 'Country': ref.country_names, 'GCAMRegion': ref.region_names}[scalestr]
+        key = {'Basin': 'basin', 'Country': 'country', 'GCAMRegion': 'region'}[scalestr]
+        ids = getattr(ref, key + '_ids', None)
+        names = getattr(ref, key + '_names', None)
+        if ids is None:
+            raise C.ValidationException("TimeSeriesPlot: no {} id map is loaded (reference data switched off?)".format(scalestr))
+        if names is None:
+            names = []
         folder = os.path.join(settings.OutputFolder, 'TimeSeriesPlot', scalestr)
         os.makedirs(folder, exist_ok=True)
         for arr, what in ((Q, 'runoff'), (Avg_ChFlow, 'streamflow')):

@@ -98,10 +98,12 @@ def _execute(n_basins, basin_ids, pet, precip, tmin, prm, n_months, spinup_steps
         pet_h = pet                                            # passthrough, abcd.py:352
     else:
         pet_f = C.Field(e.t[:int(n_months)], e.ncell)
-        pet_h = C.remember(pet_f.to_host(), pet_f)
-        if (rows < 0).any():
+        pet_h = pet_f.to_host()
+        if (rows < 0).any():            # host copy differs from the device field -> it is not registered
             C.host_sync()
             pet_h[rows < 0, :] = np.nan
+        else:
+            pet_h = C.remember(pet_h, pet_f)
     aet = C.remember(res['aet'].to_host(), res['aet'])
     q = C.remember(res['q'].to_host(), res['q'])
     sav = C.remember(res['sav'].to_host(), res['sav'])

@@ -409,7 +409,7 @@ def calibration_obs(basin_series, seed=4):
 # --------------------------------------------------------------------------
 def write_example(root, world, start_yr, end_yr, pet='pm', routing=True, seed=1, runoff_spinup=None,
                   routing_spinup=None, calibrate=False, output_vars='q,avgchflow', project='synthetic',
-                  postproc=None):
+                  postproc=None, project_overrides=None, extra_lines=None):
     """
     Write a synthetic project under `root` in the file formats the loader reads
     (xanthos/data_reader/ini_reader.py:428-435, data_load.py:47-72, 92-135, 200-211) and return the
@@ -433,6 +433,23 @@ def write_example(root, world, start_yr, end_yr, pet='pm', routing=True, seed=1,
         np.savetxt(f, world.basin_ids, fmt='%d')
     with open(os.path.join(ref, 'BasinNames235.txt'), 'w') as f:
         f.write('\n'.join('Basin_{}'.format(i + 1) for i in range(world.n_basins)) + '\n')
+    # country / GCAM region maps and their name files (data_load.py:60-69, 275-286): countries 0..nc (0 = none),
+    # regions 1..nr; both follow the basins so that they are spatially coherent
+    nc, nr = max(2, world.n_basins // 2), max(2, world.n_basins // 3)
+    rng_ids = np.random.default_rng(seed + 4242)
+    country = (world.basin_ids % (nc + 1)).astype(int)
+    country[rng_ids.random(n) < 0.01] = 0
+    region = (world.basin_ids % nr).astype(int) + 1
+    with open(os.path.join(ref, 'country.csv'), 'w') as f:
+        f.write('country_id\n')
+        np.savetxt(f, country, fmt='%d')
+    with open(os.path.join(ref, 'region32_grids.csv'), 'w') as f:
+        f.write('region_id\n')
+        np.savetxt(f, region, fmt='%d')
+    with open(os.path.join(ref, 'country-names.csv'), 'w') as f:
+        f.write('\n'.join('{},Country_{}'.format(i, i) for i in range(nc + 1)) + '\n')
+    with open(os.path.join(ref, 'Rgn32Names.csv'), 'w') as f:
+        f.write('region,region_id\n' + '\n'.join('Region_{},{}'.format(i, i) for i in range(1, nr + 1)) + '\n')
 
     data = {}
     pdir = os.path.join(dirs['pet'], pet)
@@ -549,6 +566,16 @@ def write_example(root, world, start_yr, end_yr, pet='pm', routing=True, seed=1,
         lines += ['[Calibrate]', 'set_calibrate = 0', 'observed = ' + os.path.join(root, 'input', 'obs.csv'),
                   'obs_unit = km3_per_mth', 'calib_out_dir = ' + os.path.join(root, 'output', 'calib'),
                   'calibration_basins = 1-{}'.format(world.n_basins)]
+    if extra_lines:
+        lines += list(extra_lines)
+    if project_overrides:
+        for key, val in project_overrides.items():
+            hit = [k for k, ln in enumerate(project_lines) if ln.split('=')[0].strip() == key]
+            if hit:
+                project_lines[hit[0]] = '{} = {}'.format(key, val)
+            else:
+                project_lines.append('{} = {}'.format(key, val))
+    data['country_ids'], data['region_ids'] = country, region
     ini = os.path.join(root, project + '.ini')
     with open(ini, 'w') as f:
         f.write('\n'.join(project_lines + lines) + '\n')
