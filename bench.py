@@ -48,6 +48,15 @@ BYTES_ABCD = 24 + 24 + 24 * RUNOFF_SPINUP / NMONTHS   # sim reads + writes + spi
 BYTES_MRTM = 8 + 16 + 8 * ROUTING_SPINUP / NMONTHS    # q + (ChStorage, Avg_ChFlow) + spin-up reads = 32
 
 
+def bench_config(ncell, nmonths):
+    """`config` of the JSON line - the SAME dictionary for both arms (`--impl ours` / `--impl reference`)."""
+    spin_ro, spin_rt = min(RUNOFF_SPINUP, nmonths), min(ROUTING_SPINUP, nmonths)
+    return {'workload': WORKLOAD if (ncell, nmonths) == (NCELL, NMONTHS) else 'reduced_%dx%d' % (ncell, nmonths),
+            'ncell': ncell, 'nmonths': nmonths, 'nlcs': NLCS, 'runoff_spinup': spin_ro, 'routing_spinup': spin_rt,
+            'dt_s': DT, 'members_per_gpu': 1, 'parallelism': 'member-per-gpu',
+            'l2': 'inputs (8 x %.0f MB per member) exceed the 126 MB L2; no flush needed' % (ncell * nmonths * 8 / 1e6)}
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -486,12 +495,8 @@ def run_ours(args, rank, world_size, local_rank):
         'metric': 'cell-months/s (PM+ABCD+MRTM)', 'value': value, 'unit': 'cell-months/s', 'n_gpus': world_size,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD if (ncell, nmonths) == (NCELL, NMONTHS) else 'reduced_%dx%d' % (ncell, nmonths),
-                   'ncell': ncell, 'nmonths': nmonths, 'nlcs': NLCS, 'runoff_spinup': spin_ro,
-                   'routing_spinup': spin_rt, 'dt_s': DT, 'members_per_gpu': 1,
-                   'parallelism': 'member-per-gpu x%d' % world_size,
-                   'l2': 'inputs (8 x %.0f MB per member) exceed the 126 MB L2; no flush needed' % (cm * 8 / 1e6),
-                   'mrtm_plan': um.info},
+        'config': bench_config(ncell, nmonths),
+        'mrtm_plan': um.info,
         'e2e': {'value': e2e_val, 'unit': 'cell-months/s', 'h2d_bytes_per_step': int(h2d_bytes),
                 'd2h_bytes_per_step': int(d2h_bytes_holder[0]), 'ms_per_step': e2e_ms, 'statistic': 'median step',
                 'ms_per_step_mean': float(np.mean(e2e_each)), 'ms_each_step': [round(v, 2) for v in e2e_each],
@@ -508,74 +513,132 @@ def run_ours(args, rank, world_size, local_rank):
             postproc[k]['frac_hbm'] = postproc[k]['achieved_gbs'] / peaks['hbm_gbs']
         line['postproc'] = postproc
     if world_size == 1 and not args.no_cpu_baseline:
-        line['cpu_baseline'] = cpu_baseline(world, pm, ab, end_yr, budget_s=args.cpu_budget)
+        line['cpu_baseline'] = cpu_baseline(world, pm, ab, nmonths)
         if calib is not None:
             line['cpu_baseline']['calib'] = cpu_calib_baseline(world, pm, ab)
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline (oracle port of the reference's numpy path) - also the `--impl reference` arm
+# CPU baseline and `--impl reference`: the reference's OWN modules (oracle/_ref, staged unmodified by
+# oracle/make_ref.sh), the numpy oracle port only if no staged tree travelled with the snapshot
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(world, pm, ab, end_yr, budget_s=20.0, threads=None):
+REF_SAMPLE = {'pm_cells': 16384, 'pm_months': 12, 'abcd_months': 36, 'mrtm_months': 2}
+
+
+def _reference_modules():
+    from oracle import ref_loader
+    if ref_loader.staged_available():
+        return ref_loader.load_staged(), 'reference'
+    return None, 'port'
+
+
+class ReferenceSample:
     """
-    Time the numpy oracle (a restatement of the reference's own numpy algorithm, pinned bitwise to
-    it) on a bounded sample of the same workload and extrapolate linearly in cell-months.
-    Per-stage samples: PM - 1 year, all cells; ABCD - 48 months spin-up + 48 months simulation,
-    all cells, basin chunks over threads like the reference (abcd.py:368-382); MRTM - 4 months.
+    One bounded sample of the config-1 workload through the reference's stock code path:
+      PM    run_pmpet (pet/penman_monteith.py:394) on the first `pm_cells` cells x 1 year, as Components calls it
+            (single-threaded numpy);
+      ABCD  abcd_execute (runoff/abcd.py:394) with jobs = -1 (joblib threads over 8 basin chunks, the reference's own
+            parallelism) on ALL cells, `abcd_months` of spin-up + `abcd_months` of simulation;
+      MRTM  downstream / upstream / upstream_genmatrix once (setup, not timed per step), then streamrouting
+            (routing/mrtm.py:16) on ALL cells for `mrtm_months` months at dt = 3 h, carried state.
+    cell-months/s of the whole pipeline = 1 / (t_pm + t_abcd (1 + spin-up / months) + t_mrtm (1 + spin-up / months))
+    with t_* the measured seconds per cell-month-pass of each stage (every stage is linear in cell-months).
     """
-    from concurrent.futures import ThreadPoolExecutor
-    from oracle import pet as opet, abcd as oabcd, mrtm as omrtm
-    from oracle.calendar_utils import set_month_arrays
-    ncell = world.ncell
-    threads = threads or os.cpu_count() or 1
 
-    t0 = time.perf_counter()
-    pm1 = {k: (v[:, :12] if isinstance(v, np.ndarray) and v.ndim == 2 and v.shape[0] == ncell and v.shape[1] >= 12
-               and k.endswith('_load') and k != 'lct_load' else v) for k, v in pm.items()}
-    pet = opet.pm_pet(pm1, ncell, NLCS, START_YR, START_YR, pm['water_idx'], pm['snow_idx'], pm['lc_years'])
-    t_pm = (time.perf_counter() - t0) / (ncell * 12)                       # s per cell-month, 1 thread
+    def __init__(self, world, pm, ab, nmonths):
+        self.ref, self.kind = _reference_modules()
+        self.world, self.pm, self.ab, self.nmonths = world, pm, ab, nmonths
+        n = world.ncell
+        nc = min(REF_SAMPLE['pm_cells'], n)
+        self.nc = nc
+        d = {}
+        for k, v in pm.items():
+            if isinstance(v, np.ndarray) and v.shape[:1] == (n,):
+                v = v[:nc]
+                if v.ndim == 2 and v.shape[1] >= 12 and k.endswith('_load') and k != 'lct_load':
+                    v = v[:, :12]
+            d[k] = v
+        self.pm_sample = d
+        ms = REF_SAMPLE['abcd_months']
+        self.ms = ms
+        self.pet_s = np.abs(np.random.default_rng(0).normal(80.0, 30.0, (n, ms)))
+        self.q = np.abs(np.random.default_rng(0).normal(50.0, 30.0, (n, REF_SAMPLE['mrtm_months'])))
+        self.ndays = month_days_mod4(12, START_YR)
+        self._td = tempfile.TemporaryDirectory()
+        self.calib_file = os.path.join(self._td.name, 'pars.npy')
+        np.save(self.calib_file, ab['pars'])
+        t0 = time.perf_counter()
+        if self.kind == 'reference':
+            s = world.settings()
+            dsid = self.ref.mrtm.downstream(world.coords, world.flow_dir, s)
+            upid = self.ref.mrtm.upstream(world.coords, dsid, s)
+            self.um = self.ref.mrtm.upstream_genmatrix(upid)
+        else:
+            from oracle import mrtm as omrtm
+            dsid = omrtm.downstream(world.coords, world.flow_dir, world.nrow, world.ncol)
+            self.um = omrtm.csr_rows(omrtm.upstream_fast(world.coords, dsid, world.nrow, world.ncol))
+        self.setup_s = time.perf_counter() - t0
+        self.threads = 8                      # abcd_parallel: n_chunks = 8 for jobs < 1 (runoff/abcd.py:368-371)
 
-    ms = 48
-    pet_s = np.tile(pet, (1, ms // 12))
-    rows = np.asarray(world.basin_ids) - 1
-    chunks = np.array_split(np.arange(world.n_basins), max(1, min(threads, 8)))
+    def step(self):
+        w, n = self.world, self.world.ncell
+        t0 = time.perf_counter()
+        if self.kind == 'reference':
+            data = SimpleNamespace(**{k: (np.copy(v) if isinstance(v, np.ndarray) else v)
+                                      for k, v in self.pm_sample.items()})
+            self.ref.pm.run_pmpet(data, self.nc, NLCS, START_YR, START_YR, self.pm['water_idx'], self.pm['snow_idx'],
+                                  self.pm['lc_years'])
+        else:
+            from oracle import pet as opet
+            opet.pm_pet(self.pm_sample, self.nc, NLCS, START_YR, START_YR, self.pm['water_idx'], self.pm['snow_idx'],
+                        self.pm['lc_years'])
+        t1 = time.perf_counter()
+        ms = self.ms
+        if self.kind == 'reference':
+            self.ref.abcd.abcd_execute(n_basins=w.n_basins, basin_ids=w.basin_ids, pet=self.pet_s,
+                                       precip=self.ab['precip'][:, :ms], tmin=self.ab['tmin'][:, :ms],
+                                       calib_file=self.calib_file, n_months=ms, spinup_steps=ms, jobs=-1)
+        else:
+            from oracle import abcd as oabcd
+            oabcd.abcd_execute(w.n_basins, w.basin_ids, self.pet_s, self.ab['precip'][:, :ms], self.ab['tmin'][:, :ms],
+                               self.ab['pars'], ms, ms)
+        t2 = time.perf_counter()
+        S, F = np.zeros(n), np.zeros(n)
+        nmr = self.q.shape[1]
+        for m in range(nmr):
+            if self.kind == 'reference':
+                S, _, F = self.ref.mrtm.streamrouting(w.flow_dist, S, F, w.velocity, self.q[:, m], w.area,
+                                                      int(self.ndays[m]), DT, self.um)
+            else:
+                from oracle import mrtm as omrtm
+                S, _, F = omrtm.streamrouting(w.flow_dist, S, F, w.velocity, self.q[:, m], w.area, int(self.ndays[m]),
+                                              DT, self.um)
+        t3 = time.perf_counter()
+        t_pm = (t1 - t0) / (self.nc * 12)
+        t_abcd = (t2 - t1) / (n * 2 * ms)
+        t_mrtm = (t3 - t2) / (n * nmr)
+        spin_ro, spin_rt = min(RUNOFF_SPINUP, self.nmonths), min(ROUTING_SPINUP, self.nmonths)
+        per_cm = t_pm + t_abcd * (1 + spin_ro / self.nmonths) + t_mrtm * (1 + spin_rt / self.nmonths)
+        return {'wall_s': t3 - t0, 'value': 1.0 / per_cm,
+                'stage_cell_months_per_s': {'pm': 1.0 / t_pm, 'abcd_per_pass': 1.0 / t_abcd,
+                                            'mrtm_per_pass': 1.0 / t_mrtm}}
 
-    def run_chunk(ch):
-        idx = np.nonzero(np.isin(rows, ch))[0]
-        if len(idx) == 0:
-            return
-        oabcd.abcd_emulate(ab['pars'][rows[idx]], pet_s[idx], ab['precip'][idx, :ms], ab['tmin'][idx, :ms],
-                           world.basin_ids[idx], ms, ms)
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=len(chunks)) as ex:
-        list(ex.map(run_chunk, chunks))
-    t_abcd = (time.perf_counter() - t0) / (ncell * 2 * ms)                 # s per cell-month-step
+    def describe(self):
+        return ('per step: run_pmpet 1 year x %d cells (1 thread, stock); abcd_execute(jobs=-1: 8 joblib threads over '
+                'basin chunks) %d+%d months x %d cells; streamrouting %d months x %d cells at dt = %d s (scipy CSR, '
+                '1 thread); stage rates combined to the %d-month workload with both spin-ups (every stage is linear '
+                'in cell-months) - a sampled extrapolation, not a full run'
+                % (self.nc, self.ms, self.ms, self.world.ncell, self.q.shape[1], self.world.ncell, DT, self.nmonths))
 
-    dsid = omrtm.downstream(world.coords, world.flow_dir, world.nrow, world.ncol)
-    upid = omrtm.upstream_fast(world.coords, dsid, world.nrow, world.ncol)
-    cols, sign, cnt = omrtm.gather_rows(upid)
-    import scipy.sparse as sparse
-    indptr = np.concatenate([[0], np.cumsum(cnt)])
-    mask = np.arange(9)[None, :] < cnt[:, None]
-    indices, data = cols[mask], sign[mask]
-    um = sparse.csr_matrix((data, indices, indptr), shape=(ncell, ncell))   # same operator the reference builds
-    ndays = set_month_arrays(12, START_YR, START_YR)[:, 2]
-    q = np.abs(np.random.default_rng(0).normal(50, 30, (ncell, 4)))
-    S = np.zeros(ncell)
-    t0 = time.perf_counter()
-    nmr = 3
-    for m in range(nmr):
-        S = _mrtm_month_scipy(world.flow_dist, S, world.velocity, q[:, m], world.area, int(ndays[m]), DT, um)
-    t_mrtm = (time.perf_counter() - t0) / (ncell * nmr)
 
-    per_cm = t_pm + t_abcd * (1 + RUNOFF_SPINUP / NMONTHS) + t_mrtm * (1 + ROUTING_SPINUP / NMONTHS)
-    return {'value': 1.0 / per_cm, 'unit': 'cell-months/s', 'cores': int(len(chunks)), 'kind': 'port',
-            'sample': 'PM 1 year x %d cells (1 thread); ABCD %d+%d months x %d cells (%d threads over basin chunks, '
-                      'as the reference); MRTM %d months x %d cells with scipy CSR (1 thread); extrapolated linearly '
-                      'to 360 months with both spin-ups' % (ncell, ms, ms, ncell, len(chunks), nmr, ncell),
-            'stage_cell_months_per_s': {'pm': 1.0 / t_pm, 'abcd_per_pass': 1.0 / t_abcd, 'mrtm_per_pass': 1.0 / t_mrtm},
-            'host_cpus': os.cpu_count()}
+def cpu_baseline(world, pm, ab, nmonths):
+    """One ReferenceSample step on the host cores (rank 0, N = 1), reported beside the GPU numbers."""
+    rs = ReferenceSample(world, pm, ab, nmonths)
+    r = rs.step()
+    return {'value': r['value'], 'unit': 'cell-months/s', 'cores': rs.threads, 'kind': rs.kind,
+            'sample': rs.describe(), 'stage_cell_months_per_s': r['stage_cell_months_per_s'],
+            'sample_wall_s': r['wall_s'], 'host_cpus': os.cpu_count()}
 
 
 def cpu_calib_baseline(world, pm, ab, n_eval=20):
@@ -602,51 +665,35 @@ def cpu_calib_baseline(world, pm, ab, n_eval=20):
                                                                          RUNOFF_SPINUP, NMONTHS)}
 
 
-def _mrtm_month_scipy(L, S0, ChV, q, area, nday, dt, UM):
-    """Oracle month step with the scipy CSR operator, as the reference evaluates it (mrtm.py:16-82)."""
-    nt = int(nday * 24 * 3600 / dt)
-    S = np.copy(S0)
-    tauinv = ChV / L
-    dtinv = 1. / dt
-    erl = (q * area) * (1e6 / 1e3) / (nday * 24 * 3600)
-    for _ in range(nt):
-        F = S * tauinv
-        dSdt = UM.dot(F) + erl
-        Sx = (dSdt * dt) < (-S)
-        if Sx.any():
-            F[Sx] = dSdt[Sx] + F[Sx] + S[Sx] * dtinv
-            S[Sx] = 0
-            Sxn = np.logical_not(Sx)
-            dSdt[Sxn] = (UM.dot(F))[Sxn] + erl[Sxn]
-            S[Sxn] += dSdt[Sxn] * dt
-        else:
-            S += (dSdt * dt)
-    return S
-
-
 def run_reference(args, rank, world_size):
-    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores; rank 0 only."""
+    """
+    --impl reference: the UNMODIFIED reference modules (oracle/_ref) on the host cores, rank 0 only.  A step is one
+    bounded sample of the workload (ReferenceSample); `ms_per_step` is the wall time of that sample step, `value` the
+    cell-months/s the stage rates of the step combine to for the full configuration.
+    """
     if rank != 0:
         return
     world, pm, ab, end_yr = build_inputs(member_seed=1, ncell=args.ncell, nmonths=max(12, min(args.nmonths, 48)))
-    ab48 = dict(ab)
-    vals = []
+    rs = ReferenceSample(world, pm, ab, args.nmonths)
+    res = []
     t_all = time.perf_counter()
-    for _ in range(args.warmup + args.steps):
-        vals.append(cpu_baseline(world, pm, ab48, end_yr, budget_s=args.cpu_budget))
-        if time.perf_counter() - t_all > 240:
+    for k in range(args.warmup + args.steps):
+        res.append(rs.step())
+        if time.perf_counter() - t_all > 270 and k + 1 >= args.warmup + 1:
             break
-    timed_vals = vals[min(args.warmup, len(vals) - 1):]
-    v = float(np.mean([x['value'] for x in timed_vals]))
-    cb = dict(timed_vals[-1])
-    cb['value'] = v
-    cm = float(args.ncell) * args.nmonths
+    timed = res[min(args.warmup, len(res) - 1):]
+    v = float(np.mean([x['value'] for x in timed]))
+    wall = float(np.mean([x['wall_s'] for x in timed]))
+    cb = {'value': v, 'unit': 'cell-months/s', 'cores': rs.threads, 'kind': rs.kind, 'sample': rs.describe(),
+          'stage_cell_months_per_s': {k: float(np.mean([x['stage_cell_months_per_s'][k] for x in timed]))
+                                      for k in timed[0]['stage_cell_months_per_s']},
+          'host_cpus': os.cpu_count(), 'setup_s': rs.setup_s}
     line = {'impl': 'reference', 'metric': 'cell-months/s (PM+ABCD+MRTM)', 'value': v, 'unit': 'cell-months/s',
-            'n_gpus': world_size, 'steps': len(timed_vals), 'warmup': args.warmup, 'ms_per_step': cm / v * 1e3,
+            'n_gpus': world_size, 'steps': len(timed), 'warmup': args.warmup, 'ms_per_step': wall * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'ncell': args.ncell, 'nmonths': args.nmonths, 'nlcs': NLCS,
-                       'runoff_spinup': RUNOFF_SPINUP, 'routing_spinup': ROUTING_SPINUP, 'dt_s': DT,
-                       'note': 'each step times a bounded sample and extrapolates linearly in cell-months'},
+            'config': bench_config(args.ncell, args.nmonths),
+            'note': 'ms_per_step is the wall time of one bounded sample step; value is the sampled extrapolation '
+                    'described in cpu_baseline.sample',
             'cpu_baseline': cb,
             'e2e': {'value': v, 'unit': 'cell-months/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -692,11 +739,12 @@ def main():
         run_reference(args, rank, world_size)
         return
     if world_size > 1:
-        # stdout carries ONE JSON line: NCCL prints its version banner there at the VERSION and WARN levels
+        # stdout carries ONE JSON line; NCCL's log (version banner, rank / ring summary at NCCL_DEBUG=INFO) is kept
+        # but sent to stderr instead of stdout, where NCCL prints it by default
         if 'XANTHOS_NCCL_DEBUG' in os.environ:
             os.environ['NCCL_DEBUG'] = os.environ['XANTHOS_NCCL_DEBUG']
-        else:
-            os.environ.pop('NCCL_DEBUG', None)
+        if os.environ.get('NCCL_DEBUG') and 'NCCL_DEBUG_FILE' not in os.environ:
+            os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'
         _bind_to_gpu_numa_node(local_rank)
         import torch
         import torch.distributed as dist
