@@ -159,9 +159,23 @@ int xan_mrtm_plan_info(const xan_mrtm_plan *plan, int *info8);
 int xan_mrtm_plan_packing(const xan_mrtm_plan *plan, int *h_lane_cell, int *h_edge_prod,
                           int *h_edge_cons);
 
-#define XAN_MRTM_AUTO 0  /* warp-dataflow kernel if the flow graph is a forest  */
+/* diagnostic export of the skew-kernel plan (csrc/mrtm_skew.cu; built on first use).
+ * info[0]=K (cells per lane) [1]=n_warps [2]=n_cut_edges [3]=n_levels [4]=max ghost entries of a warp
+ * [5]=max lag [6]=n_pieces [7]=row-term sources per lane [8]=index of the all-zero table entry
+ * [9]=ghost entries per warp [10]=export entries per warp; all zero if the graph has no skew plan.
+ * Tables (any pointer may be NULL): cell, lag [n_warps][32 K]; src [n_warps][32][info[7]];
+ * ghost_edge, ghost_lag [n_warps][info[9]]; exp_edge, exp_place [n_warps][info[10]]; Dw [n_warps];
+ * edge_prod, edge_cons [n_cut_edges]. */
+int xan_mrtm_skew_info(xan_mrtm_plan *plan, int *info11);
+int xan_mrtm_skew_tables(xan_mrtm_plan *plan, int *cell, int *lag, int *src, int *ghost_edge,
+                         int *ghost_lag, int *exp_edge, int *exp_place, int *Dw, int *edge_prod,
+                         int *edge_cons);
+
+#define XAN_MRTM_AUTO 0  /* skew kernel if the flow graph is a forest and the calendar allows it,
+                          * else the warp-dataflow kernel, else the grid kernel              */
 #define XAN_MRTM_GRID 1  /* cooperative grid-sync kernel (any graph)            */
-#define XAN_MRTM_TREE 2  /* force the warp kernel (fails if not a forest)       */
+#define XAN_MRTM_TREE 2  /* force the warp-dataflow kernel (fails if not a forest) */
+#define XAN_MRTM_SKEW 3  /* force the skew kernel (fails if it is not available)   */
 
 /* Replaces the routing loops of Components.calculate_routing (xanthos/components.py:262-296)
  * around streamrouting (mrtm.py:16-82): `spinup_months` months of spin-up over the first months

@@ -1,6 +1,6 @@
 """A/B timing of the MRTM warp kernel on the bench world (config 1: 360 spin-up + 360 months).
 
-usage: python tools/mrtm_ab.py NAME=ENV1=v1,ENV2=v2 ...   (each argument is one variant; the environment
+usage: python tools/mrtm_ab.py NAME=ENV1=v1,ENV2=v2 ...   e.g. tree=XANTHOS_MRTM_AUTO=tree skew=XANTHOS_MRTM_AUTO=skew   (each argument is one variant; the environment
 variables are read by xan_mrtm_route at every call).  Prints the best and median of 3 runs per variant and
 checks that every variant returns bit-identical ChStorage / Avg_ChFlow."""
 import os, sys

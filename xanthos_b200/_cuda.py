@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libxanthos_b200.so')
 
 XAN_OK, XAN_E_INVALID, XAN_E_CUDA, XAN_E_SPINUP, XAN_E_NOMEM = 0, -1, -2, -3, -4
-MRTM_AUTO, MRTM_GRID, MRTM_TREE = 0, 1, 2
+MRTM_AUTO, MRTM_GRID, MRTM_TREE, MRTM_SKEW = 0, 1, 2, 3
 PM_MAX_CLASSES = 32
 
 
@@ -62,6 +62,8 @@ SIGNATURES = {
     'xan_mrtm_plan_um': (c_int, [_P, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     'xan_mrtm_plan_info': (c_int, [_P, POINTER(c_int)]),
     'xan_mrtm_plan_packing': (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    'xan_mrtm_skew_info': (c_int, [_P, POINTER(c_int)]),
+    'xan_mrtm_skew_tables': (c_int, [_P] + [POINTER(c_int)] * 10),
     'xan_mrtm_route': (c_int, [_P, _P, _P, _P, _P, _P, POINTER(c_int), c_int, c_int, c_int, c_double, c_int,
                                _P, _P, _P, _P]),
     'xan_mrtm_route_batch': (c_int, [_P, c_int, POINTER(_P), _P, _P, _P, POINTER(_P), POINTER(c_int), c_int, c_int,

@@ -29,50 +29,12 @@
 
 namespace cg = cooperative_groups;
 
-namespace xan {
-struct Packing;
-}
-
-struct xan_mrtm_plan {
-    int ncell = 0;
-    // ---- topology (host) -------------------------------------------------------------------
-    std::vector<int> upid;      // [ncell][9] (mrtm.py:123-191)
-    bool multi_receiver = false;
-    std::vector<int> row_ptr;   // CSR of UM = UP - I, columns ascending (mrtm.py:194-230)
-    std::vector<int> col;
-    std::vector<signed char> sgn;
-    std::vector<int> down;      // routing graph: 0-based receiver of cell j, -1 if none
-    bool is_forest = false;
-    int n_components = 0, max_component = 0;
-    // ---- grid kernel ------------------------------------------------------------------------
-    std::vector<int> h_gcol;
-    int *d_gcol = nullptr;              // [9][ncell] column (bit 31 set = minus sign), -1 = empty
-    // ---- warp kernel ------------------------------------------------------------------------
-    int block_threads = 256, chunk = 64, lanes = 31;   // lanes: lanes of a warp the packing may occupy
-    int n_warps = 0, n_edges = 0, n_levels = 0, G = 0;   // G = max ghost lanes of a warp
-    xan::Packing *packing = nullptr;    // host copy of the lane tables
-    int *d_lane_cell = nullptr;         // [n_warps * 32] cell index or -1
-    int *d_lane_gedge = nullptr;        // [n_warps * 32] cut edge READ by this (ghost) lane or -1
-    int *d_lane_oedge = nullptr;        // [n_warps * 32] cut edge WRITTEN by this lane or -1
-    uint2 *d_lane_src = nullptr;        // [n_warps * 32] row of UM in column order, 9 x 7 bit (see build_packing)
-    unsigned *d_lane_meta = nullptr;    // [n_warps * 32] row length | ghost slot << 8
-    int *d_edge_prod = nullptr;         // [n_edges] producing warp
-    int *d_edge_cons = nullptr;         // [n_edges] consuming warp
-    int *d_progress = nullptr;          // [n_warps] chunks completed (reset per run)
-    int *d_edge_cell = nullptr;         // [n_edges] cell whose flow the edge carries
-    struct SchedKey {
-        const double *flow_dist, *velocity;
-        double dt;
-        int blocks, wpb, group;
-    };
-    int *d_sched = nullptr;             // [grid warps] packed warp run by each grid warp (mrtm_sched_kernel), cached
-    SchedKey sched_key{};
-    bool on_device = false;
-};
+#include "mrtm_plan.cuh"
 
 namespace xan {
 
 constexpr int RING_DEFAULT = 4;   // months of a cut-edge series kept in flight
+constexpr bool AUTO_DEFAULT_SKEW = false;   // which forest kernel XAN_MRTM_AUTO picks (the faster one as measured)
 
 // =============================================================================================
 // host: topology
@@ -1107,6 +1069,7 @@ xan_mrtm_plan *xan_mrtm_plan_create(const int64_t *h_upid, int ncell, int block_
 void xan_mrtm_plan_destroy(xan_mrtm_plan *pl) {
     if (!pl) return;
     if (pl->on_device) free_device(pl);
+    xan::skew_plan_destroy(pl->skew);
     delete pl->packing;
     delete pl;
 }
@@ -1303,7 +1266,13 @@ int xan_mrtm_route_batch(xan_mrtm_plan *pl, int n_members, const double *const *
     }
     const bool tree_ok = pl->is_forest && pl->n_warps > 0;
     XAN_REQUIRE(method != XAN_MRTM_TREE || tree_ok, "xan_mrtm_route: the flow graph is not a forest; warp kernel unavailable");
-    bool use_tree = (method == XAN_MRTM_TREE) || (method == XAN_MRTM_AUTO && tree_ok);
+    XAN_REQUIRE(method >= XAN_MRTM_AUTO && method <= XAN_MRTM_SKEW, "xan_mrtm_route: unknown method %d", method);
+    bool use_tree = (method == XAN_MRTM_TREE) || ((method == XAN_MRTM_AUTO || method == XAN_MRTM_SKEW) && tree_ok);
+    // AUTO: XANTHOS_MRTM_AUTO=skew|tree selects the forest kernel (A/B runs); see AUTO_DEFAULT_SKEW
+    const char *env_auto = getenv("XANTHOS_MRTM_AUTO");
+    const bool auto_skew = env_auto ? !strcmp(env_auto, "skew") : AUTO_DEFAULT_SKEW;
+    bool use_skew = pl->is_forest && (method == XAN_MRTM_SKEW || (method == XAN_MRTM_AUTO && auto_skew));
+    XAN_REQUIRE(method != XAN_MRTM_SKEW || use_skew, "xan_mrtm_route: the flow graph is not a forest; skew kernel unavailable");
 
     int dev = 0, sms = 0;
     XAN_CUDA_CHECK(cudaGetDevice(&dev));
@@ -1317,6 +1286,22 @@ int xan_mrtm_route_batch(xan_mrtm_plan *pl, int n_members, const double *const *
     int rc = XAN_OK;
     for (int k0 = 0; k0 < n_members && rc == XAN_OK;) {
         const int nm = std::min(nm_cap, n_members - k0);
+        if (use_skew) {
+            const int r = xan::route_skew(pl, h_runoff[k0], d_flow_dist, d_velocity, d_area,
+                                          h_chs_prev ? h_chs_prev[k0] : nullptr, h_ndays, nmonths, spinup_months, ld, dt,
+                                          h_chs ? h_chs[k0] : nullptr, h_avg ? h_avg[k0] : nullptr,
+                                          h_instream ? h_instream[k0] : nullptr, sms, s);
+            if (r == XAN_E_INVALID) {   // plan or calendar not supported by the skew kernel
+                XAN_REQUIRE(method != XAN_MRTM_SKEW, "xan_mrtm_route: the skew kernel cannot run this plan / calendar "
+                            "(row with more than 4 tributaries on one side of the diagonal, or a month shorter than "
+                            "the largest lag)");
+                use_skew = false;
+                continue;
+            }
+            rc = r;
+            k0 += 1;
+            continue;
+        }
         if (use_tree) {
             WarpArgs a;
             memset(&a, 0, sizeof(a));

@@ -1,0 +1,850 @@
+// MRTM river routing, "skewed" warp kernel (xanthos/routing/mrtm.py:16-82), fp64, -fmad=false, results
+// BIT-IDENTICAL to the reference's scipy-CSR formulation (same argument as mrtm.cu: every row of UM = UP - I is
+// accumulated term by term in ascending column order).
+//
+// Why a second kernel.  In mrtm_warp_kernel (mrtm.cu) a lane holds one cell and all lanes of a warp work on the
+// SAME sub-step t: the flow exchange, the row sum, the clamp decision (mrtm.py:54) and - when a flow changed - the
+// repeated balance with F' (mrtm.py:56-69) form one dependent chain per sub-step, and the warps that hold a cell
+// with dt V / L > 1 (it empties at every other sub-step) run that chain twice.  The run ends with the slowest
+// such chain.
+//
+// Here the cells of a warp are SKEWED in time: water only moves downstream, so cell j at sub-step t needs nothing
+// but the flows (F, F') of its tributaries at sub-step t.  A cell at depth D below its piece's outlet works `lag`
+// = Dw - D sub-steps behind the warp's leaves: in loop iteration n it does sub-step n - lag, and every tributary
+// (lag - 1) finished that sub-step one iteration earlier.  Consequences:
+//   * both the trial flow F and the final flow F' of every tributary are known when a cell starts its sub-step,
+//     so the balance for the decision (with F, mrtm.py:51) and the balance for the update (with F', mrtm.py:68)
+//     are two independent sums: no vote, no repeated pass, no branch - every warp executes the same straight code
+//     whether its cells clamp or not;
+//   * a lane holds K cells (slots): K independent chains per warp (ILP), a quarter of the warps, half the
+//     instructions per cell; slot 0 takes the cells with two or more tributaries (<= 4 before and <= 4 after the
+//     cell's own column), the other slots the cells with at most one (their row is order-free);
+//   * flows are exchanged through a double-buffered table in shared memory (one STS.128 per slot, one LDS.128 per
+//     row term; the reader always reads the parity written one iteration earlier);
+//   * cut edges between warps are time series in global memory (L2) indexed by the ABSOLUTE sub-step: the producer
+//     exports its outlet's (F, F') one iteration after they are computed, the consumer stages them into shared
+//     memory 32 sub-steps at a time with cp.async and feeds them to the table through "ghost" entries; progress
+//     counters in sub-steps give hand-over and back-pressure.  No block- or grid-wide barrier in the time loop.
+//   * month boundaries (new lateral inflow, monthly mean, ChStorage snapshot) are per-cell events: a cell crosses
+//     the boundary `lag` iterations after the warp's leaves; the event code runs only in those iterations.
+#include "mrtm_plan.cuh"
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+namespace xan {
+
+constexpr int SK_XG = 16;        // ghost entries (incoming cut edges) per warp
+constexpr int SK_XO = 16;        // exported cells (outgoing cut edges) per warp
+constexpr int SK_DMAX = 62;      // largest piece height; lags reach SK_DMAX + 1 in warps with ghost entries
+constexpr int SK_CH = 64;        // sub-steps of a cut-edge series staged per hand-over
+constexpr int SK_W = 4 * SK_CH;  // staged entries kept per ghost (a chunk is read for at most 2 SK_CH iterations)
+constexpr int SK_NB = 4;         // before / after terms of a wide row
+
+struct SkewPlan {
+    int K = 0, nw = 0, n_edges = 0, n_levels = 0, G = 0, Dmax = 0, n_pieces = 0;
+    std::vector<int> cell;         // [nw][K*32] cell index or -1
+    std::vector<int> lag;          // [nw][K*32]
+    std::vector<int> src;          // [nw][32][2*SK_NB + K - 1] table entry of every row term (ZERO entry = padding)
+    std::vector<int> ghost_edge;   // [nw][SK_XG] edge or -1
+    std::vector<int> ghost_lag;    // [nw][SK_XG]
+    std::vector<int> exp_edge;     // [nw][SK_XO] edge or -1
+    std::vector<int> exp_place;    // [nw][SK_XO] table entry of the exported cell
+    std::vector<int> Dw;           // [nw]
+    std::vector<int> edge_prod, edge_cons, edge_cell;
+    // device copies
+    int *d_cell = nullptr, *d_lag = nullptr, *d_src = nullptr, *d_ghost_edge = nullptr, *d_ghost_lag = nullptr,
+        *d_exp_edge = nullptr, *d_exp_place = nullptr, *d_Dw = nullptr, *d_edge_prod = nullptr, *d_edge_cons = nullptr,
+        *d_progress = nullptr;
+    bool on_device = false;
+    int nsrc() const { return 2 * SK_NB + K - 1; }
+    int zero_entry() const { return K * 32 + SK_XG; }
+};
+
+void skew_plan_destroy(SkewPlan *sp) {
+    if (!sp) return;
+    if (sp->on_device) {
+        cudaFree(sp->d_cell); cudaFree(sp->d_lag); cudaFree(sp->d_src); cudaFree(sp->d_ghost_edge);
+        cudaFree(sp->d_ghost_lag); cudaFree(sp->d_exp_edge); cudaFree(sp->d_exp_place); cudaFree(sp->d_Dw);
+        cudaFree(sp->d_edge_prod); cudaFree(sp->d_edge_cons); cudaFree(sp->d_progress);
+    }
+    delete sp;
+}
+
+// =============================================================================================
+// host: pieces, warps, places, lags
+// =============================================================================================
+static SkewPlan *build_skew(const xan_mrtm_plan *pl, int K) {
+    const int n = pl->ncell;
+    if (!pl->is_forest || n <= 0) return nullptr;
+    const int CAP = 32 * K;
+    auto nup = [&](int v) { return pl->upid[(size_t)v * 9 + 8]; };
+    auto child = [&](int v, int s) { return pl->upid[(size_t)v * 9 + s] - 1; };
+    // a wide row needs slot 0; its terms must fit SK_NB before and SK_NB after the own column
+    for (int v = 0; v < n; ++v)
+        if (nup(v) >= 2) {
+            int before = 0;
+            for (int s = 0; s < nup(v); ++s) before += child(v, s) < v ? 1 : 0;
+            if (before > SK_NB || nup(v) - before > SK_NB) return nullptr;
+        }
+    std::vector<int> indeg(n), order;
+    order.reserve(n);
+    for (int i = 0; i < n; ++i) indeg[i] = nup(i);
+    for (int i = 0; i < n; ++i)
+        if (indeg[i] == 0) order.push_back(i);
+    for (size_t h = 0; h < order.size(); ++h) {
+        const int r = pl->down[order[h]];
+        if (r >= 0 && --indeg[r] == 0) order.push_back(r);
+    }
+    if ((int)order.size() != n) return nullptr;
+
+    // ---- pieces, bottom-up: size <= CAP, wide cells <= 32, incoming cut edges <= SK_XG, height <= SK_DMAX --------
+    std::vector<int> sz(n, 0), wd(n, 0), gh(n, 0), ht(n, 0);
+    std::vector<char> cut(n, 0);
+    for (int h = 0; h < n; ++h) {
+        const int v = order[h];
+        const int k = nup(v);
+        int ch[8];
+        bool merged[8];
+        for (int s = 0; s < k; ++s) {
+            ch[s] = child(v, s);
+            merged[s] = true;
+        }
+        for (;;) {
+            int s_sz = 1, s_wd = (k >= 2) ? 1 : 0, s_gh = 0, s_ht = 0;
+            for (int s = 0; s < k; ++s) {
+                if (merged[s]) {
+                    s_sz += sz[ch[s]];
+                    s_wd += wd[ch[s]];
+                    s_gh += gh[ch[s]];
+                    s_ht = std::max(s_ht, ht[ch[s]] + 1);
+                } else {
+                    s_gh += 1;
+                    s_ht = std::max(s_ht, 1);
+                }
+            }
+            int viol = 0;   // 1 size, 2 wide, 3 ghosts, 4 height
+            if (s_sz > CAP) viol = 1;
+            else if (s_wd > 32) viol = 2;
+            else if (s_gh > SK_XG) viol = 3;
+            else if (s_ht > SK_DMAX) viol = 4;
+            if (!viol) {
+                sz[v] = s_sz; wd[v] = s_wd; gh[v] = s_gh; ht[v] = s_ht;
+                break;
+            }
+            int best = -1, bestval = -1;
+            for (int s = 0; s < k; ++s) {
+                if (!merged[s]) continue;
+                const int c = ch[s];
+                const int val = viol == 1 ? sz[c] : viol == 2 ? wd[c] : viol == 3 ? gh[c] : ht[c];
+                if (val > bestval || (val == bestval && best >= 0 && c < ch[best])) {
+                    bestval = val;
+                    best = s;
+                }
+            }
+            if (best < 0) return nullptr;   // cannot happen: a bare cell satisfies every bound
+            merged[best] = false;
+            cut[ch[best]] = 1;
+        }
+    }
+    std::vector<int> piece(n, -1), p_sz, p_wd, p_gh, p_ht, p_root;
+    for (int h = n - 1; h >= 0; --h) {
+        const int v = order[h];
+        if (pl->down[v] < 0 || cut[v]) {
+            piece[v] = (int)p_sz.size();
+            p_sz.push_back(sz[v]); p_wd.push_back(wd[v]); p_gh.push_back(gh[v]); p_ht.push_back(ht[v]);
+            p_root.push_back(v);
+        } else {
+            piece[v] = piece[pl->down[v]];
+        }
+    }
+    const int np = (int)p_sz.size();
+    std::vector<int> piece_down(np, -1), piece_level(np, 0);
+    for (int h = 0; h < n; ++h) {   // leaves first
+        const int v = order[h];
+        if (cut[v]) {
+            const int pu = piece[v], pd = piece[pl->down[v]];
+            piece_down[pu] = pd;
+            piece_level[pd] = std::max(piece_level[pd], piece_level[pu] + 1);
+        }
+    }
+    int n_levels = 1;
+    for (int p = 0; p < np; ++p) n_levels = std::max(n_levels, piece_level[p] + 1);
+
+    // ---- warps: pieces that feed the same downstream piece may share a warp (one consumer per warp: no cycle through
+    // the back-pressure); consumers without a receiver open a warp of their own; free pieces (whole trees) fill gaps ----
+    struct Bin { int sz = 0, wd = 0, gh = 0, out = 0; };
+    std::vector<Bin> bins;
+    std::vector<int> piece_warp(np, -1), ids(np);
+    std::iota(ids.begin(), ids.end(), 0);
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return p_sz[a] > p_sz[b]; });
+    auto fits = [&](const Bin &b, int p, int out) {
+        return b.sz + p_sz[p] <= CAP && b.wd + p_wd[p] <= 32 && b.gh + p_gh[p] <= SK_XG && b.out + out <= SK_XO;
+    };
+    auto put = [&](int w, int p, int out) {
+        bins[w].sz += p_sz[p]; bins[w].wd += p_wd[p]; bins[w].gh += p_gh[p]; bins[w].out += out;
+        piece_warp[p] = w;
+    };
+    {
+        std::vector<std::vector<int>> open(np);   // per consumer piece: warps opened for its tributary pieces
+        for (int p : ids) {
+            const bool linked = piece_down[p] >= 0 || p_gh[p] > 0;
+            if (!linked) continue;
+            if (piece_down[p] < 0) {
+                bins.emplace_back();
+                put((int)bins.size() - 1, p, 0);
+                continue;
+            }
+            int w = -1;
+            for (int cand : open[piece_down[p]])
+                if (fits(bins[cand], p, 1)) {
+                    w = cand;
+                    break;
+                }
+            if (w < 0) {
+                bins.emplace_back();
+                w = (int)bins.size() - 1;
+                open[piece_down[p]].push_back(w);
+            }
+            put(w, p, 1);
+        }
+    }
+    {
+        std::vector<std::vector<int>> by_room(CAP + 1);
+        for (size_t w = 0; w < bins.size(); ++w) by_room[CAP - bins[w].sz].push_back((int)w);
+        for (int p : ids) {
+            if (piece_down[p] >= 0 || p_gh[p] > 0) continue;
+            int w = -1;
+            for (int room = p_sz[p]; room <= CAP && w < 0; ++room) {
+                auto &lst = by_room[room];
+                for (size_t q = lst.size(); q-- > 0;)
+                    if (fits(bins[lst[q]], p, 0)) {
+                        w = lst[q];
+                        lst.erase(lst.begin() + q);
+                        break;
+                    }
+            }
+            if (w < 0) {
+                bins.emplace_back();
+                w = (int)bins.size() - 1;
+            }
+            put(w, p, 0);
+            by_room[CAP - bins[w].sz].push_back(w);
+        }
+    }
+    const int nw = (int)bins.size();
+
+    auto *sp = new SkewPlan();
+    sp->K = K;
+    sp->nw = nw;
+    sp->n_levels = n_levels;
+    sp->n_pieces = np;
+    const int NS = sp->nsrc(), ZERO = sp->zero_entry();
+    sp->cell.assign((size_t)nw * CAP, -1);
+    sp->lag.assign((size_t)nw * CAP, 0);
+    sp->src.assign((size_t)nw * 32 * NS, ZERO);
+    sp->ghost_edge.assign((size_t)nw * SK_XG, -1);
+    sp->ghost_lag.assign((size_t)nw * SK_XG, 0);
+    sp->exp_edge.assign((size_t)nw * SK_XO, -1);
+    sp->exp_place.assign((size_t)nw * SK_XO, ZERO);
+    sp->Dw.assign(nw, 0);
+
+    // ---- places: wide cells in slot 0, the others in slots 1 .. K-1 in depth-first post-order (a cell's tributary then
+    // sits in the previous lane: neighbouring lanes read neighbouring table entries), overflow into slot 0 --------------
+    std::vector<int> post;
+    post.reserve(n);
+    {
+        std::vector<std::pair<int, int>> stack;
+        for (int r = 0; r < n; ++r) {
+            if (pl->down[r] >= 0) continue;
+            stack.emplace_back(r, 0);
+            while (!stack.empty()) {
+                auto &top = stack.back();
+                const int v = top.first;
+                if (top.second < nup(v)) {
+                    const int c = child(v, top.second);
+                    ++top.second;
+                    stack.emplace_back(c, 0);
+                } else {
+                    post.push_back(v);
+                    stack.pop_back();
+                }
+            }
+        }
+    }
+    std::vector<int> cell_warp(n), place(n, -1), next_wide(nw, 0), next_c(nw, 32);
+    for (int v = 0; v < n; ++v) cell_warp[v] = piece_warp[piece[v]];
+    for (int v : post)
+        if (nup(v) >= 2) place[v] = next_wide[cell_warp[v]]++;
+    for (int v : post)
+        if (nup(v) < 2) {
+            const int w = cell_warp[v];
+            if (next_c[w] < CAP) place[v] = next_c[w]++;
+            else place[v] = next_wide[w]++;
+        }
+    for (int w = 0; w < nw; ++w)
+        if (next_wide[w] > 32) {
+            delete sp;
+            return nullptr;
+        }
+    // ---- depths (0 = outlet of a piece), cut edges, ghosts, lags --------------------------------------------------------
+    std::vector<int> depth(n, 0), ghost_slot(n, -1), n_ghost(nw, 0), n_exp(nw, 0);
+    for (int h = n - 1; h >= 0; --h) {
+        const int v = order[h];
+        depth[v] = (pl->down[v] < 0 || cut[v]) ? 0 : depth[pl->down[v]] + 1;
+        sp->Dw[cell_warp[v]] = std::max(sp->Dw[cell_warp[v]], depth[v]);
+    }
+    for (int v = 0; v < n; ++v)
+        if (cut[v]) {
+            const int r = pl->down[v], wp = cell_warp[v], wc = cell_warp[r];
+            if (wp == wc || n_ghost[wc] >= SK_XG || n_exp[wp] >= SK_XO) {
+                delete sp;
+                return nullptr;
+            }
+            const int e = (int)sp->edge_prod.size();
+            sp->edge_prod.push_back(wp);
+            sp->edge_cons.push_back(wc);
+            sp->edge_cell.push_back(v);
+            ghost_slot[v] = n_ghost[wc]++;
+            sp->ghost_edge[(size_t)wc * SK_XG + ghost_slot[v]] = e;
+            sp->Dw[wc] = std::max(sp->Dw[wc], depth[r] + 1);
+            const int o = n_exp[wp]++;
+            sp->exp_edge[(size_t)wp * SK_XO + o] = e;
+            sp->exp_place[(size_t)wp * SK_XO + o] = place[v];
+        }
+    sp->n_edges = (int)sp->edge_prod.size();
+    for (int w = 0; w < nw; ++w) {
+        // ghost entries are loaded one iteration ahead of their use (software pipelining of the import): with every
+        // lag of the warp one larger a ghost never has lag 0, i.e. never reads a series entry of a chunk still in flight
+        if (n_ghost[w] > 0) sp->Dw[w] += 1;
+        sp->G = std::max(sp->G, n_ghost[w]);
+        sp->Dmax = std::max(sp->Dmax, sp->Dw[w]);
+        if (sp->Dw[w] > SK_DMAX + 1) {
+            delete sp;
+            return nullptr;
+        }
+    }
+    for (int v = 0; v < n; ++v) {
+        const int w = cell_warp[v];
+        sp->cell[(size_t)w * CAP + place[v]] = v;
+        sp->lag[(size_t)w * CAP + place[v]] = sp->Dw[w] - depth[v];
+        if (cut[v]) {
+            const int r = pl->down[v], wc = cell_warp[r];
+            sp->ghost_lag[(size_t)wc * SK_XG + ghost_slot[v]] = sp->Dw[wc] - (depth[r] + 1);
+        }
+    }
+    // ---- row terms ----------------------------------------------------------------------------------------------------------
+    for (int v = 0; v < n; ++v) {
+        const int w = cell_warp[v], lane = place[v] & 31, slot = place[v] >> 5;
+        int *row = &sp->src[((size_t)w * 32 + lane) * NS];
+        auto entry = [&](int j) { return cell_warp[j] == w ? place[j] : CAP + ghost_slot[j]; };
+        const int beg = pl->row_ptr[v], cnt = pl->row_ptr[v + 1] - beg;
+        if (slot == 0) {
+            int before = 0;
+            for (int s = 0; s < cnt; ++s) before += pl->col[beg + s] < v ? 1 : 0;
+            int ib = SK_NB - before, ia = SK_NB;   // before terms right-aligned in 0..3, after terms in 4..7
+            for (int s = 0; s < cnt; ++s) {
+                const int j = pl->col[beg + s];
+                if (j == v) continue;
+                if (j < v) row[ib++] = entry(j);
+                else row[ia++] = entry(j);
+            }
+        } else {
+            for (int s = 0; s < cnt; ++s) {
+                const int j = pl->col[beg + s];
+                if (j != v) row[2 * SK_NB + slot - 1] = entry(j);
+            }
+        }
+    }
+    return sp;
+}
+
+static SkewPlan *get_skew(xan_mrtm_plan *pl) {
+    if (!pl->skew_tried) {
+        pl->skew_tried = true;
+        const char *ek = getenv("XANTHOS_MRTM_SKEW_K");
+        const int K = ek ? std::max(2, std::min(8, atoi(ek))) : 4;
+        pl->skew = build_skew(pl, K);
+    }
+    return pl->skew;
+}
+
+
+// =============================================================================================
+// device
+// =============================================================================================
+struct SkewArgs {
+    const int *cell, *lag, *src, *ghost_edge, *ghost_lag, *exp_edge, *exp_place, *Dw, *edge_prod, *edge_cons;
+    int *progress;               // [nw] sub-steps handed over / consumed (see the block prologue)
+    double2 *ring;               // [n_edges][RL] (F, F') by absolute sub-step
+    const double *runoff, *chs_prev, *flow_dist, *velocity, *area;
+    const int *step_start;       // [M + 1] first absolute sub-step of every routing step (spin-up months, then months)
+    const int *step_nt;          // [M]
+    const int *step_month;       // [M] runoff month read by the step
+    const double *step_secs;     // [M]
+    double *chs, *avg, *instream;
+    int nw, M, T, spinup, ld, RL, G, sleep_ns;
+    double dt;
+    long long *dbg;              // optional [nw][4]: cycles total, prologue wait, events, SM sub-partition
+};
+
+__device__ __forceinline__ int sk_ld_relaxed_pred(const int *p, int pred, int dflt) {
+    int v = dflt;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.relaxed.gpu.global.s32 %0, [%1];\n\t}"
+                 : "+r"(v)
+                 : "l"(p), "r"(pred)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void sk_st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double2 sk_lds(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sk_sts(unsigned addr, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void sk_sts_pred(unsigned addr, double x, double y, int pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t@p st.shared.v2.f64 [%0], {%1, %2};\n\t}" ::"r"(addr),
+                 "d"(x), "d"(y), "r"(pred)
+                 : "memory");
+}
+__device__ __forceinline__ void sk_stg_pred(double2 *p, double x, double y, int pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t@p st.global.v2.f64 [%0], {%1, %2};\n\t}" ::"l"(p),
+                 "d"(x), "d"(y), "r"(pred)
+                 : "memory");
+}
+
+template <int K>
+struct SkewLane {
+    double S[K], ti[K], erl[K], fav[K];
+    double erln[K], pend[K], qn[K], ar[K];   // lateral inflow of the next step, monthly sum waiting for its division,
+                                             // prefetched runoff of the step after the next, cell area
+    int cell[K], lag[K];
+    unsigned sb[2 * SK_NB];      // byte offsets (within one parity of the flow table) of the terms of the wide row
+    unsigned su[K > 1 ? K - 1 : 1];   // ... of the single tributary of the cells in slots 1 .. K-1
+};
+
+// One loop iteration of one warp.  RD / WR: shared-memory byte addresses of the table parity read / written.
+// The shared-memory accesses are volatile asm statements, which the compiler keeps in program order: all loads of
+// the iteration are therefore issued first (one batch, their latencies overlap), then the K independent balances,
+// then the stores.  (With the loads inside the per-slot code every slot waited for the store of the slot before it:
+// 96 ms instead of the numbers in DESIGN.md.)
+template <int K>
+struct SkewLoads {
+    double2 t[2 * SK_NB];
+    double2 u[K > 1 ? K - 1 : 1];
+};
+
+template <int K>
+__device__ __forceinline__ void skew_load(SkewLoads<K> &R, const SkewLane<K> &L, const unsigned RD) {
+#pragma unroll
+    for (int j = 0; j < 2 * SK_NB; ++j) R.t[j] = sk_lds(RD + L.sb[j]);
+#pragma unroll
+    for (int s = 1; s < K; ++s) R.u[s - 1] = sk_lds(RD + L.su[s - 1]);
+}
+
+template <int K>
+__device__ __forceinline__ void skew_compute_store(SkewLane<K> &L, const SkewLoads<K> &R, const unsigned WR,
+                                                   const int lane, const double dt, const double dtinv) {
+    double Fo[K], Fpo[K];
+    // ---- slot 0: up to SK_NB tributaries before and SK_NB after the cell's own column (mrtm.py:51 in CSR order) ----
+    {
+        const double F = L.S[0] * L.ti[0];                                          // mrtm.py:50
+        double d = R.t[0].x, d2 = R.t[0].y;
+#pragma unroll
+        for (int j = 1; j < SK_NB; ++j) {
+            d = d + R.t[j].x;
+            d2 = d2 + R.t[j].y;
+        }
+        d = d - F;
+        d2 = d2 - F;
+#pragma unroll
+        for (int j = SK_NB; j < 2 * SK_NB; ++j) {
+            d = d + R.t[j].x;
+            d2 = d2 + R.t[j].y;
+        }
+        d = d + L.erl[0];                                                           // balance with the trial flows
+        d2 = d2 + L.erl[0];                                                         // balance with the final flows, :68
+        const bool clamp = (d * dt) < (-L.S[0]);                                    // :54
+        const double Sn = L.S[0] + d2 * dt;                                         // :69 / :76
+        const double Fc = (d + F) + L.S[0] * dtinv;                                 // :60
+        const double Fp = clamp ? Fc : F;
+        L.S[0] = clamp ? 0.0 : Sn;                                                  // :63
+        L.fav[0] = L.fav[0] + Fp;                                                   // :78
+        Fo[0] = F;
+        Fpo[0] = Fp;
+    }
+    // ---- slots 1 .. K-1: at most one tributary; a two-term row is order-free ---------------------------------------
+#pragma unroll
+    for (int s = 1; s < K; ++s) {
+        const double2 u = R.u[s - 1];
+        const double F = L.S[s] * L.ti[s];
+        const double d = (u.x - F) + L.erl[s];
+        const double d2 = (u.y - F) + L.erl[s];
+        const bool clamp = (d * dt) < (-L.S[s]);
+        const double Sn = L.S[s] + d2 * dt;
+        const double Fc = (d + F) + L.S[s] * dtinv;
+        const double Fp = clamp ? Fc : F;
+        L.S[s] = clamp ? 0.0 : Sn;
+        L.fav[s] = L.fav[s] + Fp;
+        Fo[s] = F;
+        Fpo[s] = Fp;
+    }
+#pragma unroll
+    for (int s = 0; s < K; ++s) sk_sts(WR + (unsigned)(s * 32 + lane) * 16u, Fo[s], Fpo[s]);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256, 1) mrtm_skew_kernel(const SkewArgs a) {
+    extern __shared__ __align__(16) unsigned char sk_smem[];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int w = wib * gridDim.x + blockIdx.x;     // consecutive plan warps on different SMs
+    if (w >= a.nw) return;                          // no block-level barrier below
+    constexpr int CAP = 32 * K, NE = CAP + SK_XG + 1, NS = 2 * SK_NB + K - 1;
+    constexpr unsigned PSTRIDE = NE * 16u;
+    const int per_warp = (2 * NE + a.G * SK_W) * 16;
+    const unsigned EX0 = (unsigned)__cvta_generic_to_shared(sk_smem + (size_t)wib * per_warp);
+    const unsigned ST0 = EX0 + 2 * PSTRIDE;
+    for (int i = lane; i < per_warp / 16; i += 32) sk_sts(EX0 + (unsigned)i * 16u, 0.0, 0.0);
+    __syncwarp();
+
+    const bool dbg = a.dbg != nullptr;
+    const long long cyc0 = dbg ? clock64() : 0;
+    long long cyc_wait = 0, cyc_evt = 0;
+    const int Dw = a.Dw[w], M = a.M, T = a.T, RL = a.RL;
+    const double dt = a.dt, dtinv = 1. / a.dt;                                      // mrtm.py:43
+    SkewLane<K> L;
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        const int c = a.cell[(size_t)w * CAP + s * 32 + lane];
+        L.cell[s] = c;
+        L.lag[s] = a.lag[(size_t)w * CAP + s * 32 + lane];
+        L.S[s] = 0.0; L.ti[s] = 0.0; L.erl[s] = 0.0; L.fav[s] = 0.0; L.qn[s] = 0.0; L.ar[s] = 0.0;
+        L.erln[s] = 0.0; L.pend[s] = 0.0;
+        if (c >= 0) {
+            L.ti[s] = a.velocity[c] / a.flow_dist[c];                               // mrtm.py:42
+            L.ar[s] = a.area[c];
+            L.erln[s] = ((a.runoff[(size_t)a.step_month[0] * a.ld + c] * L.ar[s]) * (1e6 / 1e3)) / a.step_secs[0];   // mrtm.py:45
+            if (a.M > 1) L.qn[s] = a.runoff[(size_t)a.step_month[1] * a.ld + c];
+        }
+    }
+    {
+        const int *row = a.src + ((size_t)w * 32 + lane) * NS;
+#pragma unroll
+        for (int j = 0; j < 2 * SK_NB; ++j) L.sb[j] = (unsigned)row[j] * 16u;
+#pragma unroll
+        for (int s = 1; s < K; ++s) L.su[s - 1] = (unsigned)row[2 * SK_NB + s - 1] * 16u;
+    }
+    // ---- ghost imports (lanes 0 .. 15) and exports (lanes 16 .. 31) ------------------------------------------------
+    const int xi = lane & 15;
+    const bool imp_lane = lane < SK_XG;
+    const int xedge = imp_lane ? a.ghost_edge[(size_t)w * SK_XG + xi] : a.exp_edge[(size_t)w * SK_XO + xi];
+    const bool imp = imp_lane && xedge >= 0, expo = !imp_lane && xedge >= 0;
+    const int glag = imp ? a.ghost_lag[(size_t)w * SK_XG + xi] : 0;
+    const unsigned eplace16 = (unsigned)(expo ? a.exp_place[(size_t)w * SK_XO + xi] : CAP + SK_XG) * 16u;
+    double2 *const xring = a.ring + (size_t)(xedge >= 0 ? xedge : 0) * RL;
+    const int peer = imp ? a.edge_prod[xedge] : (expo ? a.edge_cons[xedge] : 0);
+    const unsigned ghost_mask = __ballot_sync(full, imp);
+    const bool has_exp = __any_sync(full, expo);
+    const bool linked = ghost_mask != 0 || has_exp;
+    const unsigned stg_lane = ST0 + (unsigned)xi * (SK_W * 16u);                    // this import lane's staged series
+    const unsigned zero_addr = EX0 + (unsigned)(CAP + SK_XG) * 16u;                 // all-zero entry (parity 0)
+
+    auto wait_peers = [&](int need_p, int need_c) {
+        const int poll_p = imp ? 1 : 0, poll_c = (expo && need_c > 0) ? 1 : 0;
+        const int *pp = a.progress + peer;
+        for (;;) {
+            const int vp = sk_ld_relaxed_pred(pp, poll_p, need_p), vc = sk_ld_relaxed_pred(pp, poll_c, need_c);
+            if (__all_sync(full, vp >= need_p && vc >= need_c)) break;
+            __nanosleep(a.sleep_ns);
+        }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire side of the hand-over
+        __syncwarp();
+    };
+    auto stage_chunk = [&](int tau0) {             // ring entries tau0 .. tau0 + SK_CH - 1 of every ghost -> shared memory
+        unsigned gm = ghost_mask;
+        while (gm) {
+            const int g = __ffs(gm) - 1;
+            gm &= gm - 1;
+            const double2 *rp = reinterpret_cast<const double2 *>(__shfl_sync(full, (unsigned long long)xring, g));
+#pragma unroll
+            for (int h = 0; h < SK_CH / 32; ++h) {
+                const int tau = tau0 + h * 32 + lane;
+                if (tau < T) {
+                    const unsigned dst = ST0 + ((unsigned)g * SK_W + (unsigned)(tau & (SK_W - 1))) * 16u;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rp + (tau & (RL - 1))) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (ghost_mask) {
+        wait_peers(min(T, SK_CH), 0);
+        stage_chunk(0);
+    }
+
+    // Boundary b = start of routing step b (b = M: end of the run).  A cell crosses it `lag` iterations after the window
+    // opens.  Everything the event code needs is in registers before the window opens (a global load or a division
+    // inside the window stalls the warp): at the crossing a cell only stores its storage, parks its monthly sum and
+    // switches to the lateral inflow prepared for the new step; the divisions (monthly mean, mrtm.py:80; lateral
+    // inflow of the step after, :45) are done for all slots together when the window closes.
+    int b = 0, evt = a.step_start[0];
+    double ev_nt_prev = 1.0, ev_secs_next = a.step_secs[M > 1 ? 1 : 0];
+    size_t ev_next2_off = (size_t)a.step_month[M > 2 ? 2 : 0] * a.ld, ev_out_off = 0;
+    double2 xv = make_double2(0.0, 0.0);            // ghost import / export value of the coming iteration
+    const int nlast = T + Dw;
+    for (int n0 = 0; n0 <= nlast; n0 += SK_CH) {
+        if (linked) {
+            const long long c0 = dbg ? clock64() : 0;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");                    // chunk n0 / SK_CH has landed
+            __syncwarp();   // every lane's ring reads and exports are ordered before lane 0's release below
+            // hand-over: every export up to sub-step n0 - 2 - Dw is in the ring; every ring entry below n0 + SK_CH of
+            // the edges this warp consumes is in shared memory
+            if (lane == 0) sk_st_release(a.progress + w, max(0, min(T, n0 - 1 - Dw)));
+            wait_peers(min(T, n0 + 2 * SK_CH), n0 + SK_CH - RL);
+            if (ghost_mask) stage_chunk(n0 + SK_CH);
+            if (dbg) cyc_wait += clock64() - c0;
+        }
+#pragma unroll 1
+        for (int i = 0; i < SK_CH; i += 2) {
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {
+                const int n = n0 + i + par;
+                const unsigned RD = EX0 + (par ? 0u : PSTRIDE), WR = EX0 + (par ? PSTRIDE : 0u);
+                // ---- per-cell month events (rare: Dw + 1 iterations per month) -----------------------------------
+                if (n >= evt) {
+                    const long long c0 = dbg ? clock64() : 0;
+                    const int k = n - evt;
+                    const bool st = b > 0 && b - 1 >= a.spinup;
+#pragma unroll
+                    for (int s = 0; s < K; ++s) {
+                        const int c = L.cell[s];
+                        if (c >= 0 && L.lag[s] == k) {
+                            if (st && a.chs) stg_stream(a.chs + ev_out_off + c, L.S[s]);
+                            if (b == M && a.instream) a.instream[c] = sk_lds(RD + (unsigned)(s * 32 + lane) * 16u).y;
+                            L.pend[s] = L.fav[s];
+                            L.fav[s] = 0.0;
+                            L.erl[s] = L.erln[s];
+                            if (b == 0) L.S[s] = a.chs_prev ? a.chs_prev[c] : 0.0;
+                        }
+                    }
+                    if (k == Dw) {   // every cell has crossed: window closed
+#pragma unroll
+                        for (int s = 0; s < K; ++s) {
+                            const int c = L.cell[s];
+                            if (c >= 0) {
+                                if (st && a.avg) stg_stream(a.avg + ev_out_off + c, L.pend[s] / ev_nt_prev);   // mrtm.py:80
+                                if (b + 1 < M) L.erln[s] = ((L.qn[s] * L.ar[s]) * (1e6 / 1e3)) / ev_secs_next;  // mrtm.py:45
+                                if (b + 2 < M) L.qn[s] = a.runoff[ev_next2_off + c];                            // used a month later
+                            }
+                        }
+                        ++b;   // constants of the next window, fetched a month ahead of their use
+                        evt = (b <= M) ? a.step_start[b] : 0x7fffffff;
+                        if (b <= M) ev_nt_prev = (double)a.step_nt[b - 1];
+                        if (b + 1 < M) ev_secs_next = a.step_secs[b + 1];
+                        if (b + 2 < M) ev_next2_off = (size_t)a.step_month[b + 2] * a.ld;
+                        ev_out_off = (size_t)max(0, b - 1 - a.spinup) * a.ld;
+                    }
+                    __syncwarp();
+                    if (dbg) cyc_evt += clock64() - c0;
+                }
+                // ---- ghost imports and exports: the value was loaded at the end of the previous iteration ---------
+                if (linked) {
+                    sk_sts_pred(WR + (unsigned)(CAP + xi) * 16u, xv.x, xv.y, imp_lane ? 1 : 0);
+                    const int tau = n - 1 - Dw;
+                    sk_stg_pred(xring + (tau & (RL - 1)), xv.x, xv.y, (expo && tau >= 0 && tau < T) ? 1 : 0);
+                }
+                SkewLoads<K> R;
+                skew_load<K>(R, L, RD);
+                skew_compute_store<K>(L, R, WR, lane, dt, dtinv);
+                if (linked) {   // for iteration n + 1: staged entry n + 1 - lag (lag >= 1: chunk landed), or the cell just stored
+                    const unsigned xaddr = imp ? stg_lane + ((unsigned)((n + 1 - glag) & (SK_W - 1)) << 4)
+                                               : (expo ? WR + eplace16 : zero_addr);
+                    xv = sk_lds(xaddr);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    if (linked) {
+        __syncwarp();
+        if (lane == 0) sk_st_release(a.progress + w, T);
+    }
+    if (dbg && lane == 0) {
+        unsigned smid, wid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        a.dbg[4 * w] = clock64() - cyc0;
+        a.dbg[4 * w + 1] = cyc_wait;
+        a.dbg[4 * w + 2] = cyc_evt;
+        a.dbg[4 * w + 3] = smid * 4 + (wid & 3);
+    }
+}
+
+template <typename V>
+static bool sk_upload(const std::vector<V> &h, V **d) {
+    const size_t bytes = sizeof(V) * std::max<size_t>(h.size(), 1);
+    if (cudaMalloc((void **)d, bytes) != cudaSuccess) return false;
+    if (!h.empty() && cudaMemcpy(*d, h.data(), sizeof(V) * h.size(), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    return true;
+}
+
+template <int K>
+static int launch_skew(SkewPlan *sp, SkewArgs &a, int sms, cudaStream_t s) {
+    auto kernel = mrtm_skew_kernel<K>;
+    const int per_warp = (2 * (32 * K + SK_XG + 1) + sp->G * SK_W) * 16;
+    int wpb = std::max(4, ((ceil_div(sp->nw, sms) + 3) / 4) * 4);
+    if (wpb > 8) return XAN_E_INVALID;
+    const size_t smem = (size_t)per_warp * wpb;
+    if (smem > 200 * 1024) return XAN_E_INVALID;
+    XAN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int per_sm = 0;
+    XAN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpb * 32, smem));
+    const int blocks = std::min(sms, sp->nw);
+    if (per_sm < 1 || blocks * wpb < sp->nw) return XAN_E_INVALID;
+    void *kargs[] = {(void *)&a};
+    // cooperative launch = all blocks co-resident (the cut-edge pipeline needs every warp alive; no grid.sync is used)
+    XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kernel, dim3(blocks), dim3(wpb * 32), kargs, smem, s));
+    return XAN_OK;
+}
+
+// Routes one member with the skew kernel.  Returns XAN_E_INVALID (without an error message) when the plan or the
+// calendar does not allow it, so that the caller can fall back to the warp-dataflow kernel.
+int route_skew(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_dist, const double *d_velocity,
+               const double *d_area, const double *d_chs_prev, const int *h_ndays, int nmonths, int spinup_months, int ld,
+               double dt, double *d_chs, double *d_avg, double *d_instream, int sms, cudaStream_t s) {
+    SkewPlan *sp = get_skew(pl);
+    if (!sp) return XAN_E_INVALID;
+    const int M = spinup_months + nmonths;
+    std::vector<int> start(M + 1, 0), nts(M), month(M);
+    std::vector<double> secs(M);
+    long long total = 0;
+    int nt_min = 1 << 30;
+    for (int b = 0; b < M; ++b) {
+        const int m = b < spinup_months ? b : b - spinup_months;
+        month[b] = m;
+        nts[b] = (int)((double)h_ndays[m] * 24 * 3600 / dt);                       // mrtm.py:36
+        secs[b] = (double)(h_ndays[m] * 24 * 3600);
+        nt_min = std::min(nt_min, nts[b]);
+        total += nts[b];
+        if (total > 0x3fffffff) return XAN_E_INVALID;
+        start[b + 1] = (int)total;
+    }
+    // the event windows of consecutive month boundaries (max lag + 1 iterations) must not overlap
+    if (nt_min <= sp->Dmax + 1) return XAN_E_INVALID;
+    if (!sp->on_device) {
+        std::vector<int> zeros(sp->nw, 0);
+        const bool ok = sk_upload(sp->cell, &sp->d_cell) && sk_upload(sp->lag, &sp->d_lag) && sk_upload(sp->src, &sp->d_src) &&
+                        sk_upload(sp->ghost_edge, &sp->d_ghost_edge) && sk_upload(sp->ghost_lag, &sp->d_ghost_lag) &&
+                        sk_upload(sp->exp_edge, &sp->d_exp_edge) && sk_upload(sp->exp_place, &sp->d_exp_place) &&
+                        sk_upload(sp->Dw, &sp->d_Dw) && sk_upload(sp->edge_prod, &sp->d_edge_prod) &&
+                        sk_upload(sp->edge_cons, &sp->d_edge_cons) && sk_upload(zeros, &sp->d_progress);
+        if (!ok) {
+            set_error("mrtm skew plan: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return XAN_E_CUDA;
+        }
+        sp->on_device = true;
+    }
+    SkewArgs a;
+    memset(&a, 0, sizeof(a));
+    a.cell = sp->d_cell; a.lag = sp->d_lag; a.src = sp->d_src; a.ghost_edge = sp->d_ghost_edge;
+    a.ghost_lag = sp->d_ghost_lag; a.exp_edge = sp->d_exp_edge; a.exp_place = sp->d_exp_place; a.Dw = sp->d_Dw;
+    a.edge_prod = sp->d_edge_prod; a.edge_cons = sp->d_edge_cons; a.progress = sp->d_progress;
+    a.runoff = d_runoff; a.chs_prev = d_chs_prev; a.flow_dist = d_flow_dist; a.velocity = d_velocity; a.area = d_area;
+    a.chs = d_chs; a.avg = d_avg; a.instream = d_instream;
+    a.nw = sp->nw; a.M = M; a.T = (int)total; a.spinup = spinup_months; a.ld = ld; a.G = sp->G; a.dt = dt;
+    const char *er = getenv("XANTHOS_MRTM_SKEW_RING"), *es = getenv("XANTHOS_MRTM_SLEEP_NS");
+    int RL = er ? atoi(er) : 1024;
+    if (RL < 256 || (RL & (RL - 1))) RL = 1024;
+    a.RL = RL;
+    a.sleep_ns = es ? std::max(0, atoi(es)) : 100;
+    // step tables: one allocation [start (M+1) | nt (M) | month (M)] ints + [secs (M)] doubles
+    int *d_int = nullptr;
+    double *d_secs = nullptr;
+    std::vector<int> hint;
+    hint.insert(hint.end(), start.begin(), start.end());
+    hint.insert(hint.end(), nts.begin(), nts.end());
+    hint.insert(hint.end(), month.begin(), month.end());
+    XAN_CUDA_CHECK(scratch_alloc(&d_int, sizeof(int) * hint.size(), s));
+    XAN_CUDA_CHECK(scratch_alloc(&d_secs, sizeof(double) * M, s));
+    // pageable host memory: cudaMemcpyAsync returns after the data were staged, the vectors may go out of scope
+    XAN_CUDA_CHECK(cudaMemcpyAsync(d_int, hint.data(), sizeof(int) * hint.size(), cudaMemcpyHostToDevice, s));
+    XAN_CUDA_CHECK(cudaMemcpyAsync(d_secs, secs.data(), sizeof(double) * M, cudaMemcpyHostToDevice, s));
+    a.step_start = d_int;
+    a.step_nt = d_int + (M + 1);
+    a.step_month = d_int + (M + 1) + M;
+    a.step_secs = d_secs;
+    double2 *ring = nullptr;
+    XAN_CUDA_CHECK(scratch_alloc(&ring, sizeof(double2) * (size_t)std::max(sp->n_edges, 1) * RL, s));
+    a.ring = ring;
+    XAN_CUDA_CHECK(cudaMemsetAsync(sp->d_progress, 0, sizeof(int) * sp->nw, s));
+    const char *edbg = getenv("XANTHOS_MRTM_DEBUG");
+    if (edbg) XAN_CUDA_CHECK(scratch_alloc(&a.dbg, sizeof(long long) * 4 * sp->nw, s));
+    int rc = XAN_E_INVALID;
+    switch (sp->K) {
+        case 2: rc = launch_skew<2>(sp, a, sms, s); break;
+        case 3: rc = launch_skew<3>(sp, a, sms, s); break;
+        case 4: rc = launch_skew<4>(sp, a, sms, s); break;
+        case 5: rc = launch_skew<5>(sp, a, sms, s); break;
+        case 6: rc = launch_skew<6>(sp, a, sms, s); break;
+        default: break;
+    }
+    if (rc == XAN_OK && a.dbg) {
+        std::vector<long long> h(4 * (size_t)sp->nw);
+        XAN_CUDA_CHECK(cudaMemcpyAsync(h.data(), a.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, s));
+        XAN_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (FILE *f = fopen(edbg, "w")) {
+            for (int w = 0; w < sp->nw; ++w)
+                fprintf(f, "%d %lld %lld %lld %lld %d\n", w, h[4 * w], h[4 * w + 1], h[4 * w + 2], h[4 * w + 3], sp->Dw[w]);
+            fclose(f);
+        }
+    }
+    if (a.dbg) cudaFreeAsync(a.dbg, s);
+    cudaFreeAsync(ring, s);
+    cudaFreeAsync(d_int, s);
+    cudaFreeAsync(d_secs, s);
+    return rc;
+}
+
+}  // namespace xan
+
+extern "C" {
+
+// Test / diagnostics access to the skew plan (sizes first, then the tables as int arrays; null pointers are skipped).
+// info: K, n_warps, n_edges, n_levels, max ghosts per warp, max lag, pieces, sources per lane, zero entry, XG, XO
+int xan_mrtm_skew_info(xan_mrtm_plan *pl, int *info) {
+    XAN_REQUIRE(pl && info, "xan_mrtm_skew_info: null pointer");
+    xan::SkewPlan *sp = xan::get_skew(pl);
+    if (!sp) {
+        for (int i = 0; i < 11; ++i) info[i] = 0;
+        return XAN_OK;
+    }
+    const int v[11] = {sp->K, sp->nw, sp->n_edges, sp->n_levels, sp->G, sp->Dmax, sp->n_pieces, sp->nsrc(),
+                       sp->zero_entry(), xan::SK_XG, xan::SK_XO};
+    for (int i = 0; i < 11; ++i) info[i] = v[i];
+    return XAN_OK;
+}
+
+int xan_mrtm_skew_tables(xan_mrtm_plan *pl, int *cell, int *lag, int *src, int *ghost_edge, int *ghost_lag,
+                         int *exp_edge, int *exp_place, int *Dw, int *edge_prod, int *edge_cons) {
+    XAN_REQUIRE(pl, "xan_mrtm_skew_tables: null plan");
+    xan::SkewPlan *sp = xan::get_skew(pl);
+    XAN_REQUIRE(sp, "xan_mrtm_skew_tables: no skew plan for this flow graph");
+    auto cp = [](const std::vector<int> &v, int *dst) {
+        if (dst) std::copy(v.begin(), v.end(), dst);
+    };
+    cp(sp->cell, cell); cp(sp->lag, lag); cp(sp->src, src); cp(sp->ghost_edge, ghost_edge);
+    cp(sp->ghost_lag, ghost_lag); cp(sp->exp_edge, exp_edge); cp(sp->exp_place, exp_place); cp(sp->Dw, Dw);
+    cp(sp->edge_prod, edge_prod); cp(sp->edge_cons, edge_cons);
+    return XAN_OK;
+}
+
+}  // extern "C"
