@@ -162,11 +162,12 @@ int xan_mrtm_plan_packing(const xan_mrtm_plan *plan, int *h_lane_cell, int *h_ed
 /* diagnostic export of the skew-kernel plan (csrc/mrtm_skew.cu; built on first use).
  * info[0]=K (cells per lane) [1]=n_warps [2]=n_cut_edges [3]=n_levels [4]=max ghost entries of a warp
  * [5]=max lag [6]=n_pieces [7]=row-term sources per lane [8]=index of the all-zero table entry
- * [9]=ghost entries per warp [10]=export entries per warp; all zero if the graph has no skew plan.
+ * [9]=ghost entries per warp [10]=export entries per warp [11]=iterations a cell lags its tributaries;
+ * all zero if the graph has no skew plan.
  * Tables (any pointer may be NULL): cell, lag [n_warps][32 K]; src [n_warps][32][info[7]];
  * ghost_edge, ghost_lag [n_warps][info[9]]; exp_edge, exp_place [n_warps][info[10]]; Dw [n_warps];
  * edge_prod, edge_cons [n_cut_edges]. */
-int xan_mrtm_skew_info(xan_mrtm_plan *plan, int *info11);
+int xan_mrtm_skew_info(xan_mrtm_plan *plan, int *info12);
 int xan_mrtm_skew_tables(xan_mrtm_plan *plan, int *cell, int *lag, int *src, int *ghost_edge,
                          int *ghost_lag, int *exp_edge, int *exp_place, int *Dw, int *edge_prod,
                          int *edge_cons);

@@ -17,7 +17,7 @@ def skew_tables(um):
     """Plan tables of an UpstreamMatrix (xanthos_b200.routing.mrtm.upstream_genmatrix) as a dict of int arrays."""
     from xanthos_b200 import _cuda as C
     lib = C.lib()
-    info = (ctypes.c_int * 11)()
+    info = (ctypes.c_int * 12)()
     C.check(lib.xan_mrtm_skew_info(um._plan, info))
     info = list(info)
     K, nw, ne = info[0], info[1], info[2]
@@ -33,14 +33,14 @@ def skew_tables(um):
                                                                       'edge_cons')]))
     t['edge_prod'], t['edge_cons'] = t['edge_prod'][:ne], t['edge_cons'][:ne]
     t['info'] = dict(K=K, n_warps=nw, n_edges=ne, n_levels=info[3], G=info[4], Dmax=info[5], n_pieces=info[6],
-                     nsrc=ns, zero=info[8], XG=xg, XO=xo)
+                     nsrc=ns, zero=info[8], XG=xg, XO=xo, lagm=info[11])
     return t
 
 
 def route(t, q, flow_dist, velocity, area, ndays, dt, spinup, chs_prev=None):
     """q [ncell, nmonths] -> (ChStorage, Avg_ChFlow [ncell, nmonths], instream flow [ncell]) by the skewed schedule."""
     inf = t['info']
-    K, nw, ne, ZERO, XG = inf['K'], inf['n_warps'], inf['n_edges'], inf['zero'], inf['XG']
+    K, nw, ne, ZERO, XG, LAGM = inf['K'], inf['n_warps'], inf['n_edges'], inf['zero'], inf['XG'], inf['lagm']
     CAP = 32 * K
     ncell, nmonths = q.shape
     steps = list(range(spinup)) + list(range(nmonths))                  # runoff month of every routing step
@@ -77,12 +77,11 @@ def route(t, q, flow_dist, velocity, area, ndays, dt, spinup, chs_prev=None):
         ti = np.zeros(CAP)
         erl = np.zeros(CAP)
         fav = np.zeros(CAP)
-        exch = np.zeros((2, CAP + XG + 1, 2))
+        exch = np.zeros((LAGM + 1, CAP + XG + 1, 2))        # a reader reads what was written LAGM iterations earlier
         tauinv = np.where(has, velocity[cidx] / flow_dist[cidx], 0.0)
         b, evt = 0, int(start[0])
         for n in range(T + Dw + 1):
-            par = n & 1
-            rd, wr = exch[par ^ 1], exch[par]
+            rd, wr, last = exch[(n - LAGM) % (LAGM + 1)], exch[n % (LAGM + 1)], exch[(n - 1) % (LAGM + 1)]
             # ---- per-cell month events ------------------------------------------------------------------------
             if b <= M and n >= evt:
                 k = n - evt
@@ -95,7 +94,7 @@ def route(t, q, flow_dist, velocity, area, ndays, dt, spinup, chs_prev=None):
                             chs[c, mprev - spinup] = S[hit]
                             avg[c, mprev - spinup] = fav[hit] / nt[mprev]
                     if b == M:
-                        inst[c] = rd[np.nonzero(hit)[0], 1]
+                        inst[c] = last[np.nonzero(hit)[0], 1]
                     else:
                         fav[hit] = 0.0
                         erl[hit] = (q[c, steps[b]] * area[c]) * (1e6 / 1e3) / secs[b]
@@ -115,7 +114,7 @@ def route(t, q, flow_dist, velocity, area, ndays, dt, spinup, chs_prev=None):
                 e = t['exp_edge'][w, o]
                 tau = n - 1 - Dw
                 if e >= 0 and 0 <= tau < T:
-                    ring[e, tau] = rd[t['exp_place'][w, o]]
+                    ring[e, tau] = last[t['exp_place'][w, o]]
             # ---- the K slots --------------------------------------------------------------------------------------
             F = S * ti
             d = np.empty(CAP)

@@ -263,3 +263,30 @@ def test_device_copies_never_go_stale():
     own.setflags(write=True)
     own *= 0.0
     assert C.resident(own) is None
+
+
+@pytest.mark.parametrize("K", ['2', '4'])
+def test_skew_routing_kernel_bitwise_against_oracle(K, monkeypatch):
+    """csrc/mrtm_skew.cu (method = MRTM_SKEW): small worlds at three sub-step lengths and the bench world (cut edges
+    between warps, ghost / export series) equal the oracle bit for bit; also equal to the warp-dataflow kernel."""
+    from xanthos_b200 import synthetic, _cuda as C
+    from xanthos_b200.routing import mrtm
+    from oracle import mrtm as omrtm
+    from oracle.calendar_utils import set_month_arrays
+    monkeypatch.setenv('XANTHOS_MRTM_SKEW_K', K)
+    cases = [(synthetic.make_world(24, 48, 320, 5, seed=43), 10800.0, 5, 2),
+             (synthetic.make_world(36, 72, 1500, 12, seed=0), 21600.0, 3, 3),
+             (synthetic.make_world(36, 72, 1500, 12, seed=0), 3600.0, 2, 1),
+             (synthetic.make_world(seed=0), 10800.0, 12, 6)]
+    for w, dt, months, spin in cases:
+        s = w.settings()
+        up = mrtm.upstream(w.coords, mrtm.downstream(w.coords, w.flow_dir, s), s)
+        um = mrtm.upstream_genmatrix(up)
+        q = synthetic.runoff_input(w, months, seed=3)
+        nd = set_month_arrays(24, 1971, 1972)[:months, 2]
+        got = mrtm.route(um, q, w.flow_dist, w.velocity, w.area, nd, dt, spin, method=C.MRTM_SKEW)
+        oup = omrtm.upstream_fast(w.coords, omrtm.downstream(w.coords, w.flow_dir, w.nrow, w.ncol), w.nrow, w.ncol)
+        want = omrtm.route(q, w.flow_dist, w.velocity, w.area, nd, dt, omrtm.csr_rows(oup), spin)
+        tree = mrtm.route(um, q, w.flow_dist, w.velocity, w.area, nd, dt, spin, method=C.MRTM_TREE)
+        for a, b, c, name in zip(got, want, tree, ('ChStorage', 'Avg_ChFlow', 'instream_flow')):
+            assert bitwise_equal(a, b) and bitwise_equal(a, c), (w.ncell, dt, name)

@@ -12,7 +12,7 @@ import sys
 import numpy as np
 import pytest
 
-from util import load_golden
+from util import load_golden, bitwise_equal
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -280,3 +280,37 @@ def test_out_writer_formats_round_trip(tmp_path, fmt, ext):
         import pyarrow.parquet as pq
         t = pq.read_table(fq).to_pandas()
         assert list(t.columns) == ['id', '2001', '2002'] and np.array_equal(t.iloc[:, 1:].values, want_q)
+
+
+def test_skew_plan_and_schedule_model_equal_the_oracle_bitwise(monkeypatch):
+    """The plan of the skew routing kernel (csrc/mrtm_skew.cu: pieces, places, per-cell lags, ghost / export entries)
+    driven through the CPU model of the kernel's schedule (tests/skew_model.py) reproduces oracle.mrtm.route bit for
+    bit, for 2 and 4 cells per lane; structural invariants of the tables."""
+    import skew_model
+    from xanthos_b200 import synthetic
+    from xanthos_b200.routing import mrtm
+    from oracle import mrtm as omrtm
+    from oracle.calendar_utils import set_month_arrays
+    w = synthetic.make_world(30, 60, 900, 4, seed=7)
+    s = w.settings()
+    up = mrtm.upstream(w.coords, mrtm.downstream(w.coords, w.flow_dir, s), s)
+    months, spin = 4, 2
+    q = synthetic.runoff_input(w, months, seed=3)
+    nd = set_month_arrays(12, 1971, 1971)[:months, 2]
+    oup = omrtm.upstream_fast(w.coords, omrtm.downstream(w.coords, w.flow_dir, w.nrow, w.ncol), w.nrow, w.ncol)
+    for K in ('2', '4'):
+        monkeypatch.setenv('XANTHOS_MRTM_SKEW_K', K)
+        um = mrtm.upstream_genmatrix(up)
+        t = skew_model.skew_tables(um)
+        inf = t['info']
+        assert inf['K'] == int(K) and inf['n_warps'] > 0
+        cells = t['cell'][t['cell'] >= 0]
+        assert np.array_equal(np.sort(cells), np.arange(w.ncell))                 # every cell has exactly one place
+        assert (t['lag'] >= 0).all() and t['lag'].max() <= inf['Dmax'] and (t['src'] <= inf['zero']).all()
+        wide = np.bincount(up[:, 8].astype(int) >= 2, minlength=2)[1]
+        assert ((t['cell'][:, :32] >= 0).sum() >= wide)                            # rows with >= 2 tributaries sit in slot 0
+        for dt in (10800.0, 21600.0):                                             # 21600 s: many cells empty at every other sub-step
+            got = skew_model.route(t, q, w.flow_dist, w.velocity, w.area, nd, dt, spin)
+            want = omrtm.route(q, w.flow_dist, w.velocity, w.area, nd, dt, omrtm.csr_rows(oup), spin)
+            for a, b, name in zip(got, want, ('ChStorage', 'Avg_ChFlow', 'instream_flow')):
+                assert bitwise_equal(a, b), (K, dt, name)

@@ -21,7 +21,7 @@ mrtm.route_device(um, q, L, V, A, nd, 10800, M, method=C.MRTM_SKEW)
 torch.cuda.synchronize()
 d = np.loadtxt(f)
 T = sum(int(x) * 8 for x in nd) * 2
-tot, wait, evt, sp, dw = d[:, 1], d[:, 2], d[:, 3], d[:, 4], d[:, 5]
+tot, wait, evt, sp, dw, nslow = d[:, 1], d[:, 2], d[:, 3], d[:, 4], d[:, 5], d[:, 6]
 print('iterations', T, 'warps', len(d))
 print('total cycles/iter   pct 0/50/90/100:', np.percentile(tot / T, [0, 50, 90, 100]).round(1))
 print('wait  cycles/iter   pct 0/50/90/100:', np.percentile(wait / T, [0, 50, 90, 100]).round(1))
@@ -30,6 +30,7 @@ loop = (tot - wait - evt) / T
 print('loop  cycles/iter   pct 0/50/90/100:', np.percentile(loop, [0, 50, 90, 100]).round(1))
 free = d[:, 2] == 0
 print('free warps', free.sum(), 'loop median', np.median(loop[free]).round(1), 'linked loop median', np.median(loop[~free]).round(1))
+print('slow iterations fraction pct 0/50/90/100:', np.percentile(nslow / T, [0, 50, 90, 100]).round(3), 'mean', (nslow / T).mean().round(3))
 cnt = np.bincount(sp.astype(int) // 4, minlength=148)
 print('warps per SM min/max', cnt.min(), cnt.max())
 for k in (0, 10, 20, 28):

@@ -39,13 +39,21 @@ namespace xan {
 
 constexpr int SK_XG = 16;        // ghost entries (incoming cut edges) per warp
 constexpr int SK_XO = 16;        // exported cells (outgoing cut edges) per warp
-constexpr int SK_DMAX = 62;      // largest piece height; lags reach SK_DMAX + 1 in warps with ghost entries
+#ifndef XAN_SKEW_LAGM
+#define XAN_SKEW_LAGM 1
+#endif
+// A cell works SK_LAGM iterations behind its tributaries.  1: the terms of iteration n + 1 are loaded after the stores of
+// iteration n.  2: they were stored an iteration earlier and are loaded while iteration n is computed (no load / store
+// latency between iterations, but twice the lags: longer month windows, three table buffers) - measured slower with
+// 4 cells per lane (57.7 against 49.5 ms) and equal with 2 (44.5 ms), see DESIGN.md section 4.
+constexpr int SK_LAGM = XAN_SKEW_LAGM;
+constexpr int SK_DMAX = 62 / SK_LAGM - 1;   // largest piece height; lags reach SK_LAGM (SK_DMAX + 1) in warps with ghost entries
 constexpr int SK_CH = 64;        // sub-steps of a cut-edge series staged per hand-over
 constexpr int SK_W = 4 * SK_CH;  // staged entries kept per ghost (a chunk is read for at most 2 SK_CH iterations)
 constexpr int SK_NB = 4;         // before / after terms of a wide row
 
 struct SkewPlan {
-    int K = 0, nw = 0, n_edges = 0, n_levels = 0, G = 0, Dmax = 0, n_pieces = 0;
+    int K = 0, nw = 0, n_edges = 0, n_levels = 0, G = 0, O = 0, Dmax = 0, n_pieces = 0;
     std::vector<int> cell;         // [nw][K*32] cell index or -1
     std::vector<int> lag;          // [nw][K*32]
     std::vector<int> src;          // [nw][32][2*SK_NB + K - 1] table entry of every row term (ZERO entry = padding)
@@ -53,7 +61,7 @@ struct SkewPlan {
     std::vector<int> ghost_lag;    // [nw][SK_XG]
     std::vector<int> exp_edge;     // [nw][SK_XO] edge or -1
     std::vector<int> exp_place;    // [nw][SK_XO] table entry of the exported cell
-    std::vector<int> Dw;           // [nw]
+    std::vector<int> Dw;           // [nw] largest lag of the warp
     std::vector<int> edge_prod, edge_cons, edge_cell;
     // device copies
     int *d_cell = nullptr, *d_lag = nullptr, *d_src = nullptr, *d_ghost_edge = nullptr, *d_ghost_lag = nullptr,
@@ -321,19 +329,21 @@ static SkewPlan *build_skew(const xan_mrtm_plan *pl, int K) {
         // lag of the warp one larger a ghost never has lag 0, i.e. never reads a series entry of a chunk still in flight
         if (n_ghost[w] > 0) sp->Dw[w] += 1;
         sp->G = std::max(sp->G, n_ghost[w]);
-        sp->Dmax = std::max(sp->Dmax, sp->Dw[w]);
+        sp->O = std::max(sp->O, n_exp[w]);
+        sp->Dmax = std::max(sp->Dmax, SK_LAGM * sp->Dw[w]);
         if (sp->Dw[w] > SK_DMAX + 1) {
             delete sp;
             return nullptr;
         }
+        sp->Dw[w] *= SK_LAGM;   // from here on: the largest lag of the warp
     }
     for (int v = 0; v < n; ++v) {
         const int w = cell_warp[v];
         sp->cell[(size_t)w * CAP + place[v]] = v;
-        sp->lag[(size_t)w * CAP + place[v]] = sp->Dw[w] - depth[v];
+        sp->lag[(size_t)w * CAP + place[v]] = sp->Dw[w] - SK_LAGM * depth[v];
         if (cut[v]) {
             const int r = pl->down[v], wc = cell_warp[r];
-            sp->ghost_lag[(size_t)wc * SK_XG + ghost_slot[v]] = sp->Dw[wc] - (depth[r] + 1);
+            sp->ghost_lag[(size_t)wc * SK_XG + ghost_slot[v]] = sp->Dw[wc] - SK_LAGM * (depth[r] + 1);
         }
     }
     // ---- row terms ----------------------------------------------------------------------------------------------------------
@@ -366,7 +376,7 @@ static SkewPlan *get_skew(xan_mrtm_plan *pl) {
     if (!pl->skew_tried) {
         pl->skew_tried = true;
         const char *ek = getenv("XANTHOS_MRTM_SKEW_K");
-        const int K = ek ? std::max(2, std::min(8, atoi(ek))) : 4;
+        const int K = ek ? std::max(2, std::min(6, atoi(ek))) : 2;   // 2 measured fastest (two warps per SM sub-partition)
         pl->skew = build_skew(pl, K);
     }
     return pl->skew;
@@ -386,9 +396,9 @@ struct SkewArgs {
     const int *step_month;       // [M] runoff month read by the step
     const double *step_secs;     // [M]
     double *chs, *avg, *instream;
-    int nw, M, T, spinup, ld, RL, G, sleep_ns;
+    int nw, M, T, spinup, ld, RL, G, O, sleep_ns;   // G / O: most ghost entries / exports of a warp
     double dt;
-    long long *dbg;              // optional [nw][4]: cycles total, prologue wait, events, SM sub-partition
+    long long *dbg;              // optional [nw][5]: cycles total, prologue wait, events, SM sub-partition, slow iterations
 };
 
 __device__ __forceinline__ int sk_ld_relaxed_pred(const int *p, int pred, int dflt) {
@@ -407,16 +417,24 @@ __device__ __forceinline__ double2 sk_lds(unsigned addr) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ double sk_lds1(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sk_sts(unsigned addr, double x, double y) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
 }
-__device__ __forceinline__ void sk_sts_pred(unsigned addr, double x, double y, int pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t@p st.shared.v2.f64 [%0], {%1, %2};\n\t}" ::"r"(addr),
-                 "d"(x), "d"(y), "r"(pred)
+__device__ __forceinline__ void sk_sts1(unsigned addr, double x) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(x) : "memory");
+}
+__device__ __forceinline__ void sk_sts1_pred(unsigned addr, double x, int pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" ::"r"(addr), "d"(x),
+                 "r"(pred)
                  : "memory");
 }
-__device__ __forceinline__ void sk_stg_pred(double2 *p, double x, double y, int pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t@p st.global.v2.f64 [%0], {%1, %2};\n\t}" ::"l"(p),
+__device__ __forceinline__ void sk_sts_pred(unsigned addr, double x, double y, int pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t@p st.shared.v2.f64 [%0], {%1, %2};\n\t}" ::"r"(addr),
                  "d"(x), "d"(y), "r"(pred)
                  : "memory");
 }
@@ -427,98 +445,121 @@ struct SkewLane {
     double erln[K], pend[K], qn[K], ar[K];   // lateral inflow of the next step, monthly sum waiting for its division,
                                              // prefetched runoff of the step after the next, cell area
     int cell[K], lag[K];
-    unsigned sb[2 * SK_NB];      // byte offsets (within one parity of the flow table) of the terms of the wide row
+    unsigned sb[2 * SK_NB];      // byte offsets (within the F half of one table parity) of the terms of the wide row
     unsigned su[K > 1 ? K - 1 : 1];   // ... of the single tributary of the cells in slots 1 .. K-1
 };
 
-// One loop iteration of one warp.  RD / WR: shared-memory byte addresses of the table parity read / written.
-// The shared-memory accesses are volatile asm statements, which the compiler keeps in program order: all loads of
-// the iteration are therefore issued first (one batch, their latencies overlap), then the K independent balances,
-// then the stores.  (With the loads inside the per-slot code every slot waited for the store of the slot before it:
-// 96 ms instead of the numbers in DESIGN.md.)
+// Row terms of one iteration: trial flows (x) and, when needed, final flows (y) of the tributaries.
 template <int K>
-struct SkewLoads {
-    double2 t[2 * SK_NB];
-    double2 u[K > 1 ? K - 1 : 1];
+struct SkewTerms {
+    double tx[2 * SK_NB], ty[2 * SK_NB], ux[K > 1 ? K - 1 : 1], uy[K > 1 ? K - 1 : 1];
 };
 
+// Loads the row terms of an iteration from table buffer LDB (shared-memory byte address).  A buffer holds the trial
+// flows F of all entries (8 B each) followed, FPOFF bytes further, by the final flows F'.  `slow`: some flow in LDB
+// has F' != F (a clamp, mrtm.py:54-60); otherwise the F' half is neither read nor used.
 template <int K>
-__device__ __forceinline__ void skew_load(SkewLoads<K> &R, const SkewLane<K> &L, const unsigned RD) {
+__device__ __forceinline__ void skew_load(SkewTerms<K> &R, const SkewLane<K> &L, const unsigned LDB, const unsigned FPOFF,
+                                          const bool slow) {
 #pragma unroll
-    for (int j = 0; j < 2 * SK_NB; ++j) R.t[j] = sk_lds(RD + L.sb[j]);
+    for (int j = 0; j < 2 * SK_NB; ++j) R.tx[j] = sk_lds1(LDB + L.sb[j]);
 #pragma unroll
-    for (int s = 1; s < K; ++s) R.u[s - 1] = sk_lds(RD + L.su[s - 1]);
+    for (int s = 1; s < K; ++s) R.ux[s - 1] = sk_lds1(LDB + L.su[s - 1]);
+    if (slow) {
+#pragma unroll
+        for (int j = 0; j < 2 * SK_NB; ++j) R.ty[j] = sk_lds1(LDB + FPOFF + L.sb[j]);
+#pragma unroll
+        for (int s = 1; s < K; ++s) R.uy[s - 1] = sk_lds1(LDB + FPOFF + L.su[s - 1]);
+    }
 }
 
+// The balances of the K slots of one iteration, from terms loaded earlier; stores (F, F') of every cell into table
+// buffer WR.  `slow`: the terms carry F' != F somewhere: the balance for the update (mrtm.py:68) is then a second sum
+// over the F'; otherwise it EQUALS the balance for the decision (mrtm.py:51) bit for bit and is not formed.
+// xdiff: this lane wrote a ghost entry with F' != F into WR.  Returns (warp-uniform) whether any flow in WR has
+// F' != F.  The only values carried from one iteration to the next are the storages S (and the monthly sums).
 template <int K>
-__device__ __forceinline__ void skew_compute_store(SkewLane<K> &L, const SkewLoads<K> &R, const unsigned WR,
-                                                   const int lane, const double dt, const double dtinv) {
-    double Fo[K], Fpo[K];
+__device__ __forceinline__ bool skew_compute_store(SkewLane<K> &L, const SkewTerms<K> &R, const unsigned WR,
+                                                   const unsigned FPOFF, const int lane, const double dt,
+                                                   const double dtinv, const bool slow, const bool xdiff) {
+    double F[K], d[K], ddt[K], Sn[K];
     // ---- slot 0: up to SK_NB tributaries before and SK_NB after the cell's own column (mrtm.py:51 in CSR order) ----
     {
-        const double F = L.S[0] * L.ti[0];                                          // mrtm.py:50
-        double d = R.t[0].x, d2 = R.t[0].y;
+        F[0] = L.S[0] * L.ti[0];                                                    // mrtm.py:50
+        double acc = R.tx[0];
 #pragma unroll
-        for (int j = 1; j < SK_NB; ++j) {
-            d = d + R.t[j].x;
-            d2 = d2 + R.t[j].y;
-        }
-        d = d - F;
-        d2 = d2 - F;
+        for (int j = 1; j < SK_NB; ++j) acc = acc + R.tx[j];
+        acc = acc - F[0];
 #pragma unroll
-        for (int j = SK_NB; j < 2 * SK_NB; ++j) {
-            d = d + R.t[j].x;
-            d2 = d2 + R.t[j].y;
-        }
-        d = d + L.erl[0];                                                           // balance with the trial flows
-        d2 = d2 + L.erl[0];                                                         // balance with the final flows, :68
-        const bool clamp = (d * dt) < (-L.S[0]);                                    // :54
-        const double Sn = L.S[0] + d2 * dt;                                         // :69 / :76
-        const double Fc = (d + F) + L.S[0] * dtinv;                                 // :60
-        const double Fp = clamp ? Fc : F;
-        L.S[0] = clamp ? 0.0 : Sn;                                                  // :63
-        L.fav[0] = L.fav[0] + Fp;                                                   // :78
-        Fo[0] = F;
-        Fpo[0] = Fp;
+        for (int j = SK_NB; j < 2 * SK_NB; ++j) acc = acc + R.tx[j];
+        d[0] = acc + L.erl[0];                                                      // balance with the trial flows
     }
     // ---- slots 1 .. K-1: at most one tributary; a two-term row is order-free ---------------------------------------
 #pragma unroll
     for (int s = 1; s < K; ++s) {
-        const double2 u = R.u[s - 1];
-        const double F = L.S[s] * L.ti[s];
-        const double d = (u.x - F) + L.erl[s];
-        const double d2 = (u.y - F) + L.erl[s];
-        const bool clamp = (d * dt) < (-L.S[s]);
-        const double Sn = L.S[s] + d2 * dt;
-        const double Fc = (d + F) + L.S[s] * dtinv;
-        const double Fp = clamp ? Fc : F;
-        L.S[s] = clamp ? 0.0 : Sn;
-        L.fav[s] = L.fav[s] + Fp;
-        Fo[s] = F;
-        Fpo[s] = Fp;
+        F[s] = L.S[s] * L.ti[s];
+        d[s] = (R.ux[s - 1] - F[s]) + L.erl[s];
     }
 #pragma unroll
-    for (int s = 0; s < K; ++s) sk_sts(WR + (unsigned)(s * 32 + lane) * 16u, Fo[s], Fpo[s]);
+    for (int s = 0; s < K; ++s) {
+        ddt[s] = d[s] * dt;
+        Sn[s] = L.S[s] + ddt[s];                                                    // :76
+    }
+    if (slow) {                                                                     // balance with the final flows, :68-69
+        double acc = R.ty[0];
+#pragma unroll
+        for (int j = 1; j < SK_NB; ++j) acc = acc + R.ty[j];
+        acc = acc - F[0];
+#pragma unroll
+        for (int j = SK_NB; j < 2 * SK_NB; ++j) acc = acc + R.ty[j];
+        Sn[0] = L.S[0] + (acc + L.erl[0]) * dt;
+#pragma unroll
+        for (int s = 1; s < K; ++s) Sn[s] = L.S[s] + ((R.uy[s - 1] - F[s]) + L.erl[s]) * dt;
+    }
+    double Fp[K];
+    bool any_clamp = false;
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        const bool clamp = ddt[s] < (-L.S[s]);                                      // :54
+        const double Fc = (d[s] + F[s]) + L.S[s] * dtinv;                           // :60
+        Fp[s] = clamp ? Fc : F[s];
+        L.S[s] = clamp ? 0.0 : Sn[s];                                               // :63
+        L.fav[s] = L.fav[s] + Fp[s];                                                // :78
+        any_clamp = any_clamp || clamp;
+    }
+    const bool changed = __any_sync(0xffffffffu, any_clamp || xdiff);
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        sk_sts1(WR + (unsigned)(s * 32 + lane) * 8u, F[s]);
+        sk_sts1(WR + FPOFF + (unsigned)(s * 32 + lane) * 8u, Fp[s]);
+    }
+    return changed;
 }
 
+// Shared memory of one warp: flow table [SK_LAGM + 1 buffers][F half | F' half] (NE entries each), staged series of the ghost
+// entries [G][SK_W] (F, F'), export series [O][SK_CH] (F, F').
 template <int K>
-__global__ void __launch_bounds__(256, 1) mrtm_skew_kernel(const SkewArgs a) {
-    extern __shared__ __align__(16) unsigned char sk_smem[];
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int w = wib * gridDim.x + blockIdx.x;     // consecutive plan warps on different SMs
-    if (w >= a.nw) return;                          // no block-level barrier below
-    constexpr int CAP = 32 * K, NE = CAP + SK_XG + 1, NS = 2 * SK_NB + K - 1;
-    constexpr unsigned PSTRIDE = NE * 16u;
-    const int per_warp = (2 * NE + a.G * SK_W) * 16;
-    const unsigned EX0 = (unsigned)__cvta_generic_to_shared(sk_smem + (size_t)wib * per_warp);
-    const unsigned ST0 = EX0 + 2 * PSTRIDE;
-    for (int i = lane; i < per_warp / 16; i += 32) sk_sts(EX0 + (unsigned)i * 16u, 0.0, 0.0);
-    __syncwarp();
+struct SkewSmem {
+    static constexpr int CAP = 32 * K, NE = CAP + SK_XG + 2;     // + all-zero entry, + 1 keeps the F' half 16-byte aligned
+    static constexpr unsigned FPOFF = NE * 8u, PSTRIDE = NE * 16u;
+    // ... + one 16-byte dump slot per lane (target of the import / export stores of lanes that have neither)
+    static __host__ __device__ int bytes(int G, int O) {
+        return (SK_LAGM + 1) * NE * 16 + G * SK_W * 16 + O * SK_CH * 16 + 32 * 16;
+    }
+};
 
+template <int K, bool LINKED>
+__device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const int lane, const unsigned EX0) {
+    using SM = SkewSmem<K>;
+    constexpr int CAP = SM::CAP, NS = 2 * SK_NB + K - 1;
+    constexpr unsigned FPOFF = SM::FPOFF, PSTRIDE = SM::PSTRIDE;
+    const unsigned full = 0xffffffffu;
+    const unsigned ST0 = EX0 + (SK_LAGM + 1) * PSTRIDE;             // staged ghost series
+    const unsigned XS0 = ST0 + (unsigned)a.G * (SK_W * 16u);        // export series
     const bool dbg = a.dbg != nullptr;
     const long long cyc0 = dbg ? clock64() : 0;
     long long cyc_wait = 0, cyc_evt = 0;
+    int n_slow = 0;
     const int Dw = a.Dw[w], M = a.M, T = a.T, RL = a.RL;
     const double dt = a.dt, dtinv = 1. / a.dt;                                      // mrtm.py:43
     SkewLane<K> L;
@@ -539,24 +580,26 @@ __global__ void __launch_bounds__(256, 1) mrtm_skew_kernel(const SkewArgs a) {
     {
         const int *row = a.src + ((size_t)w * 32 + lane) * NS;
 #pragma unroll
-        for (int j = 0; j < 2 * SK_NB; ++j) L.sb[j] = (unsigned)row[j] * 16u;
+        for (int j = 0; j < 2 * SK_NB; ++j) L.sb[j] = (unsigned)row[j] * 8u;
 #pragma unroll
-        for (int s = 1; s < K; ++s) L.su[s - 1] = (unsigned)row[2 * SK_NB + s - 1] * 16u;
+        for (int s = 1; s < K; ++s) L.su[s - 1] = (unsigned)row[2 * SK_NB + s - 1] * 8u;
     }
     // ---- ghost imports (lanes 0 .. 15) and exports (lanes 16 .. 31) ------------------------------------------------
     const int xi = lane & 15;
     const bool imp_lane = lane < SK_XG;
-    const int xedge = imp_lane ? a.ghost_edge[(size_t)w * SK_XG + xi] : a.exp_edge[(size_t)w * SK_XO + xi];
+    int xedge = -1;
+    if (LINKED) xedge = imp_lane ? a.ghost_edge[(size_t)w * SK_XG + xi] : a.exp_edge[(size_t)w * SK_XO + xi];
     const bool imp = imp_lane && xedge >= 0, expo = !imp_lane && xedge >= 0;
     const int glag = imp ? a.ghost_lag[(size_t)w * SK_XG + xi] : 0;
-    const unsigned eplace16 = (unsigned)(expo ? a.exp_place[(size_t)w * SK_XO + xi] : CAP + SK_XG) * 16u;
+    const unsigned eplace8 = (unsigned)(expo ? a.exp_place[(size_t)w * SK_XO + xi] : CAP + SK_XG) * 8u;
     double2 *const xring = a.ring + (size_t)(xedge >= 0 ? xedge : 0) * RL;
     const int peer = imp ? a.edge_prod[xedge] : (expo ? a.edge_cons[xedge] : 0);
-    const unsigned ghost_mask = __ballot_sync(full, imp);
-    const bool has_exp = __any_sync(full, expo);
-    const bool linked = ghost_mask != 0 || has_exp;
+    const unsigned ghost_mask = __ballot_sync(full, imp), exp_mask = __ballot_sync(full, expo);
     const unsigned stg_lane = ST0 + (unsigned)xi * (SK_W * 16u);                    // this import lane's staged series
-    const unsigned zero_addr = EX0 + (unsigned)(CAP + SK_XG) * 16u;                 // all-zero entry (parity 0)
+    const unsigned xs_lane = XS0 + (unsigned)xi * (SK_CH * 16u);                    // this export lane's series
+    const unsigned dump_lane = XS0 + (unsigned)a.O * (SK_CH * 16u) + (unsigned)lane * 16u;
+    // second half of an (F, F') pair: 8 bytes further in a staged series, FPOFF bytes further in the flow table
+    const unsigned xdelta = imp ? 8u : FPOFF;
 
     auto wait_peers = [&](int need_p, int need_c) {
         const int poll_p = imp ? 1 : 0, poll_c = (expo && need_c > 0) ? 1 : 0;
@@ -586,7 +629,22 @@ __global__ void __launch_bounds__(256, 1) mrtm_skew_kernel(const SkewArgs a) {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (ghost_mask) {
+    // exports of the SK_CH iterations before n0 (sub-steps n0 - SK_CH - 1 - Dw ...), shared memory -> ring, coalesced
+    auto flush_exports = [&](int n0) {
+        unsigned em = exp_mask;
+        while (em) {
+            const int l = __ffs(em) - 1;
+            em &= em - 1;
+            double2 *rp = reinterpret_cast<double2 *>(__shfl_sync(full, (unsigned long long)xring, l));
+            const unsigned src = XS0 + (unsigned)(l & 15) * (SK_CH * 16u);
+#pragma unroll
+            for (int h = 0; h < SK_CH / 32; ++h) {
+                const int i = h * 32 + lane, tau = n0 - SK_CH + i - 1 - Dw;
+                if (tau >= 0 && tau < T) rp[tau & (RL - 1)] = sk_lds(src + (unsigned)i * 16u);
+            }
+        }
+    };
+    if (LINKED && ghost_mask) {
         wait_peers(min(T, SK_CH), 0);
         stage_chunk(0);
     }
@@ -599,82 +657,133 @@ __global__ void __launch_bounds__(256, 1) mrtm_skew_kernel(const SkewArgs a) {
     int b = 0, evt = a.step_start[0];
     double ev_nt_prev = 1.0, ev_secs_next = a.step_secs[M > 1 ? 1 : 0];
     size_t ev_next2_off = (size_t)a.step_month[M > 2 ? 2 : 0] * a.ld, ev_out_off = 0;
-    double2 xv = make_double2(0.0, 0.0);            // ghost import / export value of the coming iteration
+    auto events = [&](const int n, const unsigned LAST) {   // LAST: table buffer written one iteration ago
+        const long long c0 = dbg ? clock64() : 0;
+        const int k = n - evt;
+        const bool st = b > 0 && b - 1 >= a.spinup;
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+            const int c = L.cell[s];
+            if (c >= 0 && L.lag[s] == k) {
+                if (st && a.chs) stg_stream(a.chs + ev_out_off + c, L.S[s]);
+                if (b == M && a.instream) a.instream[c] = sk_lds1(LAST + FPOFF + (unsigned)(s * 32 + lane) * 8u);
+                L.pend[s] = L.fav[s];
+                L.fav[s] = 0.0;
+                L.erl[s] = L.erln[s];
+                if (b == 0) L.S[s] = a.chs_prev ? a.chs_prev[c] : 0.0;
+            }
+        }
+        if (k == Dw) {   // every cell has crossed: window closed
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                const int c = L.cell[s];
+                if (c >= 0) {
+                    if (st && a.avg) stg_stream(a.avg + ev_out_off + c, L.pend[s] / ev_nt_prev);   // mrtm.py:80
+                    if (b + 1 < M) L.erln[s] = ((L.qn[s] * L.ar[s]) * (1e6 / 1e3)) / ev_secs_next;  // mrtm.py:45
+                    if (b + 2 < M) L.qn[s] = a.runoff[ev_next2_off + c];                            // used a month later
+                }
+            }
+            ++b;   // constants of the next window, fetched a month ahead of their use
+            evt = (b <= M) ? a.step_start[b] : 0x7fffffff;
+            if (b <= M) ev_nt_prev = (double)a.step_nt[b - 1];
+            if (b + 1 < M) ev_secs_next = a.step_secs[b + 1];
+            if (b + 2 < M) ev_next2_off = (size_t)a.step_month[b + 2] * a.ld;
+            ev_out_off = (size_t)max(0, b - 1 - a.spinup) * a.ld;
+        }
+        __syncwarp();
+        if (dbg) cyc_evt += clock64() - c0;
+    };
+
+    double xvx = 0.0, xvy = 0.0;     // ghost import / export value of the coming iteration
+    // Table buffers: iteration n writes bw = buffer n mod 3; a cell reads what its tributaries (SK_LAGM = 2 iterations
+    // ahead in their own time) wrote two iterations ago.  The terms of iteration n + 1 come from bl (written in n - 1)
+    // and are loaded while iteration n is being computed: no load, store or vote latency is on the path from one
+    // iteration to the next - only the storages S in registers.
+    unsigned bw = EX0, bl = EX0 + SK_LAGM * PSTRIDE, bt = EX0 + PSTRIDE;   // written now / one / two iterations ago
+    bool ch1 = false, ch2 = false;   // some flow written one / two iterations ago has F' != F
+    SkewTerms<K> TA, TB;
+#pragma unroll
+    for (int j = 0; j < 2 * SK_NB; ++j) TA.tx[j] = TA.ty[j] = TB.tx[j] = TB.ty[j] = 0.0;
+#pragma unroll
+    for (int s = 1; s < K; ++s) TA.ux[s - 1] = TA.uy[s - 1] = TB.ux[s - 1] = TB.uy[s - 1] = 0.0;
+    // One iteration: computes with the terms in CUR, loads the terms of the next iteration into NXT.  The import and
+    // export stores are unconditional: every lane has a destination (ghost entry halves / export series slot / dump
+    // slot) - predicated stores were turned into branches by ptxas.
+    auto iteration = [&](const int n, const SkewTerms<K> &CUR, SkewTerms<K> &NXT) {
+        bool xdiff = false;
+        if (LINKED) {   // the value was loaded at the end of the previous iteration
+            const unsigned x0 = imp_lane ? bw + (unsigned)(CAP + xi) * 8u
+                                         : (expo ? xs_lane + ((unsigned)(n & (SK_CH - 1)) << 4) : dump_lane);
+            sk_sts1(x0, xvx);
+            sk_sts1(x0 + (imp_lane ? FPOFF : 8u), xvy);
+            xdiff = imp && (__double_as_longlong(xvx) != __double_as_longlong(xvy));
+        }
+        bool ch0;
+        if (SK_LAGM == 2) {
+            skew_load<K>(NXT, L, bl, FPOFF, ch1);
+            ch0 = skew_compute_store<K>(L, CUR, bw, FPOFF, lane, dt, dtinv, ch2, xdiff);
+            if (ch2) ++n_slow;
+        } else {
+            ch0 = skew_compute_store<K>(L, CUR, bw, FPOFF, lane, dt, dtinv, ch1, xdiff);
+            if (ch1) ++n_slow;
+            skew_load<K>(NXT, L, bw, FPOFF, ch0);
+        }
+        if (LINKED) {   // for iteration n + 1: staged entry n + 1 - lag (lag >= 1: its chunk has landed), or the cell just stored
+            const unsigned xaddr = imp ? stg_lane + ((unsigned)((n + 1 - glag) & (SK_W - 1)) << 4) : bw + eplace8;
+            xvx = sk_lds1(xaddr);
+            xvy = sk_lds1(xaddr + xdelta);
+        }
+        ch2 = ch1;
+        ch1 = ch0;
+        if (SK_LAGM == 2) {
+            const unsigned t = bt;
+            bt = bl;
+            bl = bw;
+            bw = t;
+        } else {
+            const unsigned t = bl;
+            bl = bw;
+            bw = t;
+        }
+    };
+
     const int nlast = T + Dw;
     for (int n0 = 0; n0 <= nlast; n0 += SK_CH) {
-        if (linked) {
+        if (LINKED) {
             const long long c0 = dbg ? clock64() : 0;
             asm volatile("cp.async.wait_group 0;" ::: "memory");                    // chunk n0 / SK_CH has landed
-            __syncwarp();   // every lane's ring reads and exports are ordered before lane 0's release below
-            // hand-over: every export up to sub-step n0 - 2 - Dw is in the ring; every ring entry below n0 + SK_CH of
-            // the edges this warp consumes is in shared memory
+            __syncwarp();
+            // hand-over: after the flush every export up to sub-step n0 - 2 - Dw is in the ring; every ring entry below
+            // n0 + SK_CH of the edges this warp consumes is in shared memory
+            wait_peers(min(T, n0 + 2 * SK_CH), n0 - RL);
+            if (exp_mask) flush_exports(n0);
+            __syncwarp();   // every lane's ring reads and writes are ordered before lane 0's release
             if (lane == 0) sk_st_release(a.progress + w, max(0, min(T, n0 - 1 - Dw)));
-            wait_peers(min(T, n0 + 2 * SK_CH), n0 + SK_CH - RL);
             if (ghost_mask) stage_chunk(n0 + SK_CH);
             if (dbg) cyc_wait += clock64() - c0;
         }
+        int i = 0;
+        while (i < SK_CH) {
+            // pairs of iterations before the next month window opens run without any event test
+            const int lim = min(SK_CH, max(0, evt - n0)) & ~1;
+            if (i < lim) {
 #pragma unroll 1
-        for (int i = 0; i < SK_CH; i += 2) {
-#pragma unroll
-            for (int par = 0; par < 2; ++par) {
-                const int n = n0 + i + par;
-                const unsigned RD = EX0 + (par ? 0u : PSTRIDE), WR = EX0 + (par ? PSTRIDE : 0u);
-                // ---- per-cell month events (rare: Dw + 1 iterations per month) -----------------------------------
-                if (n >= evt) {
-                    const long long c0 = dbg ? clock64() : 0;
-                    const int k = n - evt;
-                    const bool st = b > 0 && b - 1 >= a.spinup;
-#pragma unroll
-                    for (int s = 0; s < K; ++s) {
-                        const int c = L.cell[s];
-                        if (c >= 0 && L.lag[s] == k) {
-                            if (st && a.chs) stg_stream(a.chs + ev_out_off + c, L.S[s]);
-                            if (b == M && a.instream) a.instream[c] = sk_lds(RD + (unsigned)(s * 32 + lane) * 16u).y;
-                            L.pend[s] = L.fav[s];
-                            L.fav[s] = 0.0;
-                            L.erl[s] = L.erln[s];
-                            if (b == 0) L.S[s] = a.chs_prev ? a.chs_prev[c] : 0.0;
-                        }
-                    }
-                    if (k == Dw) {   // every cell has crossed: window closed
-#pragma unroll
-                        for (int s = 0; s < K; ++s) {
-                            const int c = L.cell[s];
-                            if (c >= 0) {
-                                if (st && a.avg) stg_stream(a.avg + ev_out_off + c, L.pend[s] / ev_nt_prev);   // mrtm.py:80
-                                if (b + 1 < M) L.erln[s] = ((L.qn[s] * L.ar[s]) * (1e6 / 1e3)) / ev_secs_next;  // mrtm.py:45
-                                if (b + 2 < M) L.qn[s] = a.runoff[ev_next2_off + c];                            // used a month later
-                            }
-                        }
-                        ++b;   // constants of the next window, fetched a month ahead of their use
-                        evt = (b <= M) ? a.step_start[b] : 0x7fffffff;
-                        if (b <= M) ev_nt_prev = (double)a.step_nt[b - 1];
-                        if (b + 1 < M) ev_secs_next = a.step_secs[b + 1];
-                        if (b + 2 < M) ev_next2_off = (size_t)a.step_month[b + 2] * a.ld;
-                        ev_out_off = (size_t)max(0, b - 1 - a.spinup) * a.ld;
-                    }
-                    __syncwarp();
-                    if (dbg) cyc_evt += clock64() - c0;
+                for (; i < lim; i += 2) {
+                    iteration(n0 + i, TA, TB);
+                    iteration(n0 + i + 1, TB, TA);
                 }
-                // ---- ghost imports and exports: the value was loaded at the end of the previous iteration ---------
-                if (linked) {
-                    sk_sts_pred(WR + (unsigned)(CAP + xi) * 16u, xv.x, xv.y, imp_lane ? 1 : 0);
-                    const int tau = n - 1 - Dw;
-                    sk_stg_pred(xring + (tau & (RL - 1)), xv.x, xv.y, (expo && tau >= 0 && tau < T) ? 1 : 0);
-                }
-                SkewLoads<K> R;
-                skew_load<K>(R, L, RD);
-                skew_compute_store<K>(L, R, WR, lane, dt, dtinv);
-                if (linked) {   // for iteration n + 1: staged entry n + 1 - lag (lag >= 1: chunk landed), or the cell just stored
-                    const unsigned xaddr = imp ? stg_lane + ((unsigned)((n + 1 - glag) & (SK_W - 1)) << 4)
-                                               : (expo ? WR + eplace16 : zero_addr);
-                    xv = sk_lds(xaddr);
-                }
-                __syncwarp();
+            } else {             // a month boundary is being crossed by some cells (Dw + 1 iterations per month)
+                const int n = n0 + i;
+                if (n >= evt) events(n, bl);
+                iteration(n, TA, TB);
+                if (n + 1 >= evt) events(n + 1, bl);
+                iteration(n + 1, TB, TA);
+                i += 2;
             }
         }
     }
-    if (linked) {
+    if (LINKED) {
+        if (exp_mask) flush_exports(((nlast / SK_CH) + 1) * SK_CH);
         __syncwarp();
         if (lane == 0) sk_st_release(a.progress + w, T);
     }
@@ -682,11 +791,28 @@ __global__ void __launch_bounds__(256, 1) mrtm_skew_kernel(const SkewArgs a) {
         unsigned smid, wid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-        a.dbg[4 * w] = clock64() - cyc0;
-        a.dbg[4 * w + 1] = cyc_wait;
-        a.dbg[4 * w + 2] = cyc_evt;
-        a.dbg[4 * w + 3] = smid * 4 + (wid & 3);
+        a.dbg[5 * w] = clock64() - cyc0;
+        a.dbg[5 * w + 1] = cyc_wait;
+        a.dbg[5 * w + 2] = cyc_evt;
+        a.dbg[5 * w + 3] = smid * 4 + (wid & 3);
+        a.dbg[5 * w + 4] = n_slow;
     }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256, 1) mrtm_skew_kernel(const SkewArgs a) {
+    extern __shared__ __align__(16) unsigned char sk_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int w = wib * gridDim.x + blockIdx.x;     // consecutive plan warps on different SMs
+    if (w >= a.nw) return;                          // no block-level barrier below
+    const int per_warp = SkewSmem<K>::bytes(a.G, a.O);
+    const unsigned EX0 = (unsigned)__cvta_generic_to_shared(sk_smem + (size_t)wib * per_warp);
+    for (int i = lane; i < per_warp / 16; i += 32) sk_sts(EX0 + (unsigned)i * 16u, 0.0, 0.0);
+    __syncwarp();
+    bool linked = false;
+    if (lane < SK_XG) linked = a.ghost_edge[(size_t)w * SK_XG + lane] >= 0 || a.exp_edge[(size_t)w * SK_XO + lane] >= 0;
+    if (__any_sync(0xffffffffu, linked)) skew_run<K, true>(a, w, lane, EX0);
+    else skew_run<K, false>(a, w, lane, EX0);
 }
 
 template <typename V>
@@ -700,7 +826,7 @@ static bool sk_upload(const std::vector<V> &h, V **d) {
 template <int K>
 static int launch_skew(SkewPlan *sp, SkewArgs &a, int sms, cudaStream_t s) {
     auto kernel = mrtm_skew_kernel<K>;
-    const int per_warp = (2 * (32 * K + SK_XG + 1) + sp->G * SK_W) * 16;
+    const int per_warp = SkewSmem<K>::bytes(sp->G, sp->O);
     int wpb = std::max(4, ((ceil_div(sp->nw, sms) + 3) / 4) * 4);
     if (wpb > 8) return XAN_E_INVALID;
     const size_t smem = (size_t)per_warp * wpb;
@@ -760,7 +886,7 @@ int route_skew(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_d
     a.edge_prod = sp->d_edge_prod; a.edge_cons = sp->d_edge_cons; a.progress = sp->d_progress;
     a.runoff = d_runoff; a.chs_prev = d_chs_prev; a.flow_dist = d_flow_dist; a.velocity = d_velocity; a.area = d_area;
     a.chs = d_chs; a.avg = d_avg; a.instream = d_instream;
-    a.nw = sp->nw; a.M = M; a.T = (int)total; a.spinup = spinup_months; a.ld = ld; a.G = sp->G; a.dt = dt;
+    a.nw = sp->nw; a.M = M; a.T = (int)total; a.spinup = spinup_months; a.ld = ld; a.G = sp->G; a.O = sp->O; a.dt = dt;
     const char *er = getenv("XANTHOS_MRTM_SKEW_RING"), *es = getenv("XANTHOS_MRTM_SLEEP_NS");
     int RL = er ? atoi(er) : 1024;
     if (RL < 256 || (RL & (RL - 1))) RL = 1024;
@@ -787,7 +913,7 @@ int route_skew(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_d
     a.ring = ring;
     XAN_CUDA_CHECK(cudaMemsetAsync(sp->d_progress, 0, sizeof(int) * sp->nw, s));
     const char *edbg = getenv("XANTHOS_MRTM_DEBUG");
-    if (edbg) XAN_CUDA_CHECK(scratch_alloc(&a.dbg, sizeof(long long) * 4 * sp->nw, s));
+    if (edbg) XAN_CUDA_CHECK(scratch_alloc(&a.dbg, sizeof(long long) * 5 * sp->nw, s));
     int rc = XAN_E_INVALID;
     switch (sp->K) {
         case 2: rc = launch_skew<2>(sp, a, sms, s); break;
@@ -798,12 +924,13 @@ int route_skew(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_d
         default: break;
     }
     if (rc == XAN_OK && a.dbg) {
-        std::vector<long long> h(4 * (size_t)sp->nw);
+        std::vector<long long> h(5 * (size_t)sp->nw);
         XAN_CUDA_CHECK(cudaMemcpyAsync(h.data(), a.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, s));
         XAN_CUDA_CHECK(cudaStreamSynchronize(s));
         if (FILE *f = fopen(edbg, "w")) {
             for (int w = 0; w < sp->nw; ++w)
-                fprintf(f, "%d %lld %lld %lld %lld %d\n", w, h[4 * w], h[4 * w + 1], h[4 * w + 2], h[4 * w + 3], sp->Dw[w]);
+                fprintf(f, "%d %lld %lld %lld %lld %d %lld\n", w, h[5 * w], h[5 * w + 1], h[5 * w + 2], h[5 * w + 3], sp->Dw[w],
+                        h[5 * w + 4]);
             fclose(f);
         }
     }
@@ -819,17 +946,17 @@ int route_skew(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_d
 extern "C" {
 
 // Test / diagnostics access to the skew plan (sizes first, then the tables as int arrays; null pointers are skipped).
-// info: K, n_warps, n_edges, n_levels, max ghosts per warp, max lag, pieces, sources per lane, zero entry, XG, XO
+// info: K, n_warps, n_edges, n_levels, max ghosts per warp, max lag, pieces, sources per lane, zero entry, XG, XO, lag multiplier
 int xan_mrtm_skew_info(xan_mrtm_plan *pl, int *info) {
     XAN_REQUIRE(pl && info, "xan_mrtm_skew_info: null pointer");
     xan::SkewPlan *sp = xan::get_skew(pl);
     if (!sp) {
-        for (int i = 0; i < 11; ++i) info[i] = 0;
+        for (int i = 0; i < 12; ++i) info[i] = 0;
         return XAN_OK;
     }
-    const int v[11] = {sp->K, sp->nw, sp->n_edges, sp->n_levels, sp->G, sp->Dmax, sp->n_pieces, sp->nsrc(),
-                       sp->zero_entry(), xan::SK_XG, xan::SK_XO};
-    for (int i = 0; i < 11; ++i) info[i] = v[i];
+    const int v[12] = {sp->K, sp->nw, sp->n_edges, sp->n_levels, sp->G, sp->Dmax, sp->n_pieces, sp->nsrc(),
+                       sp->zero_entry(), xan::SK_XG, xan::SK_XO, xan::SK_LAGM};
+    for (int i = 0; i < 12; ++i) info[i] = v[i];
     return XAN_OK;
 }
 
