@@ -346,7 +346,39 @@ def run_ours(args, rank, world_size, local_rank):
     e2e_each = [float(v) for v in t.cpu()]
     # The GPU boxes are shared hosts: single steps are sometimes stretched by 80 - 700 ms of host-side stalls
     # (seen as a GPU waiting idle for the next launch).  The median step is reported; the mean and every step are kept.
-    e2e_ms = float(np.median(e2e_each))
+    e2e_single_ms = float(np.median(e2e_each))
+    C.forget_all()
+
+    # ---- end to end, the way a multi-scenario user runs it: xanthos_b200.ensemble.run_ensemble - every member's forcing
+    # comes from pinned host memory and its requested outputs (q, avgchflow) + basin aggregates go back to the host
+    # inside the timing; the copies of neighbouring members overlap the kernels (h2d / compute / d2h streams)
+    from xanthos_b200 import ensemble as ens
+    statics = ens.EnsembleStatics(ncell, START_YR, end_yr, tables, host['lct_load'], pm['elev'], pm['water_idx'],
+                                  pm['snow_idx'], lc_years, NLCS, world.n_basins, world.basin_ids, ab['pars'], world.area,
+                                  world.flow_dist, world.velocity, um, ndays, DT, spin_ro, spin_rt)
+    member_a = {k: host[k] for k in ens.FORCING}
+    member_b = {k: pinned(np.roll(host[k], 7, axis=0)) for k in ens.FORCING}    # a second, different member
+    n_mem = max(6, min(args.steps, 12))
+    members = [member_a if k % 2 == 0 else member_b for k in range(n_mem * world_size)]
+    sink = []
+    ens.run_ensemble(statics, members[:2 * world_size], on_result=lambda i, r: sink.append(float(r['avgchflow'][0, -1])))
+    gc.collect()
+    gc.disable()
+    try:
+        barrier()
+        t0 = time.perf_counter()
+        er = ens.run_ensemble(statics, members, on_result=lambda i, r: sink.append(float(r['avgchflow'][0, -1])))
+        barrier()
+        ens_ms = (time.perf_counter() - t0) * 1e3
+    finally:
+        gc.enable()
+    t = torch.tensor([ens_ms], dtype=torch.float64, device='cuda')
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ens_ms = float(t[0])
+    e2e_ms = ens_ms / n_mem
+    ens_stats = er['stats']
+    del member_b, members
 
     # ---- calibration objective (BASELINE.json metric, second half): one differential-evolution generation =
     # 64 candidate parameter sets x every basin, each a full spin-up + simulation + basin sum + KGE distance
@@ -497,10 +529,18 @@ def run_ours(args, rank, world_size, local_rank):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': bench_config(ncell, nmonths),
         'mrtm_plan': um.info,
-        'e2e': {'value': e2e_val, 'unit': 'cell-months/s', 'h2d_bytes_per_step': int(h2d_bytes),
-                'd2h_bytes_per_step': int(d2h_bytes_holder[0]), 'ms_per_step': e2e_ms, 'statistic': 'median step',
-                'ms_per_step_mean': float(np.mean(e2e_each)), 'ms_each_step': [round(v, 2) for v in e2e_each],
-                'steps': e2e_steps},
+        'e2e': {'value': e2e_val, 'unit': 'cell-months/s',
+                'h2d_bytes_per_step': int(ens_stats['h2d_bytes'] // max(ens_stats['members_local'], 1)),
+                'd2h_bytes_per_step': int(ens_stats['d2h_bytes'] // max(ens_stats['members_local'], 1)),
+                'ms_per_step': e2e_ms, 'steps': n_mem,
+                'mode': 'xanthos_b200.ensemble.run_ensemble: %d members per GPU back to back, forcing from pinned host '
+                        'memory, outputs q + avgchflow + basin aggregates to the host, copies of neighbouring members '
+                        'overlapped with the kernels' % n_mem,
+                'single_member': {'ms_per_step': e2e_single_ms, 'value': world_size * cm / (e2e_single_ms * 1e-3),
+                                  'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': int(d2h_bytes_holder[0]),
+                                  'statistic': 'median step', 'ms_each_step': [round(v, 2) for v in e2e_each],
+                                  'note': 'run_pmpet / abcd_execute / route on host arrays, all six outputs back to the '
+                                          'host, nothing overlapped across members (round-1 definition of e2e)'}},
         'gpu_launches': int(launches) * args.steps,
         'gpu_launches_per_step': int(launches),
         'clocks': clocks,

@@ -290,3 +290,49 @@ def test_skew_routing_kernel_bitwise_against_oracle(K, monkeypatch):
         tree = mrtm.route(um, q, w.flow_dist, w.velocity, w.area, nd, dt, spin, method=C.MRTM_TREE)
         for a, b, c, name in zip(got, want, tree, ('ChStorage', 'Avg_ChFlow', 'instream_flow')):
             assert bitwise_equal(a, b) and bitwise_equal(a, c), (w.ncell, dt, name)
+
+
+def test_ensemble_runner_equals_the_plugin_calls_member_by_member():
+    """xanthos_b200.ensemble.run_ensemble (overlapped H2D / compute / D2H over members, BASELINE config 5) returns, for
+    every member, exactly what run_pmpet -> abcd_execute -> route return for that member alone; the basin aggregates
+    equal the nansum over the basin's cells (the reference's basin_runoff aggregation, calibrate_abcd.py:159-162)."""
+    from xanthos_b200 import synthetic, ensemble as ens
+    from xanthos_b200.pet import penman_monteith as pm_mod
+    from xanthos_b200.runoff import abcd
+    from xanthos_b200.routing import mrtm
+    from oracle.calendar_utils import set_month_arrays
+    w = synthetic.make_world(24, 48, 700, 6, seed=31)
+    sy, ey, m = 1991, 1993, 36
+    s = w.settings()
+    um = mrtm.upstream_genmatrix(mrtm.upstream(w.coords, mrtm.downstream(w.coords, w.flow_dir, s), s))
+    nd = set_month_arrays(m, sy, ey)[:, 2]
+    members, pms = [], []
+    for k in range(3):
+        pm = synthetic.pm_inputs(w, sy, ey, nlcs=8, seed=10 + k)
+        ab = synthetic.abcd_inputs(w, m, seed=20 + k, with_pet=False)
+        for key in ens.PM_FORCING:
+            pm[key] = np.nan_to_num(pm[key])
+        mem = {key: pm[key] for key in ens.PM_FORCING}
+        mem['precip'], mem['tmin'] = ab['precip'], np.nan_to_num(ab['tmin'])
+        members.append(mem)
+        pms.append((pm, ab))
+    pm0, ab0 = pms[0]
+    tables = {k: v for k, v in pm0.items() if k not in ens.PM_FORCING + ('lct_load', 'tairprev_load')}
+    st = ens.EnsembleStatics(w.ncell, sy, ey, tables, pm0['lct_load'], pm0['elev'], pm0['water_idx'], pm0['snow_idx'],
+                             pm0['lc_years'], 8, w.n_basins, w.basin_ids, ab0['pars'], w.area, w.flow_dist, w.velocity, um,
+                             nd, 10800, m, 6)
+    res = ens.run_ensemble(st, members, output_vars=('pet', 'q', 'avgchflow', 'chstorage'))
+    assert res['basin_aggregates'].shape == (3, 2, m, w.n_basins) and res['stats']['members_local'] == 3
+    for k, (pm, ab) in enumerate(pms):
+        data = SimpleNamespace(**{**pm0, **{key: members[k][key] for key in ens.PM_FORCING}})   # statics of member 0
+        pet = pm_mod.run_pmpet(data, w.ncell, 8, sy, ey, pm0['water_idx'], pm0['snow_idx'], pm0['lc_years'])
+        _, _, q, _ = abcd.abcd_execute(w.n_basins, w.basin_ids, pet, members[k]['precip'], members[k]['tmin'], ab0['pars'],
+                                       m, m, -1)
+        chs, avg, _ = mrtm.route(um, q, w.flow_dist, w.velocity, w.area, nd, 10800, 6)
+        got = res[k]
+        assert bitwise_equal(got['pet'], pet) and bitwise_equal(got['q'], q)
+        assert bitwise_equal(got['avgchflow'], avg) and bitwise_equal(got['chstorage'], chs)
+        for b in range(w.n_basins):
+            idx = w.basin_ids == b + 1
+            want = np.nansum(q[idx] * (w.area[idx] * 1e-6)[:, None], axis=0)
+            assert max_rel(res['basin_aggregates'][k, 0, :, b], want, floor=1e-12) < 1e-12

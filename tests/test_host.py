@@ -231,6 +231,28 @@ st = sharding.gather_stack(agg)
 assert st.shape == (2, 3, 4) and float(st[0].mean()) == 0.0 and float(st[1].mean()) == 1.0
 members = sharding.partition_members(5, 2)[r]
 assert list(members) == ([0, 1, 2] if r == 0 else [3, 4])
+# calibrate_all under torch.distributed: whole basins per rank, result files per basin, tables gathered on every rank
+# (the differential evolution itself needs the GPU: it is replaced by a deterministic stand-in here)
+from types import SimpleNamespace
+from xanthos_b200.calibrate import calibrate_abcd as cal
+seen = []
+def fake(basin_nums, *a, **k):
+    seen.extend(basin_nums)
+    b = np.asarray(basin_nums, dtype=float)
+    return np.stack([b, b * 2, b * 3, b * 4, b * 5], axis=1), b / 10.0, {'nfev': np.full(len(b), 7)}
+cal.calibrate_basins = fake
+st = SimpleNamespace(set_calibrate=0, cal_basins=['1-4', '6'], nmonths=12, runoff_spinup=12, obs_unit='km3_per_mth',
+                     calib_out_dir=sys.argv[4])
+data = SimpleNamespace(basin_ids=basin_ids, basin_names=None, area=None, precip=None, cal_obs=None, tmin=np.zeros(1))
+pars, kge = cal.calibrate_all(st, data, None, None)
+want = np.array([1., 2., 3., 4., 6.])
+assert pars.shape == (5, 5) and np.array_equal(pars[:, 0], want) and np.allclose(kge, want / 10), (pars, kge)
+assert sorted(seen) == sorted(int(b) for b in sharding.partition_basins(basin_ids, 2, basins=[1, 2, 3, 4, 6])[r])
+dist.barrier()
+for b in (1, 2, 3, 4, 6):
+    assert np.load(os.path.join(sys.argv[4], 'kge_result_basin_%d.npy' % b))[0] == b / 10.0
+    assert np.array_equal(np.load(os.path.join(sys.argv[4], 'abcdm_parameters_basin_%d.npy' % b))[0, :2], [b, 2 * b])
+assert not os.path.exists(os.path.join(sys.argv[4], 'kge_result_basin_5.npy'))
 dist.destroy_process_group()
 print("rank", r, "ok")
 '''
@@ -240,7 +262,7 @@ def test_two_rank_gather_with_gloo(tmp_path):
     script = tmp_path / 'worker.py'
     script.write_text(GLOO_WORKER)
     port = str(29500 + os.getpid() % 2000)
-    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), str(tmp_path)], stdout=subprocess.PIPE,
                               stderr=subprocess.STDOUT) for r in range(2)]
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs

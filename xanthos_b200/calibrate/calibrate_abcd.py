@@ -371,13 +371,36 @@ def calibrate_all(settings, data, pet, router_function, popsize=15, maxiter=1000
     for b in basins:
         name = data.basin_names[b - 1] if getattr(data, 'basin_names', None) is not None else ''
         logging.info("\tCalibrating Basin:  {} ({})".format(b, name))
+    # One process per GPU (torch.distributed initialised by the launcher): whole basins per rank, balanced by cell
+    # count - every basin's differential evolution is independent (the reference's loop, :256-262, has no coupling
+    # either).  Each rank writes the result files of its own basins; the parameter / KGE tables are gathered.
+    import torch.distributed as dist
+    dist_on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist_on else (0, 1)
+    mine = basins
+    if dist_on:
+        from .. import sharding
+        mine = [int(b) for b in sharding.partition_basins(data.basin_ids, world, basins=basins)[rank]]
     st = time.time()
-    pars, kge, res = calibrate_basins(basins, data.basin_ids, data.area, data.precip, pet, data.cal_obs, data.tmin,
-                                      settings.nmonths, settings.runoff_spinup, settings.obs_unit, popsize=popsize,
-                                      maxiter=maxiter, seed=seed)
     par_names = 'abcd' + 'm' * (data.tmin is not None)
-    for i, b in enumerate(basins):
-        save_results(settings.calib_out_dir, b, np.array([kge[i]]), pars[i][None, :], par_names)
-    logging.info("\tCalibration of {} basins: {} evaluations in {:.2f} s".format(
-        len(basins), int(res['nfev'].sum()), time.time() - st))
+    npar = len(par_names)
+    pars, kge, nfev = np.zeros((0, npar)), np.zeros(0), 0
+    if mine:
+        pars, kge, res = calibrate_basins(mine, data.basin_ids, data.area, data.precip, pet, data.cal_obs, data.tmin,
+                                          settings.nmonths, settings.runoff_spinup, settings.obs_unit, popsize=popsize,
+                                          maxiter=maxiter, seed=seed)
+        nfev = int(res['nfev'].sum())
+        for i, b in enumerate(mine):
+            save_results(settings.calib_out_dir, b, np.array([kge[i]]), pars[i][None, :], par_names)
+    if dist_on:
+        import torch
+        from .. import sharding
+        pos = {b: i for i, b in enumerate(basins)}
+        rows = [pos[b] for b in mine]
+        local = torch.from_numpy(np.concatenate([pars, kge[:, None]], axis=1))
+        local = local.cuda() if dist.get_backend() == 'nccl' else local
+        full = sharding.gather_ragged_rows(rows, local, len(basins)).cpu().numpy()
+        pars, kge = full[:, :npar], full[:, npar]
+    logging.info("\tCalibration of {} basins ({} on this rank): {} evaluations in {:.2f} s".format(
+        len(basins), len(mine), nfev, time.time() - st))
     return pars, kge

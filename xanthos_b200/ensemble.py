@@ -1,0 +1,216 @@
+"""
+Multi-member runs of the hot path (BASELINE.json config 5: "64-member ESM x SSP scenario ensemble ... sharded by member").
+
+The reference has no ensemble driver: a user loops over configuration files, one `Xanthos(ini).execute()` per scenario
+(xanthos/model.py, components.py:298-385), and every scenario re-reads the static data.  Here the static part (land
+cover, PM tables, basin plan, routing plan, ABCD parameters) is staged once and the members stream through
+PET -> ABCD -> MRTM with their copies overlapped:
+
+    h2d stream     : forcing of member k+1  (8 fields, pinned host -> HBM, transposed to month-major)
+    compute stream : PM -> ABCD -> MRTM -> basin aggregates of member k
+    d2h stream     : requested outputs of member k-1  (HBM -> pinned host, cell-major like the reference's arrays)
+
+At most two members' forcing is resident.  Only the variables named in `output_vars` are copied back (the reference
+keeps PET, AET, Q, Sav, ChStorage and Avg_ChFlow of a scenario in host memory but writes `output_vars` only,
+data_writer/out_writer.py:60-110).  With torch.distributed initialised the members are dealt in contiguous blocks to the ranks
+(no collective in the data path) and the basin aggregates [n_members, 2, nmonths, n_basins] are gathered at the end.
+"""
+
+from types import SimpleNamespace
+
+import numpy as np
+
+from . import _cuda as C
+from . import sharding
+from .pet import penman_monteith as pm_mod
+from .runoff import abcd as abcd_mod
+from .routing import mrtm as mrtm_mod
+
+PM_FORCING = ('tair_load', 'TMIN_load', 'rhs_load', 'wind_load', 'rsds_load', 'rlds_load')
+FORCING = PM_FORCING + ('precip', 'tmin')
+OUTPUTS = ('pet', 'aet', 'q', 'soilmoisture', 'chstorage', 'avgchflow')
+
+
+class EnsembleStatics:
+    """Everything that does not change from member to member, staged on the device once."""
+
+    def __init__(self, ncell, start_yr, end_yr, pm_tables, lct_load, elev, water_idx, snow_idx, lc_years, nlcs,
+                 n_basins, basin_ids, abcd_pars, area, flow_dist, velocity, upstream_matrix, ndays, dt=3 * 3600,
+                 runoff_spinup=None, routing_spinup=None):
+        torch = C.torch_cuda()
+        self.ncell, self.start_yr, self.end_yr = int(ncell), int(start_yr), int(end_yr)
+        self.nmonths = (self.end_yr - self.start_yr + 1) * 12
+        self.ld = C.padded_ld(self.ncell)
+        self.tables = dict(pm_tables)
+        self.water_idx, self.snow_idx, self.lc_years, self.nlcs = int(water_idx), int(snow_idx), list(lc_years), int(nlcs)
+        self.d_lct = pm_mod.stage_land_cover(lct_load, self.ld)
+        self.d_elev = C.dev_vector(elev)
+        self.n_basins = int(n_basins)
+        self.basin_ids = np.asarray(basin_ids)
+        rows = abcd_mod._basin_rows(self.n_basins, self.basin_ids, np.asarray(abcd_pars).shape[0])
+        self.plan = abcd_mod.basin_plan(rows, self.n_basins)
+        self.d_pars = torch.from_numpy(np.ascontiguousarray(abcd_pars, dtype=np.float64)).cuda()
+        self.d_area, self.d_L, self.d_V = C.dev_vector(area), C.dev_vector(flow_dist), C.dev_vector(velocity)
+        self.d_area_km3 = self.d_area * 1e-6
+        self.um = upstream_matrix
+        self.ndays = np.asarray(ndays, dtype=np.int32)[:self.nmonths]
+        self.dt = float(dt)
+        self.runoff_spinup = self.nmonths if runoff_spinup is None else int(runoff_spinup)
+        self.routing_spinup = self.nmonths if routing_spinup is None else int(routing_spinup)
+
+    def data_ns(self, fields):
+        d = dict(self.tables)
+        d.update({k: fields[k] for k in PM_FORCING})
+        d['lct_load'] = self.d_lct
+        d['elev'] = self.d_elev
+        return SimpleNamespace(**d)
+
+
+class EnsembleRunner:
+    def __init__(self, statics, output_vars=('q', 'avgchflow'), aggregates=True):
+        torch = C.torch_cuda()
+        bad = [v for v in output_vars if v not in OUTPUTS]
+        if bad:
+            raise C.ValidationException("unknown output variable(s) {}; choose from {}".format(bad, OUTPUTS))
+        self.s, self.output_vars, self.aggregates = statics, tuple(output_vars), bool(aggregates)
+        self.h2d, self.d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        self.h2d_bytes = self.d2h_bytes = 0
+        self._torch = torch
+
+    # ---- the three pipeline stages (everything is enqueued, nothing waits) ------------------------------------------
+    def _upload(self, member):
+        torch = self._torch
+        if callable(member):
+            member = member()
+        missing = [k for k in FORCING if k not in member]
+        if missing:
+            raise C.ValidationException("ensemble member lacks {}".format(missing))
+        compute = torch.cuda.current_stream()
+        fields = {}
+        with torch.cuda.stream(self.h2d):
+            for k in FORCING:
+                a = member[k]
+                if tuple(a.shape) != (self.s.ncell, self.s.nmonths):
+                    raise C.ValidationException("member field {} has shape {}, expected {}".format(
+                        k, tuple(a.shape), (self.s.ncell, self.s.nmonths)))
+                f = C.Field.from_host(a, ld=self.s.ld)
+                f.t.record_stream(compute)
+                fields[k] = f
+                self.h2d_bytes += a.nbytes
+            ev = torch.cuda.Event()
+            ev.record(self.h2d)
+        return fields, ev
+
+    def _compute(self, fields):
+        s = self.s
+        pet = pm_mod.run_pmpet_device(s.data_ns(fields), s.ncell, s.nlcs, s.start_yr, s.end_yr, s.water_idx, s.snow_idx,
+                                      s.lc_years)
+        want = tuple(k for k, v in (('aet', 'aet'), ('q', 'q'), ('sav', 'soilmoisture')) if v in self.output_vars or k == 'q')
+        res = abcd_mod.run_device(s.plan, s.d_pars, pet, fields['precip'], fields['tmin'], s.nmonths, s.runoff_spinup,
+                                  want=want)
+        chs, avg, inst = mrtm_mod.route_device(s.um, res['q'], s.d_L, s.d_V, s.d_area, s.ndays, s.dt, s.routing_spinup,
+                                               want_chs='chstorage' in self.output_vars)
+        out = {'pet': pet, 'aet': res.get('aet'), 'q': res['q'], 'soilmoisture': res.get('sav'), 'chstorage': chs,
+               'avgchflow': avg}
+        agg = None
+        if self.aggregates:       # basin runoff in km3 / month and basin sum of the mean streamflow, [2, nmonths, n_basins]
+            agg = self._torch.empty((2, s.nmonths, s.n_basins), dtype=self._torch.float64, device='cuda')
+            C.check(C.lib().xan_basin_sum(s.plan._plan, C.ptr(res['q'].t), C.ptr(s.d_area_km3), s.nmonths, res['q'].ld,
+                                          C.ptr(agg[0]), C.stream_ptr()))
+            C.check(C.lib().xan_basin_sum(s.plan._plan, C.ptr(avg.t), None, s.nmonths, avg.ld, C.ptr(agg[1]),
+                                          C.stream_ptr()))
+        return out, agg
+
+    def _download(self, out, agg):
+        torch = self._torch
+        compute = torch.cuda.current_stream()
+        staged = {v: out[v].to_device_cell_major() for v in self.output_vars}      # transposes run on the compute stream
+        ev = torch.cuda.Event()
+        ev.record(compute)
+        self.d2h.wait_event(ev)
+        host = {}
+        with torch.cuda.stream(self.d2h):
+            for v, dev in staged.items():
+                dev.record_stream(self.d2h)
+                h = C.host_pool.acquire((self.s.ncell, self.s.nmonths))
+                h.copy_(dev, non_blocking=True)
+                host[v] = h
+                self.d2h_bytes += h.numel() * 8
+            if agg is not None:
+                agg.record_stream(self.d2h)
+                h = torch.empty(tuple(agg.shape), dtype=torch.float64, pin_memory=True)
+                h.copy_(agg, non_blocking=True)
+                host['basin_aggregates'] = h
+                self.d2h_bytes += h.numel() * 8
+            done = torch.cuda.Event()
+            done.record(self.d2h)
+        return host, done
+
+    # ---- driver ----------------------------------------------------------------------------------------------------------
+    def run(self, members):
+        """Generator: yields (index, {variable: host ndarray [ncell, nmonths], 'basin_aggregates': [2, nmonths, n_basins]})
+        in member order; member k+1 is being uploaded and member k computed while member k-1 is handed out."""
+        torch = self._torch
+        members = list(members)
+        if not members:
+            return
+        compute = torch.cuda.current_stream()
+        nxt = self._upload(members[0])
+        pending = None            # (index, host tensors, done event) of the member whose outputs are in flight
+        computed = []             # completion events of the compute stage, to bound the host's run-ahead
+        for k in range(len(members)):
+            fields, ev = nxt
+            compute.wait_event(ev)
+            out, agg = self._compute(fields)
+            host, done = self._download(out, agg)
+            cev = torch.cuda.Event()
+            cev.record(compute)
+            computed.append(cev)
+            del fields, out, agg
+            if k + 1 < len(members):
+                if k >= 1:
+                    computed[k - 1].synchronize()      # at most two members' forcing resident
+                nxt = self._upload(members[k + 1])
+            if pending is not None:
+                yield self._finish(pending)
+            pending = (k, host, done)
+        yield self._finish(pending)
+
+    @staticmethod
+    def _finish(p):
+        k, host, done = p
+        done.synchronize()
+        res = {}
+        for v, h in host.items():
+            res[v] = C.host_pool.as_array(h) if v != 'basin_aggregates' else h.numpy()
+        return k, res
+
+
+def run_ensemble(statics, members, output_vars=('q', 'avgchflow'), aggregates=True, on_result=None):
+    """
+    Run every member (this rank's share when torch.distributed is initialised: a contiguous block per rank,
+    sharding.partition_members).
+    Returns {member index: result dict}; with `on_result(index, result)` given the results are handed to it instead of
+    being kept (a 64-member ensemble of 1,032 months is 2 x 36 GB of output).  On every rank the returned dict also has
+    the key 'basin_aggregates': [n_members, 2, nmonths, n_basins] of ALL members (all-gather over NCCL).
+    """
+    torch = C.torch_cuda()
+    import torch.distributed as dist
+    members = list(members)
+    dist_on = dist.is_available() and dist.is_initialized()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist_on else (0, 1)
+    mine = [int(i) for i in sharding.partition_members(len(members), world)[rank]]
+    runner = EnsembleRunner(statics, output_vars, aggregates)
+    results = {}
+    agg_local = torch.zeros((len(mine), 2, statics.nmonths, statics.n_basins), dtype=torch.float64)
+    for j, res in runner.run([members[i] for i in mine]):
+        if aggregates:
+            agg_local[j] = torch.from_numpy(res['basin_aggregates'])
+        if on_result is not None:
+            on_result(mine[j], res)
+        else:
+            results[mine[j]] = res
+    if aggregates:      # the only collective: every rank gets the basin aggregates of all members
+        results['basin_aggregates'] = sharding.gather_ragged_rows(mine, agg_local.cuda(), len(members)).cpu().numpy()
+    results['stats'] = {'h2d_bytes': runner.h2d_bytes, 'd2h_bytes': runner.d2h_bytes, 'members_local': len(mine)}
+    return results
