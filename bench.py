@@ -361,7 +361,7 @@ def run_ours(args, rank, world_size, local_rank):
     n_mem = max(6, min(args.steps, 12))
     members = [member_a if k % 2 == 0 else member_b for k in range(n_mem * world_size)]
     sink = []
-    ens.run_ensemble(statics, members[:2 * world_size], on_result=lambda i, r: sink.append(float(r['avgchflow'][0, -1])))
+    ens.run_ensemble(statics, members[:4 * world_size], on_result=lambda i, r: sink.append(float(r['avgchflow'][0, -1])))
     gc.collect()
     gc.disable()
     try:
@@ -557,6 +557,231 @@ def run_ours(args, rank, world_size, local_rank):
         if calib is not None:
             line['cpu_baseline']['calib'] = cpu_calib_baseline(world, pm, ab)
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations (`--workload`): one JSON line each, same keys as the main line
+# ------------------------------------------------------------------------------------------------
+def _line(metric, unit, value, ms_per_step, args, world_size, config, extra):
+    line = {'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world_size, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': config.pop('scaling', 'weak'),
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': config}
+    line.update(extra)
+    return line
+
+
+def run_workload(args, rank, world_size, local_rank):
+    import torch
+    import torch.distributed as dist
+    from xanthos_b200 import synthetic, _cuda as C
+    from xanthos_b200.pet import hargreaves_samani as hs_mod
+    from xanthos_b200.runoff import abcd as abcd_mod
+    from xanthos_b200.routing import mrtm as mrtm_mod
+    torch.cuda.set_device(local_rank)
+    C.lib()
+    peaks, peak_src = _peaks()
+    world = synthetic.make_world(seed=0)
+    ncell = world.ncell
+    name = args.workload
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3], dtype=torch.float64, device='cuda')
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) / steps, float(t[1]) / steps
+
+    def pinned(a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).pin_memory().numpy()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    line = None
+    if name == 'hs_abcd_1140':
+        # BASELINE config 2: Hargreaves-Samani PET + ABCD runoff, no routing, 67,420 cells x 1,140 months (2006-2100)
+        sy, ey, m, spin = 2006, 2100, 1140, 360
+        hs = synthetic.hs_inputs(world, sy, ey, seed=2 + rank)
+        ab = synthetic.abcd_inputs(world, m, seed=1 + rank, with_pet=False)
+        host = {k: pinned(np.nan_to_num(hs[k])) for k in ('hs_tas', 'hs_tmax', 'hs_tmin')}
+        host['precip'], host['tmin'] = pinned(ab['precip']), pinned(np.nan_to_num(ab['tmin']))
+        dev = {k: C.Field.from_host(v) for k, v in host.items()}
+        rows = abcd_mod._basin_rows(world.n_basins, world.basin_ids, world.n_basins)
+        plan = abcd_mod.basin_plan(rows, world.n_basins)
+        d_pars = torch.from_numpy(ab['pars']).cuda()
+        cfg = SimpleNamespace(ncell=ncell, nmonths=m, StartYear=sy, EndYear=ey)
+
+        def dev_step():
+            pet = hs_mod.execute_device(dev['hs_tas'], dev['hs_tmax'], dev['hs_tmin'], world.coords[:, 2], sy)
+            return abcd_mod.run_device(plan, d_pars, pet, dev['precip'], dev['tmin'], m, spin)
+
+        def e2e_step():
+            C.forget_all()
+            with C.async_host():
+                data = SimpleNamespace(coords=world.coords, hs_tas=host['hs_tas'], hs_tmax=host['hs_tmax'],
+                                       hs_tmin=host['hs_tmin'])
+                pet = hs_mod.execute(cfg, data)
+                out = abcd_mod.abcd_execute(world.n_basins, world.basin_ids, pet, host['precip'], host['tmin'], ab['pars'],
+                                            m, spin, -1)
+            return float(out[2][0, -1])
+        sampler.mark()
+        ms, _ = timed(dev_step, args.steps, args.warmup)
+        clocks = sampler.stop()
+        _, e2e_ms = timed(e2e_step, max(2, min(args.steps, 4)), 1)
+        cm = float(ncell) * m
+        alg = (32 + 48 + 24 * spin / m) * cm
+        line = _line('cell-months/s (HS+ABCD)', 'cell-months/s', world_size * cm / (ms * 1e-3), ms, args, world_size,
+                     {'workload': name, 'ncell': ncell, 'nmonths': m, 'runoff_spinup': spin,
+                      'parallelism': 'member-per-gpu', 'l2': 'inputs (5 x 615 MB) exceed the 126 MB L2'},
+                     {'e2e': {'value': world_size * cm / (e2e_ms * 1e-3), 'unit': 'cell-months/s', 'ms_per_step': e2e_ms,
+                              'h2d_bytes_per_step': int(sum(v.nbytes for v in host.values())),
+                              'd2h_bytes_per_step': int(5 * ncell * m * 8)},
+                      'roofline': {'bound': 'hbm', 'kernel': 'hs_pet + abcd_spinup + abcd_sim', 'achieved': alg / (ms * 1e-3) / 1e9,
+                                   'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': alg / (ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                                   'algorithmic_bytes': alg, 'traffic': None, 'peak_source': peak_src},
+                      'clocks': clocks, 'gpu_launches': 5 * args.steps})
+    elif name == 'mrtm_hourly_360':
+        # BASELINE config 3: routing only, hourly sub-steps over 360 months (+ 360 months of spin-up)
+        m, spin, dt = 360, 360, 3600
+        q_h = pinned(synthetic.runoff_input(world, m, seed=3 + rank))
+        q = C.Field.from_host(q_h)
+        s = world.settings()
+        um = mrtm_mod.upstream_genmatrix(mrtm_mod.upstream(world.coords, mrtm_mod.downstream(world.coords, world.flow_dir, s), s))
+        L, V, A = C.dev_vector(world.flow_dist), C.dev_vector(world.velocity), C.dev_vector(world.area)
+        nd = month_days_mod4(m, START_YR)
+        sampler.mark()
+        ms, _ = timed(lambda: mrtm_mod.route_device(um, q, L, V, A, nd, dt, spin), args.steps, args.warmup)
+        clocks = sampler.stop()
+
+        def e2e_step():
+            C.forget_all()
+            return float(mrtm_mod.route(um, q_h, world.flow_dist, world.velocity, world.area, nd, dt, spin)[1][0, -1])
+        _, e2e_ms = timed(e2e_step, max(2, min(args.steps, 4)), 1)
+        cm = float(ncell) * m
+        nsub = int(sum(int(d) * 24 for d in nd)) * 2
+        alg = BYTES_MRTM * cm
+        line = _line('cell-months/s (MRTM hourly)', 'cell-months/s', world_size * cm / (ms * 1e-3), ms, args, world_size,
+                     {'workload': name, 'ncell': ncell, 'nmonths': m, 'routing_spinup': spin, 'dt_s': dt,
+                      'sub_steps': nsub, 'parallelism': 'member-per-gpu', 'mrtm_plan': um.info},
+                     {'e2e': {'value': world_size * cm / (e2e_ms * 1e-3), 'unit': 'cell-months/s', 'ms_per_step': e2e_ms,
+                              'h2d_bytes_per_step': int(q_h.nbytes), 'd2h_bytes_per_step': int(2 * q_h.nbytes + 8 * ncell)},
+                      'roofline': {'bound': 'hbm', 'kernel': 'mrtm_warp_kernel', 'achieved': alg / (ms * 1e-3) / 1e9,
+                                   'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': alg / (ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                                   'algorithmic_bytes': alg, 'traffic': None, 'peak_source': peak_src,
+                                   'us_per_sub_step': ms * 1e3 / nsub,
+                                   'note': 'bound by the sequential sub-step recurrence, not by HBM (DESIGN.md section 4)'},
+                      'clocks': clocks, 'gpu_launches': args.steps})
+    elif name == 'calib_235x64x200':
+        # BASELINE config 4: 235 basins x 64-member differential evolution x 200 generations; basins sharded over the
+        # ranks by cell count (strong scaling: the total work is fixed)
+        from xanthos_b200.calibrate import calibrate_abcd as cal
+        from xanthos_b200 import sharding
+        m, spin, P, gens = 360, 360, 64, 200
+        ab = synthetic.abcd_inputs(world, m, seed=1)
+        tmin = np.nan_to_num(ab['tmin'])
+        ev = cal.BasinEvaluator(world.basin_ids, world.area, ab['precip'], ab['pet'], tmin, m, spin, 'km3_per_mth')
+        all_b = np.arange(1, world.n_basins + 1)
+        _, series = ev.evaluate(all_b, np.broadcast_to(ab['pars'][:, None, :], (world.n_basins, 1, 5)).copy(),
+                                np.ones((world.n_basins, m)), want_series=True)
+        obs = series[:, 0, :] * (1 + np.random.default_rng(4).normal(0, 0.05, (world.n_basins, m)))   # "VIC-like"
+        mine = np.asarray(sharding.partition_basins(world.basin_ids, world_size)[rank])
+        cells = np.bincount(np.asarray(world.basin_ids).astype(int), minlength=world.n_basins + 1)
+
+        def loop():
+            return cal.differential_evolution_device(ev, mine, obs[mine - 1], cal.BOUNDS_SNOW, maxiter=gens, tol=0.0,
+                                                     seed=4, pop_members=P)
+        loop() if args.warmup and gens <= 20 else cal.differential_evolution_device(
+            ev, mine, obs[mine - 1], cal.BOUNDS_SNOW, maxiter=3, tol=0.0, seed=4, pop_members=P)
+        sampler.mark()
+        barrier()
+        t0 = time.perf_counter()
+        r = loop()
+        barrier()
+        t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device='cuda')
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        clocks = sampler.stop()
+        ms = float(t[0])
+        n_eval = world.n_basins * P * (gens + 1)
+        best = 1 - r['fun']
+        line = _line('calibration param-sets/s', 'param-sets/s', n_eval / (ms * 1e-3), ms, args, world_size,
+                     {'workload': name, 'basins': int(world.n_basins), 'population': P, 'generations': gens, 'months': m,
+                      'spinup': spin, 'scaling': 'strong',
+                      'parallelism': 'basins over %d rank(s), LPT by cell count; rank 0 holds %d basins / %d cells, largest '
+                                     'basin %d cells' % (world_size, len(mine), int(cells[mine].sum()), int(cells.max()))},
+                     {'e2e': {'value': n_eval / (ms * 1e-3), 'unit': 'param-sets/s', 'ms_per_step': ms,
+                              'h2d_bytes_per_step': int(obs[mine - 1].nbytes),
+                              'd2h_bytes_per_step': int(len(mine) * P * 6 * 8),
+                              'note': 'the whole DE loop is one public call; forcing staged once before the loop'},
+                      'roofline': {'bound': 'hbm', 'kernel': 'kge_pop_pass_kernel', 'achieved': None, 'peak': peaks['hbm_gbs'],
+                                   'unit': 'GB/s', 'frac': None, 'traffic': None,
+                                   'note': 'FP64-pipe bound (profiles/r01c_calib_kernels.csv), see roofline of the main line'},
+                      'kge_rank0': {'median': float(np.median(best)), 'min': float(best.min())},
+                      'ms_per_generation': ms / (gens + 1), 'clocks': clocks, 'gpu_launches': 6 * (gens + 1)})
+    elif name == 'ensemble_64x1032':
+        # BASELINE config 5: 64-member ensemble, full PM + ABCD + MRTM 2015-2100 (1,032 months), members over the ranks
+        from xanthos_b200 import ensemble as ens
+        sy, ey = 2015, 2100
+        m = (ey - sy + 1) * 12
+        n_members = int(os.environ.get('XANTHOS_BENCH_MEMBERS', '64'))
+        pm = synthetic.pm_inputs(world, sy, ey, nlcs=NLCS, seed=1 + rank)
+        ab = synthetic.abcd_inputs(world, m, seed=1 + rank, with_pet=False)
+        tables = {k: v for k, v in pm.items() if k not in ens.PM_FORCING + ('lct_load', 'tairprev_load')}
+        mem_a = {k: pinned(np.nan_to_num(pm[k])) for k in ens.PM_FORCING}
+        mem_a['precip'], mem_a['tmin'] = pinned(ab['precip']), pinned(np.nan_to_num(ab['tmin']))
+        mem_b = {k: pinned(np.roll(v, 11, axis=0)) for k, v in mem_a.items()}
+        s = world.settings()
+        um = mrtm_mod.upstream_genmatrix(mrtm_mod.upstream(world.coords, mrtm_mod.downstream(world.coords, world.flow_dir, s), s))
+        nd = month_days_mod4(m, sy)
+        st = ens.EnsembleStatics(ncell, sy, ey, tables, pm['lct_load'], pm['elev'], pm['water_idx'], pm['snow_idx'],
+                                 pm['lc_years'], NLCS, world.n_basins, world.basin_ids, ab['pars'], world.area,
+                                 world.flow_dist, world.velocity, um, nd, DT, RUNOFF_SPINUP, ROUTING_SPINUP)
+        members = [mem_a if k % 2 == 0 else mem_b for k in range(n_members)]
+        sink = []
+        ens.run_ensemble(st, members[:4 * world_size], on_result=lambda i, r: sink.append(float(r['avgchflow'][0, -1])))
+        sampler.mark()
+        barrier()
+        t0 = time.perf_counter()
+        er = ens.run_ensemble(st, members, on_result=lambda i, r: sink.append(float(r['avgchflow'][0, -1])))
+        barrier()
+        t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device='cuda')
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        clocks = sampler.stop()
+        ms = float(t[0])
+        cm = float(ncell) * m * n_members
+        nloc = max(er['stats']['members_local'], 1)
+        line = _line('cell-months/s (PM+ABCD+MRTM)', 'cell-months/s', cm / (ms * 1e-3), ms / nloc, args, world_size,
+                     {'workload': name, 'ncell': ncell, 'nmonths': m, 'members': n_members, 'nlcs': NLCS,
+                      'runoff_spinup': RUNOFF_SPINUP, 'routing_spinup': ROUTING_SPINUP, 'dt_s': DT, 'scaling': 'strong',
+                      'parallelism': 'members over %d rank(s), %d on rank 0' % (world_size, nloc)},
+                     {'e2e': {'value': cm / (ms * 1e-3), 'unit': 'cell-months/s', 'ms_per_step': ms / nloc,
+                              'h2d_bytes_per_step': int(er['stats']['h2d_bytes'] // nloc),
+                              'd2h_bytes_per_step': int(er['stats']['d2h_bytes'] // nloc),
+                              'note': 'value IS the end-to-end number: every member comes from pinned host memory and its '
+                                      'q / avgchflow / basin aggregates return to the host; ms_per_step = per member on a rank'},
+                      'total_ms': ms, 'clocks': clocks, 'gpu_launches': 11 * nloc, 'timeline': er['stats'].get('timeline'),
+                      'roofline': {'bound': 'hbm', 'kernel': 'pipeline (h2d | pm + abcd + mrtm | d2h)', 'achieved': None,
+                                   'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': None, 'traffic': None,
+                                   'h2d_gbs_per_rank': er['stats']['h2d_bytes'] / (ms * 1e-3) / 1e9,
+                                   'd2h_gbs_per_rank': er['stats']['d2h_bytes'] / (ms * 1e-3) / 1e9}})
+    else:
+        raise SystemExit("unknown --workload %s" % name)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -769,6 +994,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-calib', action='store_true')
     ap.add_argument('--cpu-budget', type=float, default=20.0)
+    ap.add_argument('--workload', default=WORKLOAD,
+                    choices=[WORKLOAD, 'hs_abcd_1140', 'mrtm_hourly_360', 'calib_235x64x200', 'ensemble_64x1032'])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -792,7 +1019,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     try:
-        run_ours(args, rank, world_size, local_rank)
+        if args.workload != WORKLOAD:
+            run_workload(args, rank, world_size, local_rank)
+        else:
+            run_ours(args, rank, world_size, local_rank)
     finally:
         if world_size > 1:
             import torch.distributed as dist

@@ -169,7 +169,7 @@ def differential_evolution_batched(evaluate, n_problems, bounds, popsize=15, max
 
 
 def differential_evolution_device(ev, basin_nums, robs, bounds, popsize=15, maxiter=1000, tol=0.01, atol=0.0,
-                                  mutation=(0.5, 1.0), recombination=0.7, seed=None, check_every=4):
+                                  mutation=(0.5, 1.0), recombination=0.7, seed=None, check_every=4, pop_members=None):
     """
     The same solver with population, energies and generation logic on the device (xan_de_init / xan_de_trial /
     xan_de_select, csrc/de.cu): a generation is trial kernel -> objective kernels -> selection kernel, and the host
@@ -181,7 +181,7 @@ def differential_evolution_device(ev, basin_nums, robs, bounds, popsize=15, maxi
     lib = C.lib()
     bounds = np.asarray(bounds, dtype=float)
     D = bounds.shape[0]
-    S = max(5, popsize * D)
+    S = max(5, popsize * D) if pop_members is None else int(pop_members)   # scipy: popsize x D members
     n = len(basin_nums)
     bn = np.asarray(basin_nums)
     seed = int(np.random.SeedSequence(seed).generate_state(2, dtype=np.uint32).astype(np.uint64) @ np.array([1, 1 << 32], dtype=np.uint64))

@@ -10,7 +10,7 @@ PET -> ABCD -> MRTM with their copies overlapped:
     compute stream : PM -> ABCD -> MRTM -> basin aggregates of member k
     d2h stream     : requested outputs of member k-1  (HBM -> pinned host, cell-major like the reference's arrays)
 
-At most two members' forcing is resident.  Only the variables named in `output_vars` are copied back (the reference
+The forcing of at most `prefetch_depth` (2) members is on its way ahead of the member being computed.  Only the variables named in `output_vars` are copied back (the reference
 keeps PET, AET, Q, Sav, ChStorage and Avg_ChFlow of a scenario in host memory but writes `output_vars` only,
 data_writer/out_writer.py:60-110).  With torch.distributed initialised the members are dealt in contiguous blocks to the ranks
 (no collective in the data path) and the basin aggregates [n_members, 2, nmonths, n_basins] are gathered at the end.
@@ -67,8 +67,9 @@ class EnsembleStatics:
 
 
 class EnsembleRunner:
-    def __init__(self, statics, output_vars=('q', 'avgchflow'), aggregates=True):
+    def __init__(self, statics, output_vars=('q', 'avgchflow'), aggregates=True, prefetch_depth=2):
         torch = C.torch_cuda()
+        self.prefetch_depth = max(1, int(prefetch_depth))   # members whose forcing may be on its way ahead of the compute
         bad = [v for v in output_vars if v not in OUTPUTS]
         if bad:
             raise C.ValidationException("unknown output variable(s) {}; choose from {}".format(bad, OUTPUTS))
@@ -76,6 +77,8 @@ class EnsembleRunner:
         self.h2d, self.d2h = torch.cuda.Stream(), torch.cuda.Stream()
         self.h2d_bytes = self.d2h_bytes = 0
         self._torch = torch
+        import os
+        self.timeline = [] if os.environ.get('XANTHOS_ENSEMBLE_TIMELINE') else None   # per member: stage event pairs
 
     # ---- the three pipeline stages (everything is enqueued, nothing waits) ------------------------------------------
     def _upload(self, member):
@@ -86,20 +89,47 @@ class EnsembleRunner:
         if missing:
             raise C.ValidationException("ensemble member lacks {}".format(missing))
         compute = torch.cuda.current_stream()
-        fields = {}
+        staged = {}
+        # Only copy-engine work goes on the h2d stream.  The transposes to month-major run on the compute stream in front
+        # of the member's kernels: a kernel on the h2d stream would wait for SM resources behind the routing kernel of
+        # the previous member (one cooperative block per SM, the whole register file) and hold up the next copy.
         with torch.cuda.stream(self.h2d):
+            e0 = self._mark(self.h2d)
             for k in FORCING:
                 a = member[k]
                 if tuple(a.shape) != (self.s.ncell, self.s.nmonths):
                     raise C.ValidationException("member field {} has shape {}, expected {}".format(
                         k, tuple(a.shape), (self.s.ncell, self.s.nmonths)))
-                f = C.Field.from_host(a, ld=self.s.ld)
-                f.t.record_stream(compute)
-                fields[k] = f
-                self.h2d_bytes += a.nbytes
-            ev = torch.cuda.Event()
+                if not isinstance(a, torch.Tensor):
+                    a = np.asarray(a)
+                    if a.dtype != np.float64 or not a.flags['C_CONTIGUOUS']:
+                        a = np.ascontiguousarray(a, dtype=np.float64)
+                    a = torch.from_numpy(a)
+                t = a.to(device='cuda', dtype=torch.float64, non_blocking=True)
+                t.record_stream(compute)
+                staged[k] = t
+                self.h2d_bytes += t.numel() * 8
+            ev = torch.cuda.Event(enable_timing=self.timeline is not None)
             ev.record(self.h2d)
-        return fields, ev
+            if self.timeline is not None:
+                self.timeline.append({'h2d': (e0, ev)})
+        return staged, ev
+
+    def _to_fields(self, staged):
+        """cell-major staging tensors -> month-major Fields (compute stream)."""
+        fields = {}
+        for k, t in staged.items():
+            f = C.Field.empty(self.s.ncell, self.s.nmonths, self.s.ld)
+            C.check(C.lib().xan_to_month_major(C.ptr(t), C.ptr(f.t), self.s.ncell, self.s.nmonths, f.ld, 0, C.stream_ptr()))
+            fields[k] = f
+        return fields
+
+    def _mark(self, stream):
+        if self.timeline is None:
+            return None
+        e = self._torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
 
     def _compute(self, fields):
         s = self.s
@@ -142,7 +172,7 @@ class EnsembleRunner:
                 h.copy_(agg, non_blocking=True)
                 host['basin_aggregates'] = h
                 self.d2h_bytes += h.numel() * 8
-            done = torch.cuda.Event()
+            done = torch.cuda.Event(enable_timing=self.timeline is not None)
             done.record(self.d2h)
         return host, done
 
@@ -155,22 +185,37 @@ class EnsembleRunner:
         if not members:
             return
         compute = torch.cuda.current_stream()
-        nxt = self._upload(members[0])
+        n, depth = len(members), self.prefetch_depth
+        uploaded, next_up = {}, 0
         pending = None            # (index, host tensors, done event) of the member whose outputs are in flight
-        computed = []             # completion events of the compute stage, to bound the host's run-ahead
-        for k in range(len(members)):
-            fields, ev = nxt
+        computed = []             # completion events of the compute stage, to bound the uploads' run-ahead
+
+        def pump(k):              # uploads of the members up to k + depth; member j waits for compute j - depth - 1
+            nonlocal next_up
+            while next_up < n and next_up <= k + depth:
+                if next_up - depth - 1 >= 0:
+                    computed[next_up - depth - 1].synchronize()
+                uploaded[next_up] = self._upload(members[next_up])
+                next_up += 1
+        pump(0 - 1)
+        for k in range(n):
+            if k not in uploaded:
+                pump(k - depth)
+            staged, ev = uploaded.pop(k)
             compute.wait_event(ev)
+            c0 = self._mark(compute)
+            fields = self._to_fields(staged)
+            del staged
             out, agg = self._compute(fields)
             host, done = self._download(out, agg)
-            cev = torch.cuda.Event()
+            cev = torch.cuda.Event(enable_timing=self.timeline is not None)
             cev.record(compute)
             computed.append(cev)
+            if self.timeline is not None:
+                self.timeline[k]['compute'] = (c0, cev)
+                self.timeline[k]['done'] = done
             del fields, out, agg
-            if k + 1 < len(members):
-                if k >= 1:
-                    computed[k - 1].synchronize()      # at most two members' forcing resident
-                nxt = self._upload(members[k + 1])
+            pump(k)
             if pending is not None:
                 yield self._finish(pending)
             pending = (k, host, done)
@@ -213,4 +258,11 @@ def run_ensemble(statics, members, output_vars=('q', 'avgchflow'), aggregates=Tr
     if aggregates:      # the only collective: every rank gets the basin aggregates of all members
         results['basin_aggregates'] = sharding.gather_ragged_rows(mine, agg_local.cuda(), len(members)).cpu().numpy()
     results['stats'] = {'h2d_bytes': runner.h2d_bytes, 'd2h_bytes': runner.d2h_bytes, 'members_local': len(mine)}
+    if runner.timeline:      # ms relative to the first upload: (h2d start, end), (compute start, end), outputs on the host
+        torch.cuda.synchronize()
+        t0 = runner.timeline[0]['h2d'][0]
+        results['stats']['timeline'] = [
+            {'h2d': [round(t0.elapsed_time(e), 1) for e in m['h2d']],
+             'compute': [round(t0.elapsed_time(e), 1) for e in m['compute']],
+             'done': round(t0.elapsed_time(m['done']), 1)} for m in runner.timeline if 'compute' in m]
     return results
