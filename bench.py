@@ -153,6 +153,12 @@ def build_inputs(member_seed=1, ncell=NCELL, nmonths=NMONTHS):
     for k in ('tair_load', 'TMIN_load', 'rhs_load', 'wind_load', 'rsds_load', 'rlds_load'):
         pm[k] = np.nan_to_num(pm[k])
     ab['tmin'] = np.nan_to_num(ab['tmin'])
+    # The forcing VALUES are single precision, as in the NetCDF files of the climate models (float variables); the
+    # arrays are float64 like the ones the reference's loader hands out.  Both arms compute on exactly these values.
+    for k in ('tair_load', 'TMIN_load', 'rhs_load', 'wind_load', 'rsds_load', 'rlds_load'):
+        pm[k] = pm[k].astype(np.float32).astype(np.float64)
+    for k in ('precip', 'tmin'):
+        ab[k] = ab[k].astype(np.float32).astype(np.float64)
     return world, pm, ab, end_yr
 
 
@@ -359,26 +365,30 @@ def run_ours(args, rank, world_size, local_rank):
     member_a = {k: host[k] for k in ens.FORCING}
     member_b = {k: pinned(np.roll(host[k], 7, axis=0)) for k in ens.FORCING}    # a second, different member
     n_mem = max(6, min(args.steps, 12))
-    members = [member_a if k % 2 == 0 else member_b for k in range(n_mem * world_size)]
     sink = []
-    ens.run_ensemble(statics, members[:4 * world_size], on_result=lambda i, r: sink.append(float(r['avgchflow'][0, -1])))
-    gc.collect()
-    gc.disable()
-    try:
-        barrier()
-        t0 = time.perf_counter()
-        er = ens.run_ensemble(statics, members, on_result=lambda i, r: sink.append(float(r['avgchflow'][0, -1])))
-        barrier()
-        ens_ms = (time.perf_counter() - t0) * 1e3
-    finally:
-        gc.enable()
-    t = torch.tensor([ens_ms], dtype=torch.float64, device='cuda')
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ens_ms = float(t[0])
+
+    def ensemble_ms(ma, mb):
+        members = [ma if k % 2 == 0 else mb for k in range(n_mem * world_size)]
+        ens.run_ensemble(statics, members[:4 * world_size], on_result=lambda i, r: sink.append(float(r['avgchflow'][0, -1])))
+        gc.collect()
+        gc.disable()
+        try:
+            barrier()
+            t0 = time.perf_counter()
+            er = ens.run_ensemble(statics, members, on_result=lambda i, r: sink.append(float(r['avgchflow'][0, -1])))
+            barrier()
+            ms = (time.perf_counter() - t0) * 1e3
+        finally:
+            gc.enable()
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), er['stats']
+    ens64_ms, ens64_stats = ensemble_ms(member_a, member_b)                      # float64 arrays across the link
+    # lossless single-precision transport: what a loader does once per member when the values allow it
+    ens_ms, ens_stats = ensemble_ms(ens.lossless_float32(member_a), ens.lossless_float32(member_b))
+    del member_b
     e2e_ms = ens_ms / n_mem
-    ens_stats = er['stats']
-    del member_b, members
 
     # ---- calibration objective (BASELINE.json metric, second half): one differential-evolution generation =
     # 64 candidate parameter sets x every basin, each a full spin-up + simulation + basin sum + KGE distance
@@ -535,7 +545,10 @@ def run_ours(args, rank, world_size, local_rank):
                 'ms_per_step': e2e_ms, 'steps': n_mem,
                 'mode': 'xanthos_b200.ensemble.run_ensemble: %d members per GPU back to back, forcing from pinned host '
                         'memory, outputs q + avgchflow + basin aggregates to the host, copies of neighbouring members '
-                        'overlapped with the kernels' % n_mem,
+                        'overlapped with the kernels; the forcing values are single precision and cross the link as float32 '
+                        '(ensemble.lossless_float32: verified exact per array, results bit-identical)' % n_mem,
+                'float64_transport': {'ms_per_step': ens64_ms / n_mem, 'value': world_size * cm / (ens64_ms / n_mem * 1e-3),
+                                      'h2d_bytes_per_step': int(ens64_stats['h2d_bytes'] // max(ens64_stats['members_local'], 1))},
                 'single_member': {'ms_per_step': e2e_single_ms, 'value': world_size * cm / (e2e_single_ms * 1e-3),
                                   'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': int(d2h_bytes_holder[0]),
                                   'statistic': 'median step', 'ms_each_step': [round(v, 2) for v in e2e_each],
@@ -607,6 +620,9 @@ def run_workload(args, rank, world_size, local_rank):
 
     def pinned(a):
         return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).pin_memory().numpy()
+
+    def pinned_any(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -740,9 +756,11 @@ def run_workload(args, rank, world_size, local_rank):
         pm = synthetic.pm_inputs(world, sy, ey, nlcs=NLCS, seed=1 + rank)
         ab = synthetic.abcd_inputs(world, m, seed=1 + rank, with_pet=False)
         tables = {k: v for k, v in pm.items() if k not in ens.PM_FORCING + ('lct_load', 'tairprev_load')}
-        mem_a = {k: pinned(np.nan_to_num(pm[k])) for k in ens.PM_FORCING}
-        mem_a['precip'], mem_a['tmin'] = pinned(ab['precip']), pinned(np.nan_to_num(ab['tmin']))
-        mem_b = {k: pinned(np.roll(v, 11, axis=0)) for k, v in mem_a.items()}
+        f32 = os.environ.get('XANTHOS_BENCH_F64_TRANSPORT') is None     # single-precision VALUES, float32 across the link
+        rnd = (lambda a: a.astype(np.float32)) if f32 else (lambda a: a.astype(np.float32).astype(np.float64))
+        mem_a = {k: pinned_any(rnd(np.nan_to_num(pm[k]))) for k in ens.PM_FORCING}
+        mem_a['precip'], mem_a['tmin'] = pinned_any(rnd(ab['precip'])), pinned_any(rnd(np.nan_to_num(ab['tmin'])))
+        mem_b = {k: pinned_any(np.roll(v, 11, axis=0)) for k, v in mem_a.items()}
         s = world.settings()
         um = mrtm_mod.upstream_genmatrix(mrtm_mod.upstream(world.coords, mrtm_mod.downstream(world.coords, world.flow_dir, s), s))
         nd = month_days_mod4(m, sy)
@@ -767,6 +785,7 @@ def run_workload(args, rank, world_size, local_rank):
         line = _line('cell-months/s (PM+ABCD+MRTM)', 'cell-months/s', cm / (ms * 1e-3), ms / nloc, args, world_size,
                      {'workload': name, 'ncell': ncell, 'nmonths': m, 'members': n_members, 'nlcs': NLCS,
                       'runoff_spinup': RUNOFF_SPINUP, 'routing_spinup': ROUTING_SPINUP, 'dt_s': DT, 'scaling': 'strong',
+                      'transport': 'float32 (forcing values are single precision; lossless)' if f32 else 'float64',
                       'parallelism': 'members over %d rank(s), %d on rank 0' % (world_size, nloc)},
                      {'e2e': {'value': cm / (ms * 1e-3), 'unit': 'cell-months/s', 'ms_per_step': ms / nloc,
                               'h2d_bytes_per_step': int(er['stats']['h2d_bytes'] // nloc),
@@ -1006,12 +1025,15 @@ def main():
         run_reference(args, rank, world_size)
         return
     if world_size > 1:
-        # stdout carries ONE JSON line; NCCL's log (version banner, rank / ring summary at NCCL_DEBUG=INFO) is kept
-        # but sent to stderr instead of stdout, where NCCL prints it by default
+        # stdout carries ONE JSON line.  NCCL prints its version banner / INFO log on the process's stdout: file
+        # descriptor 1 is pointed at stderr for the whole run (the log is kept, e.g. for NCCL_DEBUG=INFO rank checks)
+        # and the JSON line goes out through a duplicate of the original stdout.
         if 'XANTHOS_NCCL_DEBUG' in os.environ:
             os.environ['NCCL_DEBUG'] = os.environ['XANTHOS_NCCL_DEBUG']
-        if os.environ.get('NCCL_DEBUG') and 'NCCL_DEBUG_FILE' not in os.environ:
-            os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'
+        sys.stdout.flush()
+        real_stdout = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+        sys.stdout = real_stdout
         _bind_to_gpu_numa_node(local_rank)
         import torch
         import torch.distributed as dist

@@ -48,6 +48,11 @@ int xan_device_info(int *sm_count, int *cc_major, int *cc_minor);
  * does for the PM forcings, Thornthwaite tas and ABCD tmin (data_load.py:120-125, 138, 194). */
 int xan_to_month_major(const double *d_src, double *d_dst, int ncell, int nmonths, int ld,
                        int nan_to_num, void *stream);
+/* the same from a single-precision source: forcing whose values are single precision (NetCDF float variables of
+ * the ESMs, widened to float64 by the loader) can cross the host-device link at half the bytes; float -> double
+ * is exact, so the month-major field is bit-identical to the one made from the float64 array */
+int xan_to_month_major_f32(const float *d_src, double *d_dst, int ncell, int nmonths, int ld,
+                           int nan_to_num, void *stream);
 int xan_to_cell_major(const double *d_src, double *d_dst, int ncell, int nmonths, int ld,
                       void *stream);
 

@@ -323,6 +323,15 @@ def test_ensemble_runner_equals_the_plugin_calls_member_by_member():
                              nd, 10800, m, 6)
     res = ens.run_ensemble(st, members, output_vars=('pet', 'q', 'avgchflow', 'chstorage'))
     assert res['basin_aggregates'].shape == (3, 2, m, w.n_basins) and res['stats']['members_local'] == 3
+    # single-precision forcing values cross the link as float32 and give bit-identical results (ensemble.lossless_float32)
+    m32 = {k: v.astype(np.float32).astype(np.float64) for k, v in members[1].items()}
+    m32['tmin'] = members[1]['tmin']                                           # not representable: stays float64
+    packed = ens.lossless_float32(m32)
+    assert packed['precip'].dtype == np.float32 and packed['tmin'].dtype == np.float64
+    r64 = ens.run_ensemble(st, [m32], output_vars=('q', 'avgchflow'))
+    r32 = ens.run_ensemble(st, [packed], output_vars=('q', 'avgchflow'))
+    assert bitwise_equal(r32[0]['q'], r64[0]['q']) and bitwise_equal(r32[0]['avgchflow'], r64[0]['avgchflow'])
+    assert r32['stats']['h2d_bytes'] < 0.6 * r64['stats']['h2d_bytes']
     for k, (pm, ab) in enumerate(pms):
         data = SimpleNamespace(**{**pm0, **{key: members[k][key] for key in ens.PM_FORCING}})   # statics of member 0
         pet = pm_mod.run_pmpet(data, w.ncell, 8, sy, ey, pm0['water_idx'], pm0['snow_idx'], pm0['lc_years'])

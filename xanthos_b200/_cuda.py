@@ -44,6 +44,7 @@ SIGNATURES = {
     'xan_last_error': (c_char_p, []),
     'xan_device_info': (c_int, [POINTER(c_int)] * 3),
     'xan_to_month_major': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    'xan_to_month_major_f32': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     'xan_to_cell_major': (c_int, [_P, _P, c_int, c_int, c_int, _P]),
     'xan_hs_pet': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     'xan_thornthwaite_pet': (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
@@ -87,7 +88,7 @@ _lib = None
 
 # kernels launched by each entry point (the claim behind bench.py's "gpu_launches")
 KERNELS_PER_CALL = {
-    'xan_to_month_major': 1, 'xan_to_cell_major': 1, 'xan_hs_pet': 2, 'xan_thornthwaite_pet': 2,
+    'xan_to_month_major': 1, 'xan_to_month_major_f32': 1, 'xan_to_cell_major': 1, 'xan_hs_pet': 2, 'xan_thornthwaite_pet': 2,
     'xan_thornthwaite_daylight': 1, 'xan_pm_pet': 1, 'xan_abcd_run': 3, 'xan_abcd_kge_batch': 1,
     'xan_mrtm_route': 1, 'xan_mrtm_route_batch': 1, 'xan_hargreaves_pet': 1, 'xan_gwam_run': 1, 'xan_agg_to_year': 1, 'xan_basin_sum': 1,
     'xan_drought_stats': 1, 'xan_drought_thresholds': 1, 'xan_group_sum': 1, 'xan_year_sum_scaled': 1,

@@ -62,6 +62,11 @@ __device__ __forceinline__ double ldg_stream(const double *p) {
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ float ldg_stream(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 // Streaming store (evict-first): outputs are written once and not re-read by the same kernel.
 __device__ __forceinline__ void stg_stream(double *p, double v) {
     asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");

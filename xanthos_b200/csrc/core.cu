@@ -44,9 +44,9 @@ cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t s) {
 constexpr int TILE = 32;
 constexpr int TROWS = 8;
 
-template <bool NAN_TO_NUM>
+template <bool NAN_TO_NUM, typename SRC = double>
 __global__ void __launch_bounds__(TILE *TROWS)
-    to_month_major_kernel(const double *__restrict__ src, double *__restrict__ dst, int ncell,
+    to_month_major_kernel(const SRC *__restrict__ src, double *__restrict__ dst, int ncell,
                           int nmonths, int ld) {
     __shared__ double tile[TILE][TILE + 1];
     const int c0 = blockIdx.x * TILE;  // cell tile
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(TILE *TROWS)
     for (int r = threadIdx.y; r < TILE; r += TROWS) {
         const int c = c0 + r, m = m0 + threadIdx.x;
         if (c < ncell && m < nmonths) {
-            double v = ldg_stream(src + (size_t)c * nmonths + m);
+            double v = (double)ldg_stream(src + (size_t)c * nmonths + m);   // float -> double is exact
             if (NAN_TO_NUM) v = nan_to_num(v);
             tile[r][threadIdx.x] = v;
         }
@@ -138,6 +138,21 @@ int xan_to_month_major(const double *d_src, double *d_dst, int ncell, int nmonth
         to_month_major_kernel<true><<<grid, block, 0, s>>>(d_src, d_dst, ncell, nmonths, ld);
     else
         to_month_major_kernel<false><<<grid, block, 0, s>>>(d_src, d_dst, ncell, nmonths, ld);
+    XAN_CUDA_CHECK(cudaGetLastError());
+    return XAN_OK;
+}
+
+int xan_to_month_major_f32(const float *d_src, double *d_dst, int ncell, int nmonths, int ld, int nan_to_num_flag,
+                           void *stream) {
+    XAN_REQUIRE(d_src && d_dst, "xan_to_month_major_f32: null pointer");
+    XAN_REQUIRE(ncell > 0 && nmonths > 0 && ld >= ncell, "xan_to_month_major_f32: bad shape %d x %d (ld %d)", ncell,
+                nmonths, ld);
+    dim3 grid(ceil_div(ncell, TILE), ceil_div(nmonths, TILE)), block(TILE, TROWS);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nan_to_num_flag)
+        to_month_major_kernel<true, float><<<grid, block, 0, s>>>(d_src, d_dst, ncell, nmonths, ld);
+    else
+        to_month_major_kernel<false, float><<<grid, block, 0, s>>>(d_src, d_dst, ncell, nmonths, ld);
     XAN_CUDA_CHECK(cudaGetLastError());
     return XAN_OK;
 }

@@ -31,6 +31,30 @@ FORCING = PM_FORCING + ('precip', 'tmin')
 OUTPUTS = ('pet', 'aet', 'q', 'soilmoisture', 'chstorage', 'avgchflow')
 
 
+def lossless_float32(member, pin=True):
+    """
+    Returns the member with every forcing array whose values are all exactly representable in single precision replaced
+    by a float32 copy (pinned when a device is present); the others are kept.  Climate-model forcing is single precision
+    on disk (NetCDF float variables) and only widened to float64 by the loader (data_load.py:288-340), so the copy is
+    lossless: float -> double on the device is exact and every result stays bit-identical, while the host -> device
+    traffic - the limiter of multi-GPU ensemble runs - halves.  NaN (missing data) counts as representable.
+    Call it once per member where the data are loaded; it costs a pass over the arrays on the host.
+    """
+    out = dict(member)
+    for k in FORCING:
+        a = np.asarray(member[k])
+        if a.dtype != np.float64:
+            continue
+        a32 = a.astype(np.float32)
+        back = a32.astype(np.float64)
+        if np.array_equal(back, a, equal_nan=True):
+            if pin and C.device_available():
+                t = C.torch_cuda().from_numpy(a32).pin_memory()
+                a32 = t.numpy()
+            out[k] = a32
+    return out
+
+
 class EnsembleStatics:
     """Everything that does not change from member to member, staged on the device once."""
 
@@ -102,13 +126,15 @@ class EnsembleRunner:
                         k, tuple(a.shape), (self.s.ncell, self.s.nmonths)))
                 if not isinstance(a, torch.Tensor):
                     a = np.asarray(a)
-                    if a.dtype != np.float64 or not a.flags['C_CONTIGUOUS']:
+                    if a.dtype not in (np.float64, np.float32) or not a.flags['C_CONTIGUOUS']:
                         a = np.ascontiguousarray(a, dtype=np.float64)
                     a = torch.from_numpy(a)
-                t = a.to(device='cuda', dtype=torch.float64, non_blocking=True)
+                if a.dtype not in (torch.float64, torch.float32):
+                    a = a.to(torch.float64)
+                t = a.to(device='cuda', non_blocking=True)     # float32 arrays cross the link as float32 (see lossless_float32)
                 t.record_stream(compute)
                 staged[k] = t
-                self.h2d_bytes += t.numel() * 8
+                self.h2d_bytes += t.numel() * t.element_size()
             ev = torch.cuda.Event(enable_timing=self.timeline is not None)
             ev.record(self.h2d)
             if self.timeline is not None:
@@ -120,7 +146,8 @@ class EnsembleRunner:
         fields = {}
         for k, t in staged.items():
             f = C.Field.empty(self.s.ncell, self.s.nmonths, self.s.ld)
-            C.check(C.lib().xan_to_month_major(C.ptr(t), C.ptr(f.t), self.s.ncell, self.s.nmonths, f.ld, 0, C.stream_ptr()))
+            fn = C.lib().xan_to_month_major_f32 if t.dtype == self._torch.float32 else C.lib().xan_to_month_major
+            C.check(fn(C.ptr(t), C.ptr(f.t), self.s.ncell, self.s.nmonths, f.ld, 0, C.stream_ptr()))
             fields[k] = f
         return fields
 
