@@ -511,28 +511,63 @@ def run_ours(args, rank, world_size, local_rank):
     for v in per_kernel.values():
         v['gbs'] = v['alg_bytes'] / (v['ms'] * 1e-3) / 1e9
         v['frac_hbm'] = v['gbs'] / peaks['hbm_gbs']
-    # DRAM traffic per launch from the committed ncu --set full capture of the same workload (profiles/)
-    traffic = {}
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'r01c_traffic.json')) as f:
-            tk = json.load(f)['kernels']
-        if (ncell, nmonths) == (NCELL, NMONTHS):
-            traffic = {'pm_pet_kernel': tk['pm_pet_fast_kernel']['dram_bytes_per_launch'],
-                       'abcd_spinup+reinit+sim': tk['abcd_spinup_kernel<1>']['dram_bytes_per_launch']
-                       + tk['abcd_sim_kernel<1>']['dram_bytes_per_launch'],
-                       'mrtm_warp_kernel': tk['mrtm_warp_kernel<1, 640>']['dram_bytes_per_launch']}
-    except Exception:
-        traffic = {}
+    # DRAM traffic per launch and pipe utilisation from the committed ncu --set full capture of the same workload
+    # (profiles/r02_kernels.json, written by tools/ncu_summary.py from the .ncu-rep of this round)
+    traffic, ncu_k, ncu_src = {}, {}, None
+    for fname in ('r02_kernels.json', 'r01c_traffic.json'):
+        try:
+            with open(os.path.join(ROOT, 'profiles', fname)) as f:
+                tk = json.load(f)['kernels']
+            find = lambda prefix: next((v for k, v in tk.items() if k.startswith(prefix)), None)       # noqa: E731
+            pmk, spk, smk, mrk = find('pm_pet_fast_kernel'), find('abcd_spinup_kernel'), find('abcd_sim_kernel'), find('mrtm_warp_kernel')
+            if not (pmk and spk and smk and mrk):
+                continue
+            ncu_k = {'pm_pet_kernel': pmk, 'abcd_spinup+reinit+sim': smk, 'mrtm_warp_kernel': mrk}
+            if (ncell, nmonths) == (NCELL, NMONTHS):
+                traffic = {'pm_pet_kernel': pmk['dram_bytes_per_launch'],
+                           'abcd_spinup+reinit+sim': spk['dram_bytes_per_launch'] + smk['dram_bytes_per_launch'],
+                           'mrtm_warp_kernel': mrk['dram_bytes_per_launch']}
+            ncu_src = 'profiles/' + fname
+            break
+        except Exception:
+            continue
     dom = max(per_kernel, key=lambda k: per_kernel[k]['ms'])
+    # The dominant kernel is not bandwidth-bound: 2 x sum(nt) strictly sequential sub-steps, each a dependent chain
+    # (S -> F -> exchange -> row sum -> S).  Its floor is sub-steps x the chain of an ISOLATED warp, measured by
+    # tools/microbench (profiles/r02_fp64_peak.json: mrtm_chain_cycles for row lengths 1..9).
+    latency_model, fp64_peaks = None, None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r02_fp64_peak.json')) as f:
+            mb = json.load(f)
+        nsub = int(sum(int(d) * 24 * 3600 // DT for d in ndays[:spin_rt])) + int(sum(int(d) * 24 * 3600 // DT for d in ndays))
+        chain = mb['mrtm_chain_cycles_nt1_9'][3]          # rows are padded to the longest row of a warp: 4 - 6 terms
+        mhz = clocks['sm_mhz'] or mb['sm_mhz']
+        floor_ms = nsub * chain / (mhz * 1e3)
+        latency_model = {'sub_steps': nsub, 'chain_cycles_isolated_warp_nt4': chain, 'sm_mhz': mhz, 'floor_ms': floor_ms,
+                         'measured_ms': per_kernel['mrtm_warp_kernel']['ms'],
+                         'frac_of_floor': floor_ms / per_kernel['mrtm_warp_kernel']['ms'],
+                         'us_per_sub_step': per_kernel['mrtm_warp_kernel']['ms'] * 1e3 / nsub,
+                         'source': 'profiles/r02_fp64_peak.json (tools/microbench/fp64_peak.cu)',
+                         'note': 'the floor ignores that 20 warps share the issue ports and the shuffle pipe of an SM and '
+                                 'that a clamped flow repeats the balance (DESIGN.md section 4)'}
+        fp64_peaks = {'dfma_tflops': mb['dfma_tflops'], 'dmul_dadd_tflops': mb['dmul_dadd_tflops'],
+                      'source': 'profiles/r02_fp64_peak.json'}
+    except Exception:
+        pass
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': per_kernel[dom]['gbs'], 'peak': peaks['hbm_gbs'],
                 'unit': 'GB/s', 'frac': per_kernel[dom]['frac_hbm'], 'traffic': traffic.get(dom),
-                'traffic_source': 'profiles/r01c_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)',
+                'traffic_source': '%s (ncu dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)' % ncu_src,
                 'algorithmic_bytes': per_kernel[dom]['alg_bytes'], 'peak_source': peak_src,
                 'share_of_step': per_kernel[dom]['ms'] / sum(v['ms'] for v in per_kernel.values()),
+                'limiter': 'latency of the sequential sub-step recurrence and issue slots - NOT HBM; "bound": "hbm" only '
+                           'names the peak the contract asks to report against',
+                'latency_model': latency_model, 'fp64_peaks': fp64_peaks,
                 'note': 'dominant kernel is bound by the latency of its sequential sub-step recurrence and by issue slots, not by HBM; see DESIGN.md',
                 'kernels': {k: {'ms': round(v['ms'], 4), 'achieved_gbs': round(v['gbs'], 2),
                                 'frac_hbm': round(v['frac_hbm'], 5), 'algorithmic_bytes': v['alg_bytes'],
-                                'traffic': traffic.get(k)} for k, v in per_kernel.items()}}
+                                'traffic': traffic.get(k),
+                                'fp64_pipe_busy_pct': (ncu_k.get(k) or {}).get('fp64_pipe_pct'),
+                                'issue_active_pct': (ncu_k.get(k) or {}).get('issue_pct')} for k, v in per_kernel.items()}}
     line = {
         'metric': 'cell-months/s (PM+ABCD+MRTM)', 'value': value, 'unit': 'cell-months/s', 'n_gpus': world_size,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,

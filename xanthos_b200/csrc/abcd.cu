@@ -9,6 +9,8 @@
 //   3. abcd_sim_kernel      - thread per cell, state in registers, streams AET / Q / SW out.
 #include "common.cuh"
 
+#include <type_traits>
+
 #include <cstring>
 #include <vector>
 #include <algorithm>
@@ -57,6 +59,17 @@ __device__ __forceinline__ double div_const(double n, double d, double inv, bool
     const double r = fma(-q0, d, n);
     return fma(r, inv, q0);
 }
+// FAST: the caller has established that the divisor is covered (par.exact_ok): no test, and above all no copy of the
+// ~30-instruction division inlined at every call site of the month step.
+template <bool FAST>
+__device__ __forceinline__ double div_par(double n, double d, double inv, bool ok) {
+    if (FAST) {
+        const double q0 = n * inv;
+        const double r = fma(-q0, d, n);
+        return fma(r, inv, q0);
+    }
+    return div_const(n, d, inv, ok);
+}
 
 __device__ __forceinline__ AbcdPar load_par(const double *__restrict__ pars, int row, bool snow) {
     AbcdPar q;
@@ -83,8 +96,10 @@ __device__ __forceinline__ double np_minimum(double a, double b) {
     return (isnan(a) || isnan(b)) ? (a + b) : (a <= b ? a : b);
 }
 
-// One month of ABCD.abcd_dist (abcd.py:171-228) for one cell.
-template <bool SNOW>
+// One month of ABCD.abcd_dist (abcd.py:171-228) for one cell.  `snowpack` must start at 0 (SN0, abcd.py:79).
+// Straight-line code: the rain / snow partition (set_rain_and_snow, :140-169) and the melt (:183-192) are selects, not
+// branches - as `if / else if` they were 13 % of the executed instructions (BSSY / BRA / BSYNC) of the passes.
+template <bool SNOW, bool FASTDIV = false>
 __device__ __forceinline__ void abcd_step(bool first, double p, double e, double t, const AbcdPar &par,
                                           double &snowpack, double &sw, double &g, double &aet_out,
                                           double &q_out) {
@@ -92,29 +107,24 @@ __device__ __forceinline__ void abcd_step(bool first, double p, double e, double
     if (SNOW) {
         const bool allrain = t > TRAIN;
         const bool mixed = (t <= TRAIN) && (t >= TSNOW);
-        const bool allsnow = t < TSNOW;
-        double snow = 0.0;                                                    // :141-169
-        rain = 0.0;
-        if (mixed) {
-            snow = div_const(p * (TRAIN - t), TSPAN_C, INV_TSPAN, true);
-            rain = p - snow;
-        } else if (allrain) {
-            rain = p;
-        } else if (allsnow) {
-            snow = p;
-        }
-        snowpack = (first ? 0.0 : snowpack) + snow;                           // :178-181
-        if (allrain) snm = snowpack * par.m;                                  // :189-192
-        else if (mixed) snm = (snowpack * par.m) * div_const(TRAIN - t, TSPAN_C, INV_TSPAN, true);
-        snowpack = snowpack - snm;                                            // :195
+        const bool allsnow = t < TSNOW;                                        // a NaN temperature is none of the three
+        const double dtr = TRAIN - t;
+        const double frac = div_const(dtr, TSPAN_C, INV_TSPAN, true);
+        const double snow_mixed = div_const(p * dtr, TSPAN_C, INV_TSPAN, true);   // :154
+        const double snow = mixed ? snow_mixed : (allsnow ? p : 0.0);
+        rain = mixed ? (p - snow_mixed) : (allrain ? p : 0.0);                 // :156-166
+        snowpack = snowpack + snow;                                            // :178-181 (SN0 = 0)
+        const double sm = snowpack * par.m;
+        snm = allrain ? sm : (mixed ? sm * frac : 0.0);                        // :189-192
+        snowpack = snowpack - snm;                                             // :195
     }
-    const double w = first ? (rain + sw) : (rain + sw + snm);                 // :198-201
-    const double x = div_const(w + par.b, par.a2, par.inv_a2, par.exact_ok);  // :204-205
+    const double w = (rain + sw) + (first ? 0.0 : snm);                        // :198-201 (x + 0.0 == x here)
+    const double x = div_par<FASTDIV>(w + par.b, par.a2, par.inv_a2, par.exact_ok);  // :204-205
     const double y = x - sqrt(x * x - (w * par.b_over_a));                    // :206
-    const double swt = y * exp(div_const(-e, par.b, par.inv_b, par.exact_ok));   // :209
+    const double swt = y * exp(div_par<FASTDIV>(-e, par.b, par.inv_b, par.exact_ok));   // :209
     const double awet = w - y;                                                // :212
     const double c_awet = par.c * awet;                                       // :213
-    g = div_const(g + c_awet, par.d1, par.inv_d1, par.exact_ok);              // :216-219
+    g = div_par<FASTDIV>(g + c_awet, par.d1, par.inv_d1, par.exact_ok);       // :216-219
     double aet = y - swt;                                                     // :222
     aet = np_maximum(0.0, aet);                                               // :223
     aet = np_minimum(e, aet);                                                 // :224
@@ -123,10 +133,69 @@ __device__ __forceinline__ void abcd_step(bool first, double p, double e, double
     aet_out = aet;
 }
 
-constexpr int ABCD_U = 4;   // months of forcing in flight per thread (software prefetch)
+// Forcing of one cell, months 0 .. n-1, through `body(month, p, e, t)`.
+// Every thread owns a column of a small ring in shared memory: ABCD_STAGES stages of ABCD_SM months x 3 fields,
+// filled with 8-byte cp.async (a warp's 32 copies are one 256-byte segment of a month row) ABCD_STAGES - 1 stages
+// ahead of the stage being stepped through.  The data never pass through registers before they are needed, so the
+// month loop is ROLLED: the month step exists once per stage position instead of once per prefetched month - with the
+// register double buffer of 2 x 6 months the kernel was 63 KB of code and stalled on instruction fetch for a quarter of
+// its issue slots (ncu: no_instruction 0.95 per issued instruction).  No block-level synchronisation: a thread reads
+// only what it copied itself.
+constexpr int ABCD_SM = 4;        // months per stage
+constexpr int ABCD_STAGES = 4;    // stages in the ring: 3 x 4 months x 3 fields x 8 B = 288 B in flight per thread
+constexpr int ABCD_BLOCK = 128;
 
 template <bool SNOW>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void abcd_stage_load(double *ring, const double *__restrict__ pet,
+                                                const double *__restrict__ precip, const double *__restrict__ tmin,
+                                                int c, int ld, int stage, int i0, int n) {
+#pragma unroll
+    for (int u = 0; u < ABCD_SM; ++u) {
+        if (i0 + u < n) {                                  // uniform over the block
+            const size_t off = (size_t)(i0 + u) * ld + c;
+            double *dst = ring + ((size_t)(stage * ABCD_SM + u) * 3) * ABCD_BLOCK + threadIdx.x;
+            const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0), "l"(precip + off) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + ABCD_BLOCK * 8), "l"(pet + off) : "memory");
+            if (SNOW)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + 2 * ABCD_BLOCK * 8), "l"(tmin + off)
+                             : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <bool SNOW, typename Body>
+__device__ __forceinline__ void abcd_stream(const double *__restrict__ pet, const double *__restrict__ precip,
+                                            const double *__restrict__ tmin, int c, int ld, int n, Body body) {
+    extern __shared__ double abcd_ring[];   // [ABCD_STAGES][ABCD_SM][3][ABCD_BLOCK]
+#pragma unroll
+    for (int st = 0; st < ABCD_STAGES - 1; ++st) abcd_stage_load<SNOW>(abcd_ring, pet, precip, tmin, c, ld, st, st * ABCD_SM, n);
+    int stage = 0;
+#pragma unroll 1
+    for (int i = 0; i < n; i += ABCD_SM) {
+        // the stage ABCD_STAGES - 1 ahead goes into the slot that was consumed in the previous iteration
+        abcd_stage_load<SNOW>(abcd_ring, pet, precip, tmin, c, ld, (stage + ABCD_STAGES - 1) % ABCD_STAGES,
+                              i + (ABCD_STAGES - 1) * ABCD_SM, n);
+        asm volatile("cp.async.wait_group %0;" ::"n"(ABCD_STAGES - 1) : "memory");   // this stage has landed
+        const double *col = abcd_ring + ((size_t)stage * ABCD_SM * 3) * ABCD_BLOCK + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < ABCD_SM; ++u) {
+            if (i + u < n) {
+                const double p = col[(u * 3 + 0) * ABCD_BLOCK], e = col[(u * 3 + 1) * ABCD_BLOCK];
+                const double t = SNOW ? col[(u * 3 + 2) * ABCD_BLOCK] : 0.0;
+                body(i + u, p, e, t);
+            }
+        }
+        stage = (stage + 1) % ABCD_STAGES;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+constexpr size_t ABCD_RING_BYTES = sizeof(double) * ABCD_STAGES * ABCD_SM * 3 * ABCD_BLOCK;   // 48 KB per block
+
+// 4 blocks of 128 threads per SM (<= 128 registers): 67,420 cells are 527 blocks = 3.6 per SM, one wave
+template <bool SNOW>
+__global__ void __launch_bounds__(128, 4)
     abcd_spinup_kernel(const double *__restrict__ pet, const double *__restrict__ precip,
                        const double *__restrict__ tmin, const int *__restrict__ basin_idx,
                        const double *__restrict__ pars, int ncell, int spinup, int ld,
@@ -138,34 +207,17 @@ __global__ void __launch_bounds__(128)
     const AbcdPar par = load_par(pars, row, SNOW);
     double snowpack = 0.0, sw = SW_INIT, g = GW_INIT;
     const int s1 = spinup - 25, s2 = spinup - 13, s3 = spinup - 1;   // Decembers -25, -13, -1 (:255)
-    int i = 0;
-    for (; i + ABCD_U <= spinup; i += ABCD_U) {
-        double p[ABCD_U], e[ABCD_U], t[ABCD_U];
-#pragma unroll
-        for (int u = 0; u < ABCD_U; ++u) {
-            const size_t off = (size_t)(i + u) * ld + c;
-            p[u] = ldg_stream(precip + off);
-            e[u] = ldg_stream(pet + off);
-            t[u] = SNOW ? ldg_stream(tmin + off) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < ABCD_U; ++u) {
+    auto run = [&](auto fast) {
+        abcd_stream<SNOW>(pet, precip, tmin, c, ld, spinup, [&](int k, double p, double e, double t) {
             double aet, q;
-            abcd_step<SNOW>(i + u == 0, p[u], e[u], t[u], par, snowpack, sw, g, aet, q);
-            const int k = i + u;
+            abcd_step<SNOW, decltype(fast)::value>(k == 0, p, e, t, par, snowpack, sw, g, aet, q);
             if (k == s1) { snap[2 * (size_t)ncell + c] = sw; snap[5 * (size_t)ncell + c] = g; }
             if (k == s2) { snap[1 * (size_t)ncell + c] = sw; snap[4 * (size_t)ncell + c] = g; }
             if (k == s3) { snap[0 * (size_t)ncell + c] = sw; snap[3 * (size_t)ncell + c] = g; }
-        }
-    }
-    for (; i < spinup; ++i) {
-        const size_t off = (size_t)i * ld + c;
-        double aet, q;
-        abcd_step<SNOW>(i == 0, precip[off], pet[off], SNOW ? tmin[off] : 0.0, par, snowpack, sw, g, aet, q);
-        if (i == s1) { snap[2 * (size_t)ncell + c] = sw; snap[5 * (size_t)ncell + c] = g; }
-        if (i == s2) { snap[1 * (size_t)ncell + c] = sw; snap[4 * (size_t)ncell + c] = g; }
-        if (i == s3) { snap[0 * (size_t)ncell + c] = sw; snap[3 * (size_t)ncell + c] = g; }
-    }
+        });
+    };
+    if (par.exact_ok) run(std::true_type{});      // practically always: no divisor with an all-ones significand
+    else run(std::false_type{});
 }
 
 // Deterministic block reduction of (sum, count) pairs; result valid in thread 0.
@@ -226,7 +278,7 @@ __global__ void __launch_bounds__(256)
 }
 
 template <bool SNOW>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
     abcd_sim_kernel(const double *__restrict__ pet, const double *__restrict__ precip,
                     const double *__restrict__ tmin, const int *__restrict__ basin_idx,
                     const double *__restrict__ pars, const double *__restrict__ init, int ncell, int nmonths,
@@ -247,34 +299,18 @@ __global__ void __launch_bounds__(128)
     }
     const AbcdPar par = load_par(pars, row, SNOW);
     double snowpack = 0.0, sw = init[2 * row], g = init[2 * row + 1];
-    int i = 0;
-    for (; i + ABCD_U <= nmonths; i += ABCD_U) {
-        double p[ABCD_U], e[ABCD_U], t[ABCD_U];
-#pragma unroll
-        for (int u = 0; u < ABCD_U; ++u) {
-            const size_t off = (size_t)(i + u) * ld + c;
-            p[u] = ldg_stream(precip + off);
-            e[u] = ldg_stream(pet + off);
-            t[u] = SNOW ? ldg_stream(tmin + off) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < ABCD_U; ++u) {
+    auto run = [&](auto fast) {
+        abcd_stream<SNOW>(pet, precip, tmin, c, ld, nmonths, [&](int k, double p, double e, double t) {
             double aet, q;
-            abcd_step<SNOW>(i + u == 0, p[u], e[u], t[u], par, snowpack, sw, g, aet, q);
-            const size_t off = (size_t)(i + u) * ld + c;
+            abcd_step<SNOW, decltype(fast)::value>(k == 0, p, e, t, par, snowpack, sw, g, aet, q);
+            const size_t off = (size_t)k * ld + c;
             if (aet_o) stg_stream(aet_o + off, aet);
             if (q_o) stg_stream(q_o + off, q);
             if (sav_o) stg_stream(sav_o + off, sw);
-        }
-    }
-    for (; i < nmonths; ++i) {
-        const size_t off = (size_t)i * ld + c;
-        double aet, q;
-        abcd_step<SNOW>(i == 0, precip[off], pet[off], SNOW ? tmin[off] : 0.0, par, snowpack, sw, g, aet, q);
-        if (aet_o) stg_stream(aet_o + off, aet);
-        if (q_o) stg_stream(q_o + off, q);
-        if (sav_o) stg_stream(sav_o + off, sw);
-    }
+        });
+    };
+    if (par.exact_ok) run(std::true_type{});
+    else run(std::false_type{});
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -470,6 +506,9 @@ __global__ void __launch_bounds__(128)
     }
     const int s1 = nsteps - 25, s2 = nsteps - 13, s3 = nsteps - 1;   // Decembers -25, -13, -1 (abcd.py:255)
     double *o = SIM ? out + (size_t)quad * nsteps * npad + p : out + (size_t)ch * 12 * npad + p;
+    // block-uniform choice of the division: the fast form needs every divisor of every candidate of the block covered
+    const bool fast_all = __syncthreads_and(par.exact_ok ? 1 : 0) != 0;
+    auto months = [&](auto fastc) {
     for (int i = 0; i < nsteps; ++i) {
         const size_t off = (size_t)i * ld;
         double e[KC], pr[KC], t[KC];
@@ -483,7 +522,7 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             double aet, q;
-            abcd_step<SNOW>(i == 0, pr[k], e[k], t[k], par, sn[k], sw[k], g[k], aet, q);
+            abcd_step<SNOW, decltype(fastc)::value>(i == 0, pr[k], e[k], t[k], par, sn[k], sw[k], g[k], aet, q);
             if (SIM) {
                 const double v = unit_km3 ? (q * __ldg(area + cell[k]) * 1e-6) : q;   // rsim * area * 1e-6 (:159)
                 if (k < c.n && !isnan(v)) acc += v;
@@ -511,6 +550,9 @@ __global__ void __launch_bounds__(128)
             o[(size_t)(9 + which) * npad] = ng;
         }
     }
+    };
+    if (fast_all) months(std::true_type{});
+    else months(std::false_type{});
 }
 
 // set_vals with every cell of the basin in one group (calibrate_abcd.py:143): mean over the three Decembers
@@ -694,19 +736,30 @@ int xan_abcd_run(const xan_abcd_plan *pl, const double *d_pet, const double *d_p
     double *snap = nullptr, *init = nullptr;
     XAN_CUDA_CHECK(scratch_alloc(&snap, sizeof(double) * 6 * (size_t)ncell, s));
     XAN_CUDA_CHECK(scratch_alloc(&init, sizeof(double) * 2 * (size_t)pl->n_basins, s));
-    const int grid = ceil_div(ncell, 128);
+    const int grid = ceil_div(ncell, ABCD_BLOCK);
+    {   // 4 blocks x 48 KB of ring per SM: ask for the large shared-memory carve-out (otherwise the 527 blocks of the
+        // 0.5 degree grid do not fit in one wave)
+        static bool once = false;
+        if (!once) {
+            once = true;
+            cudaFuncSetAttribute(abcd_spinup_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(abcd_spinup_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(abcd_sim_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(abcd_sim_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        }
+    }
     if (d_tmin)
-        abcd_spinup_kernel<true><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, pl->d_basin_idx, d_pars, ncell,
+        abcd_spinup_kernel<true><<<grid, ABCD_BLOCK, ABCD_RING_BYTES, s>>>(d_pet, d_precip, d_tmin, pl->d_basin_idx, d_pars, ncell,
                                                       spinup, ld, snap);
     else
-        abcd_spinup_kernel<false><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, pl->d_basin_idx, d_pars, ncell,
+        abcd_spinup_kernel<false><<<grid, ABCD_BLOCK, ABCD_RING_BYTES, s>>>(d_pet, d_precip, d_tmin, pl->d_basin_idx, d_pars, ncell,
                                                        spinup, ld, snap);
     abcd_reinit_kernel<<<pl->n_basins, 256, 0, s>>>(snap, pl->d_order, pl->d_offsets, ncell, init);
     if (d_tmin)
-        abcd_sim_kernel<true><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, pl->d_basin_idx, d_pars, init, ncell,
+        abcd_sim_kernel<true><<<grid, ABCD_BLOCK, ABCD_RING_BYTES, s>>>(d_pet, d_precip, d_tmin, pl->d_basin_idx, d_pars, init, ncell,
                                                    nmonths, ld, d_aet, d_q, d_sav);
     else
-        abcd_sim_kernel<false><<<grid, 128, 0, s>>>(d_pet, d_precip, d_tmin, pl->d_basin_idx, d_pars, init, ncell,
+        abcd_sim_kernel<false><<<grid, ABCD_BLOCK, ABCD_RING_BYTES, s>>>(d_pet, d_precip, d_tmin, pl->d_basin_idx, d_pars, init, ncell,
                                                     nmonths, ld, d_aet, d_q, d_sav);
     XAN_CUDA_CHECK(cudaGetLastError());
     XAN_CUDA_CHECK(cudaFreeAsync(snap, s));
