@@ -167,13 +167,15 @@ __device__ __forceinline__ void abcd_stage_load(double *ring, const double *__re
 
 template <bool SNOW, typename Body>
 __device__ __forceinline__ void abcd_stream(const double *__restrict__ pet, const double *__restrict__ precip,
-                                            const double *__restrict__ tmin, int c, int ld, int n, Body body) {
+                                            const double *__restrict__ tmin, int c, int ld, int n, Body body,
+                                            int begin = 0) {
     extern __shared__ double abcd_ring[];   // [ABCD_STAGES][ABCD_SM][3][ABCD_BLOCK]
 #pragma unroll
-    for (int st = 0; st < ABCD_STAGES - 1; ++st) abcd_stage_load<SNOW>(abcd_ring, pet, precip, tmin, c, ld, st, st * ABCD_SM, n);
+    for (int st = 0; st < ABCD_STAGES - 1; ++st)
+        abcd_stage_load<SNOW>(abcd_ring, pet, precip, tmin, c, ld, st, begin + st * ABCD_SM, n);
     int stage = 0;
 #pragma unroll 1
-    for (int i = 0; i < n; i += ABCD_SM) {
+    for (int i = begin; i < n; i += ABCD_SM) {
         // the stage ABCD_STAGES - 1 ahead goes into the slot that was consumed in the previous iteration
         abcd_stage_load<SNOW>(abcd_ring, pet, precip, tmin, c, ld, (stage + ABCD_STAGES - 1) % ABCD_STAGES,
                               i + (ABCD_STAGES - 1) * ABCD_SM, n);
@@ -207,14 +209,20 @@ __global__ void __launch_bounds__(128, 4)
     const AbcdPar par = load_par(pars, row, SNOW);
     double snowpack = 0.0, sw = SW_INIT, g = GW_INIT;
     const int s1 = spinup - 25, s2 = spinup - 13, s3 = spinup - 1;   // Decembers -25, -13, -1 (:255)
+    // three segments ending at the three Decembers whose state is kept: no per-month test for the snapshot months
     auto run = [&](auto fast) {
-        abcd_stream<SNOW>(pet, precip, tmin, c, ld, spinup, [&](int k, double p, double e, double t) {
-            double aet, q;
-            abcd_step<SNOW, decltype(fast)::value>(k == 0, p, e, t, par, snowpack, sw, g, aet, q);
-            if (k == s1) { snap[2 * (size_t)ncell + c] = sw; snap[5 * (size_t)ncell + c] = g; }
-            if (k == s2) { snap[1 * (size_t)ncell + c] = sw; snap[4 * (size_t)ncell + c] = g; }
-            if (k == s3) { snap[0 * (size_t)ncell + c] = sw; snap[3 * (size_t)ncell + c] = g; }
-        });
+        int begin = 0;
+#pragma unroll 1
+        for (int seg = 0; seg < 3; ++seg) {
+            const int last = seg == 0 ? s1 : (seg == 1 ? s2 : s3);
+            abcd_stream<SNOW>(pet, precip, tmin, c, ld, last + 1, [&](int k, double p, double e, double t) {
+                double aet, q;
+                abcd_step<SNOW, decltype(fast)::value>(k == 0, p, e, t, par, snowpack, sw, g, aet, q);
+            }, begin);
+            snap[(2 - seg) * (size_t)ncell + c] = sw;
+            snap[(5 - seg) * (size_t)ncell + c] = g;
+            begin = last + 1;
+        }
     };
     if (par.exact_ok) run(std::true_type{});      // practically always: no divisor with an all-ones significand
     else run(std::false_type{});

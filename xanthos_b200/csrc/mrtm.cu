@@ -1178,8 +1178,52 @@ static int launch_warp_t(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, int
     }
     if (getenv("XANTHOS_MRTM_DEBUG")) XAN_CUDA_CHECK(scratch_alloc(&a.dbg, sizeof(long long) * 6 * pl->n_warps, s));
     void *kargs[] = {(void *)&a};
+    // The cut-edge rings (n_edges x ring x ntmax x 16 B = 33 MB for the 0.5 degree world) are written once and read
+    // once, a month apart; the streaming ChStorage / Avg_ChFlow / runoff traffic of the same kernel pushed part of them
+    // out of the 126 MB L2 (ncu, round 1: 1.83 GB of DRAM traffic per launch against 0.78 GB algorithmic).  They are
+    // pinned with a persisting access-policy window for the duration of the launch (XANTHOS_MRTM_L2_PERSIST=0: off).
+    const char *epers = getenv("XANTHOS_MRTM_L2_PERSIST");
+    bool window = !(epers && atoi(epers) == 0);
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof(av));
+    if (window) {
+        static int max_persist = -1, max_window = 0;
+        static size_t persist_limit = 0;
+        if (max_persist < 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+            cudaGetLastError();
+        }
+        const size_t ring_bytes = sizeof(double2) * ring_elems;
+        // the carve-out is taken from the L2 of every other kernel (the calibration passes re-use their forcing from
+        // L2): only as much as the rings need, not the device maximum
+        const size_t want = std::min((size_t)std::max(max_persist, 0), ring_bytes + ring_bytes / 4);
+        if (want > persist_limit && max_persist > 0) {
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) persist_limit = want;
+            cudaGetLastError();
+        }
+        window = max_persist > 0 && max_window > 0 && persist_limit > 0;
+        if (window) {
+            av.accessPolicyWindow.base_ptr = ring;
+            av.accessPolicyWindow.num_bytes = std::min(ring_bytes, (size_t)max_window);
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist_limit / (double)av.accessPolicyWindow.num_bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) {
+                cudaGetLastError();
+                window = false;
+            }
+        }
+    }
     // cooperative launch = all blocks co-resident (no grid.sync is used)
     XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kernel, dim3(blocks), dim3(threads), kargs, smem, s));
+    if (window) {   // the window applies to kernels launched while it is set: switch it off again for the stream
+        av.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    }
     if (a.dbg) {
         std::vector<long long> h(6 * (size_t)pl->n_warps);
         XAN_CUDA_CHECK(cudaMemcpyAsync(h.data(), a.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, s));
