@@ -1178,12 +1178,15 @@ static int launch_warp_t(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, int
     }
     if (getenv("XANTHOS_MRTM_DEBUG")) XAN_CUDA_CHECK(scratch_alloc(&a.dbg, sizeof(long long) * 6 * pl->n_warps, s));
     void *kargs[] = {(void *)&a};
-    // The cut-edge rings (n_edges x ring x ntmax x 16 B = 33 MB for the 0.5 degree world) are written once and read
-    // once, a month apart; the streaming ChStorage / Avg_ChFlow / runoff traffic of the same kernel pushed part of them
-    // out of the 126 MB L2 (ncu, round 1: 1.83 GB of DRAM traffic per launch against 0.78 GB algorithmic).  They are
-    // pinned with a persisting access-policy window for the duration of the launch (XANTHOS_MRTM_L2_PERSIST=0: off).
+    // Optional (XANTHOS_MRTM_L2_PERSIST=1): pin the cut-edge rings (n_edges x ring x ntmax x 16 B = 33 MB for the 0.5
+    // degree world) in L2 with a persisting access-policy window.  Measured in round 2: the kernel's time does not
+    // change (44.6 ms either way - it moves 38 GB/s), and its DRAM traffic above the algorithmic 0.78 GB is not ring
+    // eviction but the 32-byte sector granularity of the 8-byte runoff reads / ChStorage and Avg_ChFlow writes, which
+    // are scattered by the depth-first cell order of the warps (reads 2.0x, writes 1.7x, proportional to the months).
+    // Setting the window on the stream around every launch also serialises the ensemble runner's copy streams
+    // (end to end 75 instead of 54 ms per member).  Hence off by default.
     const char *epers = getenv("XANTHOS_MRTM_L2_PERSIST");
-    bool window = !(epers && atoi(epers) == 0);
+    bool window = epers && atoi(epers) != 0;
     cudaStreamAttrValue av;
     memset(&av, 0, sizeof(av));
     if (window) {
