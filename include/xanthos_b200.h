@@ -198,8 +198,8 @@ int xan_mrtm_route(xan_mrtm_plan *plan, const double *d_runoff, const double *d_
 /* Ensemble variant of xan_mrtm_route: n_members independent scenarios (same topology, same static
  * fields, same calendar) in one call.  The h_* arguments are HOST arrays of n_members DEVICE
  * pointers (h_chs_prev, h_chs, h_avg, h_instream and any of their entries may be NULL).  Members are
- * advanced two at a time by every warp of the warp-dataflow kernel (independent dependency chains
- * hide the latency of the sequential sub-step recurrence; XANTHOS_MRTM_MEMBERS=1 disables it).
+ * advanced one after the other (two members per warp measured slower: 69 against 54 ms per member;
+ * XANTHOS_MRTM_MEMBERS=2 keeps that path testable).
  * Results are bit-identical to n_members calls of xan_mrtm_route. */
 int xan_mrtm_route_batch(xan_mrtm_plan *plan, int n_members, const double *const *h_runoff,
                          const double *d_flow_dist, const double *d_velocity, const double *d_area,

@@ -1145,7 +1145,12 @@ static int launch_warp_t(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, int
     double2 *ring = nullptr;
     const size_t ring_elems = (size_t)std::max(pl->n_edges, 1) * a.ring * ntmax * NM;
     XAN_CUDA_CHECK(scratch_alloc(&ring, sizeof(double2) * ring_elems, s));
-    XAN_CUDA_CHECK(cudaMemsetAsync(pl->d_progress, 0, sizeof(int) * pl->n_warps, s));
+    // hand-over counters of THIS launch (stream-ordered scratch): two routes on the same plan from different streams
+    // share no mutable device state
+    int *progress = nullptr;
+    XAN_CUDA_CHECK(scratch_alloc(&progress, sizeof(int) * pl->n_warps, s));
+    XAN_CUDA_CHECK(cudaMemsetAsync(progress, 0, sizeof(int) * pl->n_warps, s));
+    a.progress = progress;
     a.ring_buf = ring;
     a.dbg = nullptr;
     a.sched = nullptr;
@@ -1241,6 +1246,7 @@ static int launch_warp_t(xan_mrtm_plan *pl, WarpArgs &a, int ntmax, int sms, int
         XAN_CUDA_CHECK(cudaFreeAsync(a.dbg, s));
     }
     XAN_CUDA_CHECK(cudaFreeAsync(ring, s));
+    XAN_CUDA_CHECK(cudaFreeAsync(progress, s));
     return XAN_OK;
 }
 
@@ -1359,7 +1365,6 @@ int xan_mrtm_route_batch(xan_mrtm_plan *pl, int n_members, const double *const *
             a.lane_meta = pl->d_lane_meta;
             a.edge_prod = pl->d_edge_prod;
             a.edge_cons = pl->d_edge_cons;
-            a.progress = pl->d_progress;
             for (int k = 0; k < nm; ++k) {
                 a.runoff[k] = h_runoff[k0 + k];
                 a.chs_prev[k] = h_chs_prev ? h_chs_prev[k0 + k] : nullptr;

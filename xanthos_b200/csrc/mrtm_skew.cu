@@ -911,7 +911,10 @@ int route_skew(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_d
     double2 *ring = nullptr;
     XAN_CUDA_CHECK(scratch_alloc(&ring, sizeof(double2) * (size_t)std::max(sp->n_edges, 1) * RL, s));
     a.ring = ring;
-    XAN_CUDA_CHECK(cudaMemsetAsync(sp->d_progress, 0, sizeof(int) * sp->nw, s));
+    int *progress = nullptr;   // per launch: concurrent routes on one plan share no mutable device state
+    XAN_CUDA_CHECK(scratch_alloc(&progress, sizeof(int) * sp->nw, s));
+    XAN_CUDA_CHECK(cudaMemsetAsync(progress, 0, sizeof(int) * sp->nw, s));
+    a.progress = progress;
     const char *edbg = getenv("XANTHOS_MRTM_DEBUG");
     if (edbg) XAN_CUDA_CHECK(scratch_alloc(&a.dbg, sizeof(long long) * 5 * sp->nw, s));
     int rc = XAN_E_INVALID;
@@ -936,6 +939,7 @@ int route_skew(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_d
     }
     if (a.dbg) cudaFreeAsync(a.dbg, s);
     cudaFreeAsync(ring, s);
+    cudaFreeAsync(progress, s);
     cudaFreeAsync(d_int, s);
     cudaFreeAsync(d_secs, s);
     return rc;
