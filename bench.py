@@ -511,6 +511,9 @@ def run_ours(args, rank, world_size, local_rank):
     for v in per_kernel.values():
         v['gbs'] = v['alg_bytes'] / (v['ms'] * 1e-3) / 1e9
         v['frac_hbm'] = v['gbs'] / peaks['hbm_gbs']
+    # which forest kernel XAN_MRTM_AUTO ran (csrc/mrtm.cu AUTO_DEFAULT_SKEW; XANTHOS_MRTM_AUTO=tree|skew overrides)
+    mrtm_kernel = 'mrtm_warp_kernel<1,640>' if os.environ.get('XANTHOS_MRTM_AUTO', 'skew') == 'tree' else \
+        'mrtm_skew_kernel<%s>' % os.environ.get('XANTHOS_MRTM_SKEW_K', '2')
     # DRAM traffic per launch and pipe utilisation from the committed ncu --set full capture of the same workload
     # (profiles/r02_kernels.json, written by tools/ncu_summary.py from the .ncu-rep of this round)
     traffic, ncu_k, ncu_src = {}, {}, None
@@ -519,7 +522,8 @@ def run_ours(args, rank, world_size, local_rank):
             with open(os.path.join(ROOT, 'profiles', fname)) as f:
                 tk = json.load(f)['kernels']
             find = lambda prefix: next((v for k, v in tk.items() if k.startswith(prefix)), None)       # noqa: E731
-            pmk, spk, smk, mrk = find('pm_pet_fast_kernel'), find('abcd_spinup_kernel'), find('abcd_sim_kernel'), find('mrtm_warp_kernel')
+            pmk, spk, smk = find('pm_pet_fast_kernel'), find('abcd_spinup_kernel'), find('abcd_sim_kernel')
+            mrk = find(mrtm_kernel.split('<')[0])
             if not (pmk and spk and smk and mrk):
                 continue
             ncu_k = {'pm_pet_kernel': pmk, 'abcd_spinup+reinit+sim': smk, 'mrtm_warp_kernel': mrk}
@@ -548,8 +552,8 @@ def run_ours(args, rank, world_size, local_rank):
                          'frac_of_floor': floor_ms / per_kernel['mrtm_warp_kernel']['ms'],
                          'us_per_sub_step': per_kernel['mrtm_warp_kernel']['ms'] * 1e3 / nsub,
                          'source': 'profiles/r02_fp64_peak.json (tools/microbench/fp64_peak.cu)',
-                         'note': 'the floor ignores that 20 warps share the issue ports and the shuffle pipe of an SM and '
-                                 'that a clamped flow repeats the balance (DESIGN.md section 4)'}
+                         'note': 'the floor is the dependent chain of one isolated warp of the warp-dataflow kernel (row of 4 '
+                                 'terms); the warps of an SM share its issue ports (DESIGN.md section 4)'}
         fp64_peaks = {'dfma_tflops': mb['dfma_tflops'], 'dmul_dadd_tflops': mb['dmul_dadd_tflops'],
                       'source': 'profiles/r02_fp64_peak.json'}
     except Exception:
@@ -559,6 +563,7 @@ def run_ours(args, rank, world_size, local_rank):
                 'traffic_source': '%s (ncu dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)' % ncu_src,
                 'algorithmic_bytes': per_kernel[dom]['alg_bytes'], 'peak_source': peak_src,
                 'share_of_step': per_kernel[dom]['ms'] / sum(v['ms'] for v in per_kernel.values()),
+                'mrtm_kernel': mrtm_kernel,
                 'limiter': 'latency of the sequential sub-step recurrence and issue slots - NOT HBM; "bound": "hbm" only '
                            'names the peak the contract asks to report against',
                 'latency_model': latency_model, 'fp64_peaks': fp64_peaks,

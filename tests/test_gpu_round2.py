@@ -265,7 +265,7 @@ def test_device_copies_never_go_stale():
     assert C.resident(own) is None
 
 
-@pytest.mark.parametrize("K", ['2', '4'])
+@pytest.mark.parametrize("K", ['1', '2', '4'])
 def test_skew_routing_kernel_bitwise_against_oracle(K, monkeypatch):
     """csrc/mrtm_skew.cu (method = MRTM_SKEW): small worlds at three sub-step lengths and the bench world (cut edges
     between warps, ghost / export series) equal the oracle bit for bit; also equal to the warp-dataflow kernel."""

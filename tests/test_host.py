@@ -320,7 +320,7 @@ def test_skew_plan_and_schedule_model_equal_the_oracle_bitwise(monkeypatch):
     q = synthetic.runoff_input(w, months, seed=3)
     nd = set_month_arrays(12, 1971, 1971)[:months, 2]
     oup = omrtm.upstream_fast(w.coords, omrtm.downstream(w.coords, w.flow_dir, w.nrow, w.ncol), w.nrow, w.ncol)
-    for K in ('2', '4'):
+    for K in ('1', '2', '4'):
         monkeypatch.setenv('XANTHOS_MRTM_SKEW_K', K)
         um = mrtm.upstream_genmatrix(up)
         t = skew_model.skew_tables(um)

@@ -34,7 +34,7 @@ namespace cg = cooperative_groups;
 namespace xan {
 
 constexpr int RING_DEFAULT = 4;   // months of a cut-edge series kept in flight
-constexpr bool AUTO_DEFAULT_SKEW = false;   // which forest kernel XAN_MRTM_AUTO picks (the faster one as measured)
+constexpr bool AUTO_DEFAULT_SKEW = true;    // which forest kernel XAN_MRTM_AUTO picks (the faster one as measured)
 
 // =============================================================================================
 // host: topology
@@ -1330,9 +1330,16 @@ int xan_mrtm_route_batch(xan_mrtm_plan *pl, int n_members, const double *const *
     int dev = 0, sms = 0;
     XAN_CUDA_CHECK(cudaGetDevice(&dev));
     XAN_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // month lengths on the device for the warp-dataflow / grid kernels, made on first need: the skew kernel keeps
+    // its own cached step tables (a small host -> device copy here would queue behind the forcing uploads of an
+    // ensemble run on the copy engine)
     int *d_ndays = nullptr;
-    XAN_CUDA_CHECK(scratch_alloc(&d_ndays, sizeof(int) * nmonths, s));
-    XAN_CUDA_CHECK(cudaMemcpyAsync(d_ndays, h_ndays, sizeof(int) * nmonths, cudaMemcpyHostToDevice, s));
+    auto need_ndays = [&]() -> int {
+        if (d_ndays) return XAN_OK;
+        XAN_CUDA_CHECK(scratch_alloc(&d_ndays, sizeof(int) * nmonths, s));
+        XAN_CUDA_CHECK(cudaMemcpyAsync(d_ndays, h_ndays, sizeof(int) * nmonths, cudaMemcpyHostToDevice, s));
+        return XAN_OK;
+    };
 
     const char *env_nm = getenv("XANTHOS_MRTM_MEMBERS");
     const int nm_cap = std::max(1, std::min(NM_MAX, env_nm ? atoi(env_nm) : 1));   // members per warp pass (2 measured slower: 69 vs 54 ms per member)
@@ -1354,6 +1361,10 @@ int xan_mrtm_route_batch(xan_mrtm_plan *pl, int n_members, const double *const *
             rc = r;
             k0 += 1;
             continue;
+        }
+        {
+            const int rcn = need_ndays();
+            if (rcn != XAN_OK) return rcn;
         }
         if (use_tree) {
             WarpArgs a;
@@ -1399,7 +1410,7 @@ int xan_mrtm_route_batch(xan_mrtm_plan *pl, int n_members, const double *const *
             k0 += 1;
         }
     }
-    cudaFreeAsync(d_ndays, s);
+    if (d_ndays) cudaFreeAsync(d_ndays, s);
     return rc;
 }
 

@@ -68,6 +68,12 @@ struct SkewPlan {
         *d_exp_edge = nullptr, *d_exp_place = nullptr, *d_Dw = nullptr, *d_edge_prod = nullptr, *d_edge_cons = nullptr,
         *d_progress = nullptr;
     bool on_device = false;
+    // step tables of the last calendar routed (device, kept with the plan: a per-call host -> device copy would queue
+    // behind the forcing uploads of the ensemble runner on the copy engine and hold up the kernel)
+    std::vector<int> cal_key;
+    double cal_dt = 0.0;
+    int *d_cal_int = nullptr;
+    double *d_cal_secs = nullptr;
     int nsrc() const { return 2 * SK_NB + K - 1; }
     int zero_entry() const { return K * 32 + SK_XG; }
 };
@@ -79,6 +85,8 @@ void skew_plan_destroy(SkewPlan *sp) {
         cudaFree(sp->d_ghost_lag); cudaFree(sp->d_exp_edge); cudaFree(sp->d_exp_place); cudaFree(sp->d_Dw);
         cudaFree(sp->d_edge_prod); cudaFree(sp->d_edge_cons); cudaFree(sp->d_progress);
     }
+    if (sp->d_cal_int) cudaFree(sp->d_cal_int);
+    if (sp->d_cal_secs) cudaFree(sp->d_cal_secs);
     delete sp;
 }
 
@@ -376,7 +384,7 @@ static SkewPlan *get_skew(xan_mrtm_plan *pl) {
     if (!pl->skew_tried) {
         pl->skew_tried = true;
         const char *ek = getenv("XANTHOS_MRTM_SKEW_K");
-        const int K = ek ? std::max(2, std::min(6, atoi(ek))) : 2;   // 2 measured fastest (two warps per SM sub-partition)
+        const int K = ek ? std::max(1, std::min(6, atoi(ek))) : 2;   // 2 measured fastest (two warps per SM sub-partition)
         pl->skew = build_skew(pl, K);
     }
     return pl->skew;
@@ -445,8 +453,12 @@ struct SkewLane {
     double erln[K], pend[K], qn[K], ar[K];   // lateral inflow of the next step, monthly sum waiting for its division,
                                              // prefetched runoff of the step after the next, cell area
     int cell[K], lag[K];
-    unsigned sb[2 * SK_NB];      // byte offsets (within the F half of one table parity) of the terms of the wide row
-    unsigned su[K > 1 ? K - 1 : 1];   // ... of the single tributary of the cells in slots 1 .. K-1
+    // shared-memory byte ADDRESSES in table buffer 0 (F half): the terms of the wide row, the single tributary of the cells
+    // in slots 1 .. K-1, this lane's own entry of slot 0.  A buffer offset is added at the use; with lag 1 it is a compile-
+    // time constant, so every table access is register + immediate.
+    unsigned sb[2 * SK_NB];
+    unsigned su[K > 1 ? K - 1 : 1];
+    unsigned mp;
 };
 
 // Row terms of one iteration: trial flows (x) and, when needed, final flows (y) of the tributaries.
@@ -460,16 +472,16 @@ struct SkewTerms {
 // has F' != F (a clamp, mrtm.py:54-60); otherwise the F' half is neither read nor used.
 template <int K>
 __device__ __forceinline__ void skew_load(SkewTerms<K> &R, const SkewLane<K> &L, const unsigned LDB, const unsigned FPOFF,
-                                          const bool slow) {
+                                          const bool slow) {   // LDB: byte offset of the buffer within the table
 #pragma unroll
-    for (int j = 0; j < 2 * SK_NB; ++j) R.tx[j] = sk_lds1(LDB + L.sb[j]);
+    for (int j = 0; j < 2 * SK_NB; ++j) R.tx[j] = sk_lds1(L.sb[j] + LDB);
 #pragma unroll
-    for (int s = 1; s < K; ++s) R.ux[s - 1] = sk_lds1(LDB + L.su[s - 1]);
+    for (int s = 1; s < K; ++s) R.ux[s - 1] = sk_lds1(L.su[s - 1] + LDB);
     if (slow) {
 #pragma unroll
-        for (int j = 0; j < 2 * SK_NB; ++j) R.ty[j] = sk_lds1(LDB + FPOFF + L.sb[j]);
+        for (int j = 0; j < 2 * SK_NB; ++j) R.ty[j] = sk_lds1(L.sb[j] + (LDB + FPOFF));
 #pragma unroll
-        for (int s = 1; s < K; ++s) R.uy[s - 1] = sk_lds1(LDB + FPOFF + L.su[s - 1]);
+        for (int s = 1; s < K; ++s) R.uy[s - 1] = sk_lds1(L.su[s - 1] + (LDB + FPOFF));
     }
 }
 
@@ -530,32 +542,108 @@ __device__ __forceinline__ bool skew_compute_store(SkewLane<K> &L, const SkewTer
     const bool changed = __any_sync(0xffffffffu, any_clamp || xdiff);
 #pragma unroll
     for (int s = 0; s < K; ++s) {
-        sk_sts1(WR + (unsigned)(s * 32 + lane) * 8u, F[s]);
-        sk_sts1(WR + FPOFF + (unsigned)(s * 32 + lane) * 8u, Fp[s]);
+        sk_sts1(L.mp + (WR + (unsigned)s * 256u), F[s]);               // WR: byte offset of the buffer within the table
+        sk_sts1(L.mp + (WR + FPOFF + (unsigned)s * 256u), Fp[s]);
     }
     return changed;
 }
 
-// Shared memory of one warp: flow table [SK_LAGM + 1 buffers][F half | F' half] (NE entries each), staged series of the ghost
-// entries [G][SK_W] (F, F'), export series [O][SK_CH] (F, F').
+// Lag 1, the form that measured fastest: loads, balances and stores of one iteration in one piece, the balances slot by
+// slot (42.7 ms with 2 cells per lane against 47.4 ms for the load-ahead form above, which exists for lag 2).
+// RDO / WRO: byte offsets of the table buffers read / written (compile-time constants at the call sites).
+template <int K, bool SLOW>
+__device__ __forceinline__ bool skew_iter(SkewLane<K> &L, const unsigned RDO, const unsigned WRO, const unsigned FPOFF,
+                                          const double dt, const double dtinv, const bool xdiff) {
+    double tx[2 * SK_NB], ty[2 * SK_NB], ux[K > 1 ? K - 1 : 1], uy[K > 1 ? K - 1 : 1];
+#pragma unroll
+    for (int j = 0; j < 2 * SK_NB; ++j) tx[j] = sk_lds1(L.sb[j] + RDO);
+#pragma unroll
+    for (int s = 1; s < K; ++s) ux[s - 1] = sk_lds1(L.su[s - 1] + RDO);
+    if (SLOW) {
+#pragma unroll
+        for (int j = 0; j < 2 * SK_NB; ++j) ty[j] = sk_lds1(L.sb[j] + (RDO + FPOFF));
+#pragma unroll
+        for (int s = 1; s < K; ++s) uy[s - 1] = sk_lds1(L.su[s - 1] + (RDO + FPOFF));
+    }
+    double Fo[K], Fpo[K];
+    bool any_clamp = false;
+    {   // slot 0: up to SK_NB tributaries before and SK_NB after the cell's own column (mrtm.py:51 in CSR order)
+        const double F = L.S[0] * L.ti[0];                                          // mrtm.py:50
+        double d = tx[0], d2 = SLOW ? ty[0] : 0.0;
+#pragma unroll
+        for (int j = 1; j < SK_NB; ++j) {
+            d = d + tx[j];
+            if (SLOW) d2 = d2 + ty[j];
+        }
+        d = d - F;
+        if (SLOW) d2 = d2 - F;
+#pragma unroll
+        for (int j = SK_NB; j < 2 * SK_NB; ++j) {
+            d = d + tx[j];
+            if (SLOW) d2 = d2 + ty[j];
+        }
+        d = d + L.erl[0];                                                           // balance with the trial flows
+        if (SLOW) d2 = d2 + L.erl[0];                                               // balance with the final flows, :68
+        const double ddt = d * dt;
+        const bool clamp = ddt < (-L.S[0]);                                         // :54
+        const double Sn = L.S[0] + (SLOW ? d2 * dt : ddt);                          // :69 / :76
+        const double Fc = (d + F) + L.S[0] * dtinv;                                 // :60
+        const double Fp = clamp ? Fc : F;
+        L.S[0] = clamp ? 0.0 : Sn;                                                  // :63
+        L.fav[0] = L.fav[0] + Fp;                                                   // :78
+        Fo[0] = F;
+        Fpo[0] = Fp;
+        any_clamp = clamp;
+    }
+#pragma unroll
+    for (int s = 1; s < K; ++s) {   // at most one tributary; a two-term row is order-free
+        const double F = L.S[s] * L.ti[s];
+        const double d = (ux[s - 1] - F) + L.erl[s];
+        const double ddt = d * dt;
+        const bool clamp = ddt < (-L.S[s]);
+        double Sn;
+        if (SLOW) {
+            const double d2 = (uy[s - 1] - F) + L.erl[s];
+            Sn = L.S[s] + d2 * dt;
+        } else {
+            Sn = L.S[s] + ddt;
+        }
+        const double Fc = (d + F) + L.S[s] * dtinv;
+        const double Fp = clamp ? Fc : F;
+        L.S[s] = clamp ? 0.0 : Sn;
+        L.fav[s] = L.fav[s] + Fp;
+        Fo[s] = F;
+        Fpo[s] = Fp;
+        any_clamp = any_clamp || clamp;
+    }
+    const bool changed = __any_sync(0xffffffffu, any_clamp || xdiff);   // before the stores: its latency hides behind them
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        sk_sts1(L.mp + (WRO + (unsigned)s * 256u), Fo[s]);
+        sk_sts1(L.mp + (WRO + FPOFF + (unsigned)s * 256u), Fpo[s]);
+    }
+    return changed;
+}
+
+// Shared memory of a block: per warp a fixed part - flow table [SK_LAGM + 1 buffers][F half | F' half] (NE entries each),
+// export series [O][SK_CH] (F, F'), one 16-byte dump slot per lane - followed by the staged series [SK_W] (F, F') of the
+// ghost entries of all its warps, packed (a warp has 0 .. SK_XG of them; the block's total is what is allocated).
 template <int K>
 struct SkewSmem {
     static constexpr int CAP = 32 * K, NE = CAP + SK_XG + 2;     // + all-zero entry, + 1 keeps the F' half 16-byte aligned
     static constexpr unsigned FPOFF = NE * 8u, PSTRIDE = NE * 16u;
     // ... + one 16-byte dump slot per lane (target of the import / export stores of lanes that have neither)
-    static __host__ __device__ int bytes(int G, int O) {
-        return (SK_LAGM + 1) * NE * 16 + G * SK_W * 16 + O * SK_CH * 16 + 32 * 16;
-    }
+    static __host__ __device__ int bytes_fixed(int O) { return (SK_LAGM + 1) * NE * 16 + O * SK_CH * 16 + 32 * 16; }
 };
 
 template <int K, bool LINKED>
-__device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const int lane, const unsigned EX0) {
+__device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const int lane, const unsigned EX0,
+                                         const unsigned ST0 /* staged series of this warp's ghost entries */) {
     using SM = SkewSmem<K>;
     constexpr int CAP = SM::CAP, NS = 2 * SK_NB + K - 1;
     constexpr unsigned FPOFF = SM::FPOFF, PSTRIDE = SM::PSTRIDE;
     const unsigned full = 0xffffffffu;
-    const unsigned ST0 = EX0 + (SK_LAGM + 1) * PSTRIDE;             // staged ghost series
-    const unsigned XS0 = ST0 + (unsigned)a.G * (SK_W * 16u);        // export series
+    const unsigned XS0 = EX0 + (SK_LAGM + 1) * PSTRIDE;             // export series
     const bool dbg = a.dbg != nullptr;
     const long long cyc0 = dbg ? clock64() : 0;
     long long cyc_wait = 0, cyc_evt = 0;
@@ -580,9 +668,10 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
     {
         const int *row = a.src + ((size_t)w * 32 + lane) * NS;
 #pragma unroll
-        for (int j = 0; j < 2 * SK_NB; ++j) L.sb[j] = (unsigned)row[j] * 8u;
+        for (int j = 0; j < 2 * SK_NB; ++j) L.sb[j] = EX0 + (unsigned)row[j] * 8u;
 #pragma unroll
-        for (int s = 1; s < K; ++s) L.su[s - 1] = (unsigned)row[2 * SK_NB + s - 1] * 8u;
+        for (int s = 1; s < K; ++s) L.su[s - 1] = EX0 + (unsigned)row[2 * SK_NB + s - 1] * 8u;
+        L.mp = EX0 + (unsigned)lane * 8u;
     }
     // ---- ghost imports (lanes 0 .. 15) and exports (lanes 16 .. 31) ------------------------------------------------
     const int xi = lane & 15;
@@ -591,7 +680,8 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
     if (LINKED) xedge = imp_lane ? a.ghost_edge[(size_t)w * SK_XG + xi] : a.exp_edge[(size_t)w * SK_XO + xi];
     const bool imp = imp_lane && xedge >= 0, expo = !imp_lane && xedge >= 0;
     const int glag = imp ? a.ghost_lag[(size_t)w * SK_XG + xi] : 0;
-    const unsigned eplace8 = (unsigned)(expo ? a.exp_place[(size_t)w * SK_XO + xi] : CAP + SK_XG) * 8u;
+    const unsigned eplace8 = EX0 + (unsigned)(expo ? a.exp_place[(size_t)w * SK_XO + xi] : CAP + SK_XG) * 8u;
+    const unsigned ximp0 = EX0 + (unsigned)(CAP + xi) * 8u;   // this import lane's ghost entry in buffer 0
     double2 *const xring = a.ring + (size_t)(xedge >= 0 ? xedge : 0) * RL;
     const int peer = imp ? a.edge_prod[xedge] : (expo ? a.edge_cons[xedge] : 0);
     const unsigned ghost_mask = __ballot_sync(full, imp), exp_mask = __ballot_sync(full, expo);
@@ -601,12 +691,21 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
     // second half of an (F, F') pair: 8 bytes further in a staged series, FPOFF bytes further in the flow table
     const unsigned xdelta = imp ? 8u : FPOFF;
 
+    // Hand-over test.  The counters of the peers are remembered: a producer that runs far ahead (leaves are not
+    // throttled by anything but the ring) or a consumer that is close behind satisfies many prologues with one read,
+    // and a read is an L2 round trip plus a fence.
+    int seen_p = 0, seen_c = 0;
     auto wait_peers = [&](int need_p, int need_c) {
         const int poll_p = imp ? 1 : 0, poll_c = (expo && need_c > 0) ? 1 : 0;
+        if (__all_sync(full, (!poll_p || seen_p >= need_p) && (!poll_c || seen_c >= need_c))) return;
         const int *pp = a.progress + peer;
         for (;;) {
             const int vp = sk_ld_relaxed_pred(pp, poll_p, need_p), vc = sk_ld_relaxed_pred(pp, poll_c, need_c);
-            if (__all_sync(full, vp >= need_p && vc >= need_c)) break;
+            if (__all_sync(full, vp >= need_p && vc >= need_c)) {
+                if (poll_p) seen_p = vp;
+                if (poll_c) seen_c = vc;
+                break;
+            }
             __nanosleep(a.sleep_ns);
         }
         asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire side of the hand-over
@@ -657,7 +756,7 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
     int b = 0, evt = a.step_start[0];
     double ev_nt_prev = 1.0, ev_secs_next = a.step_secs[M > 1 ? 1 : 0];
     size_t ev_next2_off = (size_t)a.step_month[M > 2 ? 2 : 0] * a.ld, ev_out_off = 0;
-    auto events = [&](const int n, const unsigned LAST) {   // LAST: table buffer written one iteration ago
+    auto events = [&](const int n, const unsigned LAST) {   // LAST: byte offset of the table buffer written one iteration ago
         const long long c0 = dbg ? clock64() : 0;
         const int k = n - evt;
         const bool st = b > 0 && b - 1 >= a.spinup;
@@ -666,7 +765,7 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
             const int c = L.cell[s];
             if (c >= 0 && L.lag[s] == k) {
                 if (st && a.chs) stg_stream(a.chs + ev_out_off + c, L.S[s]);
-                if (b == M && a.instream) a.instream[c] = sk_lds1(LAST + FPOFF + (unsigned)(s * 32 + lane) * 8u);
+                if (b == M && a.instream) a.instream[c] = sk_lds1(L.mp + (LAST + FPOFF + (unsigned)s * 256u));
                 L.pend[s] = L.fav[s];
                 L.fav[s] = 0.0;
                 L.erl[s] = L.erln[s];
@@ -699,20 +798,21 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
     // ahead in their own time) wrote two iterations ago.  The terms of iteration n + 1 come from bl (written in n - 1)
     // and are loaded while iteration n is being computed: no load, store or vote latency is on the path from one
     // iteration to the next - only the storages S in registers.
-    unsigned bw = EX0, bl = EX0 + SK_LAGM * PSTRIDE, bt = EX0 + PSTRIDE;   // written now / one / two iterations ago
+    unsigned bw = 0, bl = SK_LAGM * PSTRIDE, bt = PSTRIDE;   // lag 2 only: byte offsets of the buffers written now / one / two iterations ago
     bool ch1 = false, ch2 = false;   // some flow written one / two iterations ago has F' != F
     SkewTerms<K> TA, TB;
 #pragma unroll
     for (int j = 0; j < 2 * SK_NB; ++j) TA.tx[j] = TA.ty[j] = TB.tx[j] = TB.ty[j] = 0.0;
 #pragma unroll
     for (int s = 1; s < K; ++s) TA.ux[s - 1] = TA.uy[s - 1] = TB.ux[s - 1] = TB.uy[s - 1] = 0.0;
-    // One iteration: computes with the terms in CUR, loads the terms of the next iteration into NXT.  The import and
-    // export stores are unconditional: every lane has a destination (ghost entry halves / export series slot / dump
-    // slot) - predicated stores were turned into branches by ptxas.
-    auto iteration = [&](const int n, const SkewTerms<K> &CUR, SkewTerms<K> &NXT) {
+    // One iteration: computes with the terms in CUR, loads the terms of the next iteration into NXT; WRO is the byte
+    // offset of the buffer this iteration writes (lag 1: a compile-time constant, 0 or PSTRIDE).  The import and export
+    // stores are unconditional: every lane has a destination (ghost entry halves / export series slot / dump slot) -
+    // predicated stores were turned into branches by ptxas.
+    auto iteration = [&](const int n, const SkewTerms<K> &CUR, SkewTerms<K> &NXT, const unsigned WRO) {
         bool xdiff = false;
         if (LINKED) {   // the value was loaded at the end of the previous iteration
-            const unsigned x0 = imp_lane ? bw + (unsigned)(CAP + xi) * 8u
+            const unsigned x0 = imp_lane ? ximp0 + WRO
                                          : (expo ? xs_lane + ((unsigned)(n & (SK_CH - 1)) << 4) : dump_lane);
             sk_sts1(x0, xvx);
             sk_sts1(x0 + (imp_lane ? FPOFF : 8u), xvy);
@@ -724,12 +824,17 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
             ch0 = skew_compute_store<K>(L, CUR, bw, FPOFF, lane, dt, dtinv, ch2, xdiff);
             if (ch2) ++n_slow;
         } else {
-            ch0 = skew_compute_store<K>(L, CUR, bw, FPOFF, lane, dt, dtinv, ch1, xdiff);
-            if (ch1) ++n_slow;
-            skew_load<K>(NXT, L, bw, FPOFF, ch0);
+            const unsigned RDO = WRO ^ PSTRIDE;     // the other of the two buffers
+            if (ch1) {
+                ch0 = skew_iter<K, true>(L, RDO, WRO, FPOFF, dt, dtinv, xdiff);
+                ++n_slow;
+            } else {
+                ch0 = skew_iter<K, false>(L, RDO, WRO, FPOFF, dt, dtinv, xdiff);
+            }
         }
         if (LINKED) {   // for iteration n + 1: staged entry n + 1 - lag (lag >= 1: its chunk has landed), or the cell just stored
-            const unsigned xaddr = imp ? stg_lane + ((unsigned)((n + 1 - glag) & (SK_W - 1)) << 4) : bw + eplace8;
+            const unsigned xaddr = imp ? stg_lane + ((unsigned)((n + 1 - glag) & (SK_W - 1)) << 4)
+                                       : eplace8 + (SK_LAGM == 2 ? bw : WRO);
             xvx = sk_lds1(xaddr);
             xvy = sk_lds1(xaddr + xdelta);
         }
@@ -740,12 +845,10 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
             bt = bl;
             bl = bw;
             bw = t;
-        } else {
-            const unsigned t = bl;
-            bl = bw;
-            bw = t;
         }
     };
+    // buffer written by even / odd iterations (lag 1); lag 2 rotates three buffers at run time
+    constexpr unsigned WE = 0u, WO = PSTRIDE;
 
     const int nlast = T + Dw;
     for (int n0 = 0; n0 <= nlast; n0 += SK_CH) {
@@ -769,15 +872,15 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
             if (i < lim) {
 #pragma unroll 1
                 for (; i < lim; i += 2) {
-                    iteration(n0 + i, TA, TB);
-                    iteration(n0 + i + 1, TB, TA);
+                    iteration(n0 + i, TA, TB, WE);
+                    iteration(n0 + i + 1, TB, TA, WO);
                 }
             } else {             // a month boundary is being crossed by some cells (Dw + 1 iterations per month)
                 const int n = n0 + i;
-                if (n >= evt) events(n, bl);
-                iteration(n, TA, TB);
-                if (n + 1 >= evt) events(n + 1, bl);
-                iteration(n + 1, TB, TA);
+                if (n >= evt) events(n, SK_LAGM == 2 ? bl : WO);
+                iteration(n, TA, TB, WE);
+                if (n + 1 >= evt) events(n + 1, SK_LAGM == 2 ? bl : WE);
+                iteration(n + 1, TB, TA, WO);
                 i += 2;
             }
         }
@@ -800,19 +903,31 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
 }
 
 template <int K>
-__global__ void __launch_bounds__(256, 1) mrtm_skew_kernel(const SkewArgs a) {
+__global__ void __launch_bounds__(K == 1 ? 512 : 256, 1) mrtm_skew_kernel(const SkewArgs a) {
     extern __shared__ __align__(16) unsigned char sk_smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    __shared__ int s_ghosts[17];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int w = wib * gridDim.x + blockIdx.x;     // consecutive plan warps on different SMs
-    if (w >= a.nw) return;                          // no block-level barrier below
-    const int per_warp = SkewSmem<K>::bytes(a.G, a.O);
-    const unsigned EX0 = (unsigned)__cvta_generic_to_shared(sk_smem + (size_t)wib * per_warp);
-    for (int i = lane; i < per_warp / 16; i += 32) sk_sts(EX0 + (unsigned)i * 16u, 0.0, 0.0);
+    const bool live = w < a.nw;
+    bool has_ghost = false, linked = false;
+    if (live && lane < SK_XG) {
+        has_ghost = a.ghost_edge[(size_t)w * SK_XG + lane] >= 0;
+        linked = has_ghost || a.exp_edge[(size_t)w * SK_XO + lane] >= 0;
+    }
+    const int ng = __popc(__ballot_sync(0xffffffffu, has_ghost));
+    if (lane == 0) s_ghosts[wib] = ng;
+    __syncthreads();                                // the only block-level barrier: before the time loop
+    if (!live) return;
+    int g0 = 0;
+    for (int k = 0; k < wib; ++k) g0 += s_ghosts[k];
+    const int fixed = SkewSmem<K>::bytes_fixed(a.O);
+    const unsigned EX0 = (unsigned)__cvta_generic_to_shared(sk_smem + (size_t)wib * fixed);
+    const unsigned ST0 = (unsigned)__cvta_generic_to_shared(sk_smem + (size_t)wpb * fixed) + (unsigned)g0 * (SK_W * 16u);
+    for (int i = lane; i < fixed / 16; i += 32) sk_sts(EX0 + (unsigned)i * 16u, 0.0, 0.0);
+    for (int i = lane; i < ng * SK_W; i += 32) sk_sts(ST0 + (unsigned)i * 16u, 0.0, 0.0);
     __syncwarp();
-    bool linked = false;
-    if (lane < SK_XG) linked = a.ghost_edge[(size_t)w * SK_XG + lane] >= 0 || a.exp_edge[(size_t)w * SK_XO + lane] >= 0;
-    if (__any_sync(0xffffffffu, linked)) skew_run<K, true>(a, w, lane, EX0);
-    else skew_run<K, false>(a, w, lane, EX0);
+    if (__any_sync(0xffffffffu, linked)) skew_run<K, true>(a, w, lane, EX0, ST0);
+    else skew_run<K, false>(a, w, lane, EX0, ST0);
 }
 
 template <typename V>
@@ -826,15 +941,23 @@ static bool sk_upload(const std::vector<V> &h, V **d) {
 template <int K>
 static int launch_skew(SkewPlan *sp, SkewArgs &a, int sms, cudaStream_t s) {
     auto kernel = mrtm_skew_kernel<K>;
-    const int per_warp = SkewSmem<K>::bytes(sp->G, sp->O);
-    int wpb = std::max(4, ((ceil_div(sp->nw, sms) + 3) / 4) * 4);
-    if (wpb > 8) return XAN_E_INVALID;
-    const size_t smem = (size_t)per_warp * wpb;
-    if (smem > 200 * 1024) return XAN_E_INVALID;
-    XAN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const int fixed = SkewSmem<K>::bytes_fixed(sp->O);
+    const int blocks = std::min(sms, sp->nw);
+    const int wpb = std::max(4, ((ceil_div(sp->nw, blocks) + 3) / 4) * 4);
+    if (wpb > (K == 1 ? 16 : 8)) return XAN_E_INVALID;
+    // ghost entries of the warps of a block (warp w runs as warp w / blocks of block w % blocks)
+    int max_g = 0;
+    for (int b = 0; b < blocks; ++b) {
+        int g = 0;
+        for (int w = b; w < sp->nw; w += blocks)
+            for (int k = 0; k < SK_XG; ++k) g += sp->ghost_edge[(size_t)w * SK_XG + k] >= 0 ? 1 : 0;
+        max_g = std::max(max_g, g);
+    }
+    const size_t smem = (size_t)fixed * wpb + (size_t)max_g * SK_W * 16;
+    if (smem > 220 * 1024) return XAN_E_INVALID;
+    XAN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     int per_sm = 0;
     XAN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpb * 32, smem));
-    const int blocks = std::min(sms, sp->nw);
     if (per_sm < 1 || blocks * wpb < sp->nw) return XAN_E_INVALID;
     void *kargs[] = {(void *)&a};
     // cooperative launch = all blocks co-resident (the cut-edge pipeline needs every warp alive; no grid.sync is used)
@@ -892,22 +1015,32 @@ int route_skew(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_d
     if (RL < 256 || (RL & (RL - 1))) RL = 1024;
     a.RL = RL;
     a.sleep_ns = es ? std::max(0, atoi(es)) : 100;
-    // step tables: one allocation [start (M+1) | nt (M) | month (M)] ints + [secs (M)] doubles
-    int *d_int = nullptr;
-    double *d_secs = nullptr;
-    std::vector<int> hint;
-    hint.insert(hint.end(), start.begin(), start.end());
-    hint.insert(hint.end(), nts.begin(), nts.end());
-    hint.insert(hint.end(), month.begin(), month.end());
-    XAN_CUDA_CHECK(scratch_alloc(&d_int, sizeof(int) * hint.size(), s));
-    XAN_CUDA_CHECK(scratch_alloc(&d_secs, sizeof(double) * M, s));
-    // pageable host memory: cudaMemcpyAsync returns after the data were staged, the vectors may go out of scope
-    XAN_CUDA_CHECK(cudaMemcpyAsync(d_int, hint.data(), sizeof(int) * hint.size(), cudaMemcpyHostToDevice, s));
-    XAN_CUDA_CHECK(cudaMemcpyAsync(d_secs, secs.data(), sizeof(double) * M, cudaMemcpyHostToDevice, s));
-    a.step_start = d_int;
-    a.step_nt = d_int + (M + 1);
-    a.step_month = d_int + (M + 1) + M;
-    a.step_secs = d_secs;
+    // step tables: [start (M+1) | nt (M) | month (M)] ints + [secs (M)] doubles, cached with the plan per calendar
+    std::vector<int> key;
+    key.push_back(spinup_months);
+    key.insert(key.end(), h_ndays, h_ndays + nmonths);
+    if (key != sp->cal_key || dt != sp->cal_dt || !sp->d_cal_int) {
+        std::vector<int> hint;
+        hint.insert(hint.end(), start.begin(), start.end());
+        hint.insert(hint.end(), nts.begin(), nts.end());
+        hint.insert(hint.end(), month.begin(), month.end());
+        // a route with the previous calendar may still be running: the old tables are released in stream order
+        if (sp->d_cal_int) cudaFreeAsync(sp->d_cal_int, s);
+        if (sp->d_cal_secs) cudaFreeAsync(sp->d_cal_secs, s);
+        sp->d_cal_int = nullptr;
+        sp->d_cal_secs = nullptr;
+        XAN_CUDA_CHECK(scratch_alloc(&sp->d_cal_int, sizeof(int) * hint.size(), s));
+        XAN_CUDA_CHECK(scratch_alloc(&sp->d_cal_secs, sizeof(double) * M, s));
+        // pageable host memory: cudaMemcpyAsync returns after the data were staged, the vectors may go out of scope
+        XAN_CUDA_CHECK(cudaMemcpyAsync(sp->d_cal_int, hint.data(), sizeof(int) * hint.size(), cudaMemcpyHostToDevice, s));
+        XAN_CUDA_CHECK(cudaMemcpyAsync(sp->d_cal_secs, secs.data(), sizeof(double) * M, cudaMemcpyHostToDevice, s));
+        sp->cal_key = key;
+        sp->cal_dt = dt;
+    }
+    a.step_start = sp->d_cal_int;
+    a.step_nt = sp->d_cal_int + (M + 1);
+    a.step_month = sp->d_cal_int + (M + 1) + M;
+    a.step_secs = sp->d_cal_secs;
     double2 *ring = nullptr;
     XAN_CUDA_CHECK(scratch_alloc(&ring, sizeof(double2) * (size_t)std::max(sp->n_edges, 1) * RL, s));
     a.ring = ring;
@@ -919,6 +1052,7 @@ int route_skew(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_d
     if (edbg) XAN_CUDA_CHECK(scratch_alloc(&a.dbg, sizeof(long long) * 5 * sp->nw, s));
     int rc = XAN_E_INVALID;
     switch (sp->K) {
+        case 1: rc = launch_skew<1>(sp, a, sms, s); break;
         case 2: rc = launch_skew<2>(sp, a, sms, s); break;
         case 3: rc = launch_skew<3>(sp, a, sms, s); break;
         case 4: rc = launch_skew<4>(sp, a, sms, s); break;
@@ -940,8 +1074,6 @@ int route_skew(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_d
     if (a.dbg) cudaFreeAsync(a.dbg, s);
     cudaFreeAsync(ring, s);
     cudaFreeAsync(progress, s);
-    cudaFreeAsync(d_int, s);
-    cudaFreeAsync(d_secs, s);
     return rc;
 }
 
