@@ -1070,6 +1070,7 @@ void xan_mrtm_plan_destroy(xan_mrtm_plan *pl) {
     if (!pl) return;
     if (pl->on_device) free_device(pl);
     xan::skew_plan_destroy(pl->skew);
+    xan::skew_plan_destroy(pl->skew_multi);
     delete pl->packing;
     delete pl;
 }
@@ -1343,14 +1344,22 @@ int xan_mrtm_route_batch(xan_mrtm_plan *pl, int n_members, const double *const *
 
     const char *env_nm = getenv("XANTHOS_MRTM_MEMBERS");
     const int nm_cap = std::max(1, std::min(NM_MAX, env_nm ? atoi(env_nm) : 1));   // members per warp pass (2 measured slower: 69 vs 54 ms per member)
+    const char *env_snm = getenv("XANTHOS_MRTM_SKEW_MEMBERS");
+    int skew_nm = std::max(1, std::min(4, env_snm ? atoi(env_snm) : 2));
     int rc = XAN_OK;
     for (int k0 = 0; k0 < n_members && rc == XAN_OK;) {
         const int nm = std::min(nm_cap, n_members - k0);
         if (use_skew) {
-            const int r = xan::route_skew(pl, h_runoff[k0], d_flow_dist, d_velocity, d_area,
-                                          h_chs_prev ? h_chs_prev[k0] : nullptr, h_ndays, nmonths, spinup_months, ld, dt,
-                                          h_chs ? h_chs[k0] : nullptr, h_avg ? h_avg[k0] : nullptr,
-                                          h_instream ? h_instream[k0] : nullptr, sms, s);
+            // several members per launch: their blocks share the SMs (XANTHOS_MRTM_SKEW_MEMBERS=1: off)
+            const int nms = std::min(skew_nm, n_members - k0);
+            const int r = xan::route_skew(pl, nms, h_runoff + k0, d_flow_dist, d_velocity, d_area,
+                                          h_chs_prev ? h_chs_prev + k0 : nullptr, h_ndays, nmonths, spinup_months, ld, dt,
+                                          h_chs ? h_chs + k0 : nullptr, h_avg ? h_avg + k0 : nullptr,
+                                          h_instream ? h_instream + k0 : nullptr, sms, s);
+            if (r == XAN_E_INVALID && nms > 1) {   // that many blocks per SM do not fit / are not compiled: one fewer
+                skew_nm = nms - 1;
+                continue;
+            }
             if (r == XAN_E_INVALID) {   // plan or calendar not supported by the skew kernel
                 XAN_REQUIRE(method != XAN_MRTM_SKEW, "xan_mrtm_route: the skew kernel cannot run this plan / calendar "
                             "(row with more than 4 tributaries on one side of the diagonal, or a month shorter than "
@@ -1359,7 +1368,7 @@ int xan_mrtm_route_batch(xan_mrtm_plan *pl, int n_members, const double *const *
                 continue;
             }
             rc = r;
-            k0 += 1;
+            k0 += nms;
             continue;
         }
         {

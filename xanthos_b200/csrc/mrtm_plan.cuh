@@ -12,10 +12,12 @@ void skew_plan_destroy(SkewPlan *sp);
 }
 struct xan_mrtm_plan;
 namespace xan {
-// mrtm_skew.cu: routes one member with the skew kernel; XAN_E_INVALID (no error message set) = not applicable
-int route_skew(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_dist, const double *d_velocity,
-               const double *d_area, const double *d_chs_prev, const int *h_ndays, int nmonths, int spinup_months, int ld,
-               double dt, double *d_chs, double *d_avg, double *d_instream, int sms, cudaStream_t s);
+// mrtm_skew.cu: routes nm (1 or 2) members with one launch of the skew kernel; XAN_E_INVALID (no error message set) =
+// not applicable
+int route_skew(xan_mrtm_plan *pl, int nm, const double *const *d_runoff, const double *d_flow_dist,
+               const double *d_velocity, const double *d_area, const double *const *d_chs_prev, const int *h_ndays,
+               int nmonths, int spinup_months, int ld, double dt, double *const *d_chs, double *const *d_avg,
+               double *const *d_instream, int sms, cudaStream_t s);
 }
 
 namespace xan {
@@ -58,7 +60,7 @@ struct xan_mrtm_plan {
     SchedKey sched_key{};
     bool on_device = false;
     // ---- skew kernel (mrtm_skew.cu), built on first use ----------------------------------------
-    xan::SkewPlan *skew = nullptr;
-    bool skew_tried = false;
+    xan::SkewPlan *skew = nullptr, *skew_multi = nullptr;   // single-member launches / several members per launch
+    bool skew_tried = false, skew_multi_tried = false;
 };
 

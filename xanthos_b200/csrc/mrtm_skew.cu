@@ -380,20 +380,32 @@ static SkewPlan *build_skew(const xan_mrtm_plan *pl, int K) {
     return sp;
 }
 
-static SkewPlan *get_skew(xan_mrtm_plan *pl) {
-    if (!pl->skew_tried) {
-        pl->skew_tried = true;
-        const char *ek = getenv("XANTHOS_MRTM_SKEW_K");
-        const int K = ek ? std::max(1, std::min(6, atoi(ek))) : 2;   // 2 measured fastest (two warps per SM sub-partition)
-        pl->skew = build_skew(pl, K);
+// Two plans per flow graph, built on first use: one for launches of a single member (K = 2 cells per lane measured
+// fastest: two warps per SM sub-partition) and one for launches of several members (K = 4: fewer instructions and
+// shared-memory wavefronts per cell; the other members' warps cover the latencies).  XANTHOS_MRTM_SKEW_K / _KM override.
+static SkewPlan *get_skew(xan_mrtm_plan *pl, int nm = 1) {
+    if (nm <= 1) {
+        if (!pl->skew_tried) {
+            pl->skew_tried = true;
+            const char *ek = getenv("XANTHOS_MRTM_SKEW_K");
+            pl->skew = build_skew(pl, ek ? std::max(1, std::min(6, atoi(ek))) : 2);
+        }
+        return pl->skew;
     }
-    return pl->skew;
+    if (!pl->skew_multi_tried) {
+        pl->skew_multi_tried = true;
+        const char *ek = getenv("XANTHOS_MRTM_SKEW_KM");
+        pl->skew_multi = build_skew(pl, ek ? std::max(1, std::min(6, atoi(ek))) : 4);
+    }
+    return pl->skew_multi;
 }
 
 
 // =============================================================================================
 // device
 // =============================================================================================
+constexpr int SK_NM_MAX = 4;     // members per launch (co-resident blocks per SM)
+
 struct SkewArgs {
     const int *cell, *lag, *src, *ghost_edge, *ghost_lag, *exp_edge, *exp_place, *Dw, *edge_prod, *edge_cons;
     int *progress;               // [nw] sub-steps handed over / consumed (see the block prologue)
@@ -407,6 +419,15 @@ struct SkewArgs {
     int nw, M, T, spinup, ld, RL, G, O, sleep_ns;   // G / O: most ghost entries / exports of a warp
     double dt;
     long long *dbg;              // optional [nw][5]: cycles total, prologue wait, events, SM sub-partition, slow iterations
+    // further members of a multi-member launch (member m = blocks [m, m + 1) * blocks_per_member of the grid): the same
+    // plan, calendar and static arrays, their own series, rings and counters
+    struct Member {
+        const double *runoff, *chs_prev;
+        double *chs, *avg, *instream;
+        double2 *ring;
+        int *progress;
+    } more[SK_NM_MAX - 1];
+    int blocks_per_member;
 };
 
 __device__ __forceinline__ int sk_ld_relaxed_pred(const int *p, int pred, int dflt) {
@@ -551,7 +572,8 @@ __device__ __forceinline__ bool skew_compute_store(SkewLane<K> &L, const SkewTer
 // Lag 1, the form that measured fastest: loads, balances and stores of one iteration in one piece, the balances slot by
 // slot (42.7 ms with 2 cells per lane against 47.4 ms for the load-ahead form above, which exists for lag 2).
 // RDO / WRO: byte offsets of the table buffers read / written (compile-time constants at the call sites).
-template <int K, bool SLOW>
+// LAZY: the F' half is written only when it differs somewhere (launches of several members, see below).
+template <int K, bool SLOW, bool LAZY>
 __device__ __forceinline__ bool skew_iter(SkewLane<K> &L, const unsigned RDO, const unsigned WRO, const unsigned FPOFF,
                                           const double dt, const double dtinv, const bool xdiff) {
     double tx[2 * SK_NB], ty[2 * SK_NB], ux[K > 1 ? K - 1 : 1], uy[K > 1 ? K - 1 : 1];
@@ -618,9 +640,14 @@ __device__ __forceinline__ bool skew_iter(SkewLane<K> &L, const unsigned RDO, co
     }
     const bool changed = __any_sync(0xffffffffu, any_clamp || xdiff);   // before the stores: its latency hides behind them
 #pragma unroll
-    for (int s = 0; s < K; ++s) {
-        sk_sts1(L.mp + (WRO + (unsigned)s * 256u), Fo[s]);
-        sk_sts1(L.mp + (WRO + FPOFF + (unsigned)s * 256u), Fpo[s]);
+    for (int s = 0; s < K; ++s) sk_sts1(L.mp + (WRO + (unsigned)s * 256u), Fo[s]);
+    // LAZY: the F' half is written only when some flow of this iteration has F' != F: nobody reads it otherwise (the
+    // next iteration takes the fast path, an export lane copies F, the final instream flow is read from the F half) - a
+    // quarter of the shared-memory stores of a fast iteration.  Measured: 2 % faster with two members per launch
+    // (32.1 -> 31.5 ms per member), 3 % slower with one (the stores wait for the vote), hence the switch.
+    if (!LAZY || changed) {
+#pragma unroll
+        for (int s = 0; s < K; ++s) sk_sts1(L.mp + (WRO + FPOFF + (unsigned)s * 256u), Fpo[s]);
     }
     return changed;
 }
@@ -636,7 +663,7 @@ struct SkewSmem {
     static __host__ __device__ int bytes_fixed(int O) { return (SK_LAGM + 1) * NE * 16 + O * SK_CH * 16 + 32 * 16; }
 };
 
-template <int K, bool LINKED>
+template <int K, bool LINKED, bool LAZY>
 __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const int lane, const unsigned EX0,
                                          const unsigned ST0 /* staged series of this warp's ghost entries */) {
     using SM = SkewSmem<K>;
@@ -756,6 +783,7 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
     int b = 0, evt = a.step_start[0];
     double ev_nt_prev = 1.0, ev_secs_next = a.step_secs[M > 1 ? 1 : 0];
     size_t ev_next2_off = (size_t)a.step_month[M > 2 ? 2 : 0] * a.ld, ev_out_off = 0;
+    bool ch1 = false, ch2 = false;   // some flow written one / two iterations ago has F' != F
     auto events = [&](const int n, const unsigned LAST) {   // LAST: byte offset of the table buffer written one iteration ago
         const long long c0 = dbg ? clock64() : 0;
         const int k = n - evt;
@@ -765,7 +793,8 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
             const int c = L.cell[s];
             if (c >= 0 && L.lag[s] == k) {
                 if (st && a.chs) stg_stream(a.chs + ev_out_off + c, L.S[s]);
-                if (b == M && a.instream) a.instream[c] = sk_lds1(L.mp + (LAST + FPOFF + (unsigned)s * 256u));
+                if (b == M && a.instream)   // the final flow F' of the last sub-step (= F when that iteration was a fast one)
+                    a.instream[c] = sk_lds1(L.mp + (LAST + ((!LAZY || SK_LAGM == 2 || ch1) ? FPOFF : 0u) + (unsigned)s * 256u));
                 L.pend[s] = L.fav[s];
                 L.fav[s] = 0.0;
                 L.erl[s] = L.erln[s];
@@ -799,7 +828,6 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
     // and are loaded while iteration n is being computed: no load, store or vote latency is on the path from one
     // iteration to the next - only the storages S in registers.
     unsigned bw = 0, bl = SK_LAGM * PSTRIDE, bt = PSTRIDE;   // lag 2 only: byte offsets of the buffers written now / one / two iterations ago
-    bool ch1 = false, ch2 = false;   // some flow written one / two iterations ago has F' != F
     SkewTerms<K> TA, TB;
 #pragma unroll
     for (int j = 0; j < 2 * SK_NB; ++j) TA.tx[j] = TA.ty[j] = TB.tx[j] = TB.ty[j] = 0.0;
@@ -826,10 +854,10 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
         } else {
             const unsigned RDO = WRO ^ PSTRIDE;     // the other of the two buffers
             if (ch1) {
-                ch0 = skew_iter<K, true>(L, RDO, WRO, FPOFF, dt, dtinv, xdiff);
+                ch0 = skew_iter<K, true, LAZY>(L, RDO, WRO, FPOFF, dt, dtinv, xdiff);
                 ++n_slow;
             } else {
-                ch0 = skew_iter<K, false>(L, RDO, WRO, FPOFF, dt, dtinv, xdiff);
+                ch0 = skew_iter<K, false, LAZY>(L, RDO, WRO, FPOFF, dt, dtinv, xdiff);
             }
         }
         if (LINKED) {   // for iteration n + 1: staged entry n + 1 - lag (lag >= 1: its chunk has landed), or the cell just stored
@@ -837,6 +865,7 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
                                        : eplace8 + (SK_LAGM == 2 ? bw : WRO);
             xvx = sk_lds1(xaddr);
             xvy = sk_lds1(xaddr + xdelta);
+            if (LAZY && SK_LAGM == 1 && !imp && !ch0) xvy = xvx;   // exported cell of a fast iteration: its F' half was not written
         }
         ch2 = ch1;
         ch1 = ch0;
@@ -902,12 +931,15 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
     }
 }
 
-template <int K>
-__global__ void __launch_bounds__(K == 1 ? 512 : 256, 1) mrtm_skew_kernel(const SkewArgs a) {
+// NM = members per launch.  NM = 2: two blocks per SM (launch bound), block b serves member b / blocks_per_member: the
+// warps of the second member fill the issue slots the first one leaves idle (one or two in-order warps per SM
+// sub-partition wait 60 - 70 % of the cycles on fixed-latency dependencies).
+template <int K, bool LAZY>
+__device__ __forceinline__ void skew_block(const SkewArgs &a, const int bx, const int blocks) {
     extern __shared__ __align__(16) unsigned char sk_smem[];
     __shared__ int s_ghosts[17];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int w = wib * gridDim.x + blockIdx.x;     // consecutive plan warps on different SMs
+    const int w = wib * blocks + bx;                // consecutive plan warps on different SMs
     const bool live = w < a.nw;
     bool has_ghost = false, linked = false;
     if (live && lane < SK_XG) {
@@ -926,8 +958,28 @@ __global__ void __launch_bounds__(K == 1 ? 512 : 256, 1) mrtm_skew_kernel(const 
     for (int i = lane; i < fixed / 16; i += 32) sk_sts(EX0 + (unsigned)i * 16u, 0.0, 0.0);
     for (int i = lane; i < ng * SK_W; i += 32) sk_sts(ST0 + (unsigned)i * 16u, 0.0, 0.0);
     __syncwarp();
-    if (__any_sync(0xffffffffu, linked)) skew_run<K, true>(a, w, lane, EX0, ST0);
-    else skew_run<K, false>(a, w, lane, EX0, ST0);
+    if (__any_sync(0xffffffffu, linked)) skew_run<K, true, LAZY>(a, w, lane, EX0, ST0);
+    else skew_run<K, false, LAZY>(a, w, lane, EX0, ST0);
+}
+
+// NM = members per launch = blocks per SM (launch bound).  The warps of the other members fill the issue slots one
+// member leaves idle: one or two in-order warps per SM sub-partition wait 60 - 70 % of the cycles on fixed-latency
+// dependencies.  MAXT = threads per block the variant is compiled for.
+template <int K, int NM, int MAXT>
+__global__ void __launch_bounds__(MAXT, NM) mrtm_skew_kernel(const SkewArgs a0) {
+    if constexpr (NM == 1) {
+        skew_block<K, false>(a0, blockIdx.x, gridDim.x);
+    } else {
+        // one copy of the code for all members (two copies thrash the instruction cache: measured 6 x the requests)
+        const int bpm = a0.blocks_per_member, m = (int)blockIdx.x / bpm;
+        SkewArgs a = a0;
+        if (m > 0) {
+            const SkewArgs::Member &x = a0.more[m - 1];
+            a.runoff = x.runoff; a.chs_prev = x.chs_prev; a.chs = x.chs; a.avg = x.avg; a.instream = x.instream;
+            a.ring = x.ring; a.progress = x.progress; a.dbg = nullptr;
+        }
+        skew_block<K, true>(a, (int)blockIdx.x - m * bpm, bpm);
+    }
 }
 
 template <typename V>
@@ -938,13 +990,18 @@ static bool sk_upload(const std::vector<V> &h, V **d) {
     return true;
 }
 
-template <int K>
+static int skew_geometry(const SkewPlan *sp, int K, int sms, int *blocks, int *wpb) {
+    *blocks = std::min(sms, sp->nw);
+    *wpb = std::max(4, ((ceil_div(sp->nw, *blocks) + 3) / 4) * 4);
+    return *wpb > (K == 1 ? 16 : 8) ? XAN_E_INVALID : XAN_OK;
+}
+
+template <int K, int NM, int MAXT>
 static int launch_skew(SkewPlan *sp, SkewArgs &a, int sms, cudaStream_t s) {
-    auto kernel = mrtm_skew_kernel<K>;
+    auto kernel = mrtm_skew_kernel<K, NM, MAXT>;
     const int fixed = SkewSmem<K>::bytes_fixed(sp->O);
-    const int blocks = std::min(sms, sp->nw);
-    const int wpb = std::max(4, ((ceil_div(sp->nw, blocks) + 3) / 4) * 4);
-    if (wpb > (K == 1 ? 16 : 8)) return XAN_E_INVALID;
+    int blocks = 0, wpb = 0;
+    if (skew_geometry(sp, K, sms, &blocks, &wpb) != XAN_OK || wpb * 32 > MAXT) return XAN_E_INVALID;
     // ghost entries of the warps of a block (warp w runs as warp w / blocks of block w % blocks)
     int max_g = 0;
     for (int b = 0; b < blocks; ++b) {
@@ -958,19 +1015,47 @@ static int launch_skew(SkewPlan *sp, SkewArgs &a, int sms, cudaStream_t s) {
     XAN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     int per_sm = 0;
     XAN_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpb * 32, smem));
-    if (per_sm < 1 || blocks * wpb < sp->nw) return XAN_E_INVALID;
+    // every block of every member must be resident (the cut-edge pipeline needs every warp alive)
+    if (per_sm < 1 || blocks * wpb < sp->nw || (long long)per_sm * sms < (long long)NM * blocks) return XAN_E_INVALID;
+    a.blocks_per_member = blocks;
     void *kargs[] = {(void *)&a};
-    // cooperative launch = all blocks co-resident (the cut-edge pipeline needs every warp alive; no grid.sync is used)
-    XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kernel, dim3(blocks), dim3(wpb * 32), kargs, smem, s));
+    // cooperative launch = all blocks co-resident; no grid.sync is used
+    XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kernel, dim3(NM * blocks), dim3(wpb * 32), kargs, smem, s));
     return XAN_OK;
 }
 
-// Routes one member with the skew kernel.  Returns XAN_E_INVALID (without an error message) when the plan or the
-// calendar does not allow it, so that the caller can fall back to the warp-dataflow kernel.
-int route_skew(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_dist, const double *d_velocity,
-               const double *d_area, const double *d_chs_prev, const int *h_ndays, int nmonths, int spinup_months, int ld,
-               double dt, double *d_chs, double *d_avg, double *d_instream, int sms, cudaStream_t s) {
-    SkewPlan *sp = get_skew(pl);
+// Variants compiled: one member for every K (the register budget of a whole SM); several members for K = 2 (256- and
+// 128-thread blocks) and K = 4 (128-thread blocks), where NM blocks fit the register file without (much) spilling.
+template <int K>
+static int launch_skew_nm(SkewPlan *sp, SkewArgs &a, int nm, int sms, cudaStream_t s) {
+    if (nm == 1) return launch_skew<K, 1, (K == 1 ? 512 : 256)>(sp, a, sms, s);
+    int blocks = 0, wpb = 0;
+    if (skew_geometry(sp, K, sms, &blocks, &wpb) != XAN_OK) return XAN_E_INVALID;
+    if constexpr (K == 2) {
+        if (wpb == 8 && nm == 2) return launch_skew<2, 2, 256>(sp, a, sms, s);
+        if (wpb == 4 && nm == 2) return launch_skew<2, 2, 128>(sp, a, sms, s);
+        if (wpb == 4 && nm == 3) return launch_skew<2, 3, 128>(sp, a, sms, s);
+        if (wpb == 4 && nm == 4) return launch_skew<2, 4, 128>(sp, a, sms, s);
+    }
+    if constexpr (K == 4) {
+        if (wpb == 4 && nm == 2) return launch_skew<4, 2, 128>(sp, a, sms, s);
+        if (wpb == 4 && nm == 3) return launch_skew<4, 3, 128>(sp, a, sms, s);
+    }
+    if constexpr (K == 3 || K == 5 || K == 6) {
+        if (wpb == 4 && nm == 2) return launch_skew<K, 2, 128>(sp, a, sms, s);
+    }
+    return XAN_E_INVALID;
+}
+
+// Routes nm (1 .. SK_NM_MAX) members with one launch of the skew kernel.  Returns XAN_E_INVALID (without an error
+// message) when the plan or the calendar does not allow it (nm > 1: when nm blocks per SM do not fit or the variant is
+// not compiled), so that the caller can fall back to fewer members per launch / the warp-dataflow kernel.
+int route_skew(xan_mrtm_plan *pl, int nm, const double *const *d_runoff, const double *d_flow_dist,
+               const double *d_velocity, const double *d_area, const double *const *d_chs_prev, const int *h_ndays,
+               int nmonths, int spinup_months, int ld, double dt, double *const *d_chs, double *const *d_avg,
+               double *const *d_instream, int sms, cudaStream_t s) {
+    if (nm < 1 || nm > SK_NM_MAX) return XAN_E_INVALID;
+    SkewPlan *sp = get_skew(pl, nm);
     if (!sp) return XAN_E_INVALID;
     const int M = spinup_months + nmonths;
     std::vector<int> start(M + 1, 0), nts(M), month(M);
@@ -1007,8 +1092,15 @@ int route_skew(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_d
     a.cell = sp->d_cell; a.lag = sp->d_lag; a.src = sp->d_src; a.ghost_edge = sp->d_ghost_edge;
     a.ghost_lag = sp->d_ghost_lag; a.exp_edge = sp->d_exp_edge; a.exp_place = sp->d_exp_place; a.Dw = sp->d_Dw;
     a.edge_prod = sp->d_edge_prod; a.edge_cons = sp->d_edge_cons; a.progress = sp->d_progress;
-    a.runoff = d_runoff; a.chs_prev = d_chs_prev; a.flow_dist = d_flow_dist; a.velocity = d_velocity; a.area = d_area;
-    a.chs = d_chs; a.avg = d_avg; a.instream = d_instream;
+    a.runoff = d_runoff[0]; a.chs_prev = d_chs_prev ? d_chs_prev[0] : nullptr;
+    a.flow_dist = d_flow_dist; a.velocity = d_velocity; a.area = d_area;
+    a.chs = d_chs ? d_chs[0] : nullptr; a.avg = d_avg ? d_avg[0] : nullptr; a.instream = d_instream ? d_instream[0] : nullptr;
+    for (int m = 1; m < nm; ++m) {
+        SkewArgs::Member &x = a.more[m - 1];
+        x.runoff = d_runoff[m]; x.chs_prev = d_chs_prev ? d_chs_prev[m] : nullptr;
+        x.chs = d_chs ? d_chs[m] : nullptr; x.avg = d_avg ? d_avg[m] : nullptr;
+        x.instream = d_instream ? d_instream[m] : nullptr;
+    }
     a.nw = sp->nw; a.M = M; a.T = (int)total; a.spinup = spinup_months; a.ld = ld; a.G = sp->G; a.O = sp->O; a.dt = dt;
     const char *er = getenv("XANTHOS_MRTM_SKEW_RING"), *es = getenv("XANTHOS_MRTM_SLEEP_NS");
     int RL = er ? atoi(er) : 1024;
@@ -1041,23 +1133,27 @@ int route_skew(xan_mrtm_plan *pl, const double *d_runoff, const double *d_flow_d
     a.step_nt = sp->d_cal_int + (M + 1);
     a.step_month = sp->d_cal_int + (M + 1) + M;
     a.step_secs = sp->d_cal_secs;
+    // per launch (and member): concurrent routes on one plan share no mutable device state
+    const size_t ring_len = (size_t)std::max(sp->n_edges, 1) * RL;
     double2 *ring = nullptr;
-    XAN_CUDA_CHECK(scratch_alloc(&ring, sizeof(double2) * (size_t)std::max(sp->n_edges, 1) * RL, s));
+    XAN_CUDA_CHECK(scratch_alloc(&ring, sizeof(double2) * ring_len * nm, s));
     a.ring = ring;
-    int *progress = nullptr;   // per launch: concurrent routes on one plan share no mutable device state
-    XAN_CUDA_CHECK(scratch_alloc(&progress, sizeof(int) * sp->nw, s));
-    XAN_CUDA_CHECK(cudaMemsetAsync(progress, 0, sizeof(int) * sp->nw, s));
+    for (int m = 1; m < nm; ++m) a.more[m - 1].ring = ring + m * ring_len;
+    int *progress = nullptr;
+    XAN_CUDA_CHECK(scratch_alloc(&progress, sizeof(int) * sp->nw * nm, s));
+    XAN_CUDA_CHECK(cudaMemsetAsync(progress, 0, sizeof(int) * sp->nw * nm, s));
     a.progress = progress;
+    for (int m = 1; m < nm; ++m) a.more[m - 1].progress = progress + (size_t)m * sp->nw;
     const char *edbg = getenv("XANTHOS_MRTM_DEBUG");
     if (edbg) XAN_CUDA_CHECK(scratch_alloc(&a.dbg, sizeof(long long) * 5 * sp->nw, s));
     int rc = XAN_E_INVALID;
     switch (sp->K) {
-        case 1: rc = launch_skew<1>(sp, a, sms, s); break;
-        case 2: rc = launch_skew<2>(sp, a, sms, s); break;
-        case 3: rc = launch_skew<3>(sp, a, sms, s); break;
-        case 4: rc = launch_skew<4>(sp, a, sms, s); break;
-        case 5: rc = launch_skew<5>(sp, a, sms, s); break;
-        case 6: rc = launch_skew<6>(sp, a, sms, s); break;
+        case 1: rc = launch_skew_nm<1>(sp, a, nm, sms, s); break;
+        case 2: rc = launch_skew_nm<2>(sp, a, nm, sms, s); break;
+        case 3: rc = launch_skew_nm<3>(sp, a, nm, sms, s); break;
+        case 4: rc = launch_skew_nm<4>(sp, a, nm, sms, s); break;
+        case 5: rc = launch_skew_nm<5>(sp, a, nm, sms, s); break;
+        case 6: rc = launch_skew_nm<6>(sp, a, nm, sms, s); break;
         default: break;
     }
     if (rc == XAN_OK && a.dbg) {

@@ -6,11 +6,13 @@ The reference has no ensemble driver: a user loops over configuration files, one
 cover, PM tables, basin plan, routing plan, ABCD parameters) is staged once and the members stream through
 PET -> ABCD -> MRTM with their copies overlapped:
 
-    h2d stream     : forcing of member k+1  (8 fields, pinned host -> HBM, transposed to month-major)
-    compute stream : PM -> ABCD -> MRTM -> basin aggregates of member k
-    d2h stream     : requested outputs of member k-1  (HBM -> pinned host, cell-major like the reference's arrays)
+    h2d stream     : forcing of the next members  (8 fields each, pinned host -> HBM; transposed to month-major on the
+                     compute stream)
+    compute stream : PM -> ABCD of members k and k+1, then ONE routing launch for both (`route_device_batch`: the thread
+                     blocks of the two members share the SMs), basin aggregates
+    d2h stream     : requested outputs of the members before  (HBM -> pinned host, cell-major like the reference's arrays)
 
-The forcing of at most `prefetch_depth` (2) members is on its way ahead of the member being computed.  Only the variables named in `output_vars` are copied back (the reference
+The forcing of at most `prefetch_depth` (2) members is on its way ahead of the group being computed.  Only the variables named in `output_vars` are copied back (the reference
 keeps PET, AET, Q, Sav, ChStorage and Avg_ChFlow of a scenario in host memory but writes `output_vars` only,
 data_writer/out_writer.py:60-110).  With torch.distributed initialised the members are dealt in contiguous blocks to the ranks
 (no collective in the data path) and the basin aggregates [n_members, 2, nmonths, n_basins] are gathered at the end.
@@ -91,9 +93,10 @@ class EnsembleStatics:
 
 
 class EnsembleRunner:
-    def __init__(self, statics, output_vars=('q', 'avgchflow'), aggregates=True, prefetch_depth=2):
+    def __init__(self, statics, output_vars=('q', 'avgchflow'), aggregates=True, prefetch_depth=2, group=2):
         torch = C.torch_cuda()
         self.prefetch_depth = max(1, int(prefetch_depth))   # members whose forcing may be on its way ahead of the compute
+        self.group = max(1, int(group))                     # members routed by one launch
         bad = [v for v in output_vars if v not in OUTPUTS]
         if bad:
             raise C.ValidationException("unknown output variable(s) {}; choose from {}".format(bad, OUTPUTS))
@@ -158,25 +161,43 @@ class EnsembleRunner:
         e.record(stream)
         return e
 
-    def _compute(self, fields):
+    def _compute(self, uploads):
+        """Per member: wait for its upload, transposes, PM -> ABCD; then one routing call for the group and the basin
+        aggregates per member.  `uploads`: [(staged tensors, upload event)]."""
         s = self.s
-        pet = pm_mod.run_pmpet_device(s.data_ns(fields), s.ncell, s.nlcs, s.start_yr, s.end_yr, s.water_idx, s.snow_idx,
-                                      s.lc_years)
+        compute = self._torch.cuda.current_stream()
         want = tuple(k for k, v in (('aet', 'aet'), ('q', 'q'), ('sav', 'soilmoisture')) if v in self.output_vars or k == 'q')
-        res = abcd_mod.run_device(s.plan, s.d_pars, pet, fields['precip'], fields['tmin'], s.nmonths, s.runoff_spinup,
-                                  want=want)
-        chs, avg, inst = mrtm_mod.route_device(s.um, res['q'], s.d_L, s.d_V, s.d_area, s.ndays, s.dt, s.routing_spinup,
-                                               want_chs='chstorage' in self.output_vars)
-        out = {'pet': pet, 'aet': res.get('aet'), 'q': res['q'], 'soilmoisture': res.get('sav'), 'chstorage': chs,
-               'avgchflow': avg}
-        agg = None
-        if self.aggregates:       # basin runoff in km3 / month and basin sum of the mean streamflow, [2, nmonths, n_basins]
-            agg = self._torch.empty((2, s.nmonths, s.n_basins), dtype=self._torch.float64, device='cuda')
-            C.check(C.lib().xan_basin_sum(s.plan._plan, C.ptr(res['q'].t), C.ptr(s.d_area_km3), s.nmonths, res['q'].ld,
-                                          C.ptr(agg[0]), C.stream_ptr()))
-            C.check(C.lib().xan_basin_sum(s.plan._plan, C.ptr(avg.t), None, s.nmonths, avg.ld, C.ptr(agg[1]),
-                                          C.stream_ptr()))
-        return out, agg
+        pets, ress = [], []
+        while uploads:
+            staged, ev = uploads.pop(0)
+            compute.wait_event(ev)     # the first member's PET and runoff run under the second member's upload
+            fields = self._to_fields(staged)
+            del staged
+            pet = pm_mod.run_pmpet_device(s.data_ns(fields), s.ncell, s.nlcs, s.start_yr, s.end_yr, s.water_idx,
+                                          s.snow_idx, s.lc_years)
+            pets.append(pet)
+            ress.append(abcd_mod.run_device(s.plan, s.d_pars, pet, fields['precip'], fields['tmin'], s.nmonths,
+                                            s.runoff_spinup, want=want))
+        want_chs = 'chstorage' in self.output_vars
+        if len(ress) == 1:
+            routed = [mrtm_mod.route_device(s.um, ress[0]['q'], s.d_L, s.d_V, s.d_area, s.ndays, s.dt, s.routing_spinup,
+                                            want_chs=want_chs)]
+        else:
+            routed = mrtm_mod.route_device_batch(s.um, [r['q'] for r in ress], s.d_L, s.d_V, s.d_area, s.ndays, s.dt,
+                                                 s.routing_spinup, want_chs=want_chs)
+        results = []
+        for pet, res, (chs, avg, _) in zip(pets, ress, routed):
+            out = {'pet': pet, 'aet': res.get('aet'), 'q': res['q'], 'soilmoisture': res.get('sav'), 'chstorage': chs,
+                   'avgchflow': avg}
+            agg = None
+            if self.aggregates:   # basin runoff in km3 / month and basin sum of the mean streamflow, [2, nmonths, n_basins]
+                agg = self._torch.empty((2, s.nmonths, s.n_basins), dtype=self._torch.float64, device='cuda')
+                C.check(C.lib().xan_basin_sum(s.plan._plan, C.ptr(res['q'].t), C.ptr(s.d_area_km3), s.nmonths,
+                                              res['q'].ld, C.ptr(agg[0]), C.stream_ptr()))
+                C.check(C.lib().xan_basin_sum(s.plan._plan, C.ptr(avg.t), None, s.nmonths, avg.ld, C.ptr(agg[1]),
+                                              C.stream_ptr()))
+            results.append((out, agg))
+        return results
 
     def _download(self, out, agg):
         torch = self._torch
@@ -206,47 +227,51 @@ class EnsembleRunner:
     # ---- driver ----------------------------------------------------------------------------------------------------------
     def run(self, members):
         """Generator: yields (index, {variable: host ndarray [ncell, nmonths], 'basin_aggregates': [2, nmonths, n_basins]})
-        in member order; member k+1 is being uploaded and member k computed while member k-1 is handed out."""
+        in member order; the next members are being uploaded and a group of `group` members computed while the outputs of
+        the group before are handed out."""
         torch = self._torch
         members = list(members)
         if not members:
             return
         compute = torch.cuda.current_stream()
-        n, depth = len(members), self.prefetch_depth
+        n, depth, g = len(members), self.prefetch_depth, self.group
+        # pinned output buffers in flight: the group being computed, the group before it on its way to the host, and the
+        # results the caller still holds from the last hand-out - allocated before the pipeline starts, not inside it
+        C.host_pool.reserve((self.s.ncell, self.s.nmonths), min(3 * g, n + g) * len(self.output_vars))
         uploaded, next_up = {}, 0
-        pending = None            # (index, host tensors, done event) of the member whose outputs are in flight
-        computed = []             # completion events of the compute stage, to bound the uploads' run-ahead
+        pending = []              # (index, host tensors, done event) of the members whose outputs are in flight
+        computed = {}             # member -> completion event of its group's compute stage, to bound the uploads' run-ahead
 
-        def pump(k):              # uploads of the members up to k + depth; member j waits for compute j - depth - 1
+        def pump(k):              # uploads of the members up to k + depth; member j waits for the compute of member j - depth - g
             nonlocal next_up
             while next_up < n and next_up <= k + depth:
-                if next_up - depth - 1 >= 0:
-                    computed[next_up - depth - 1].synchronize()
+                old = next_up - depth - g
+                if old >= 0:
+                    computed[old].synchronize()
                 uploaded[next_up] = self._upload(members[next_up])
                 next_up += 1
-        pump(0 - 1)
-        for k in range(n):
-            if k not in uploaded:
-                pump(k - depth)
-            staged, ev = uploaded.pop(k)
-            compute.wait_event(ev)
+        pump(g - 1)
+        for k0 in range(0, n, g):
+            ks = list(range(k0, min(n, k0 + g)))
+            if ks[-1] not in uploaded:
+                pump(ks[-1] - depth)
             c0 = self._mark(compute)
-            fields = self._to_fields(staged)
-            del staged
-            out, agg = self._compute(fields)
-            host, done = self._download(out, agg)
+            results = self._compute([uploaded.pop(k) for k in ks])
+            downloads = [self._download(out, agg) for out, agg in results]
+            del results
             cev = torch.cuda.Event(enable_timing=self.timeline is not None)
             cev.record(compute)
-            computed.append(cev)
-            if self.timeline is not None:
-                self.timeline[k]['compute'] = (c0, cev)
-                self.timeline[k]['done'] = done
-            del fields, out, agg
-            pump(k)
-            if pending is not None:
-                yield self._finish(pending)
-            pending = (k, host, done)
-        yield self._finish(pending)
+            for k, (host, done) in zip(ks, downloads):
+                computed[k] = cev
+                if self.timeline is not None:
+                    self.timeline[k]['compute'] = (c0, cev)
+                    self.timeline[k]['done'] = done
+            pump(ks[-1])
+            for p in pending:
+                yield self._finish(p)
+            pending = [(k, host, done) for k, (host, done) in zip(ks, downloads)]
+        for p in pending:
+            yield self._finish(p)
 
     @staticmethod
     def _finish(p):

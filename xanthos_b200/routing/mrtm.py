@@ -133,11 +133,14 @@ def route_device(um, runoff, flow_dist, str_velocity, area, ndays, dt, spinup_mo
     return chs, avg, inst
 
 
-def route_device_batch(um, runoffs, flow_dist, str_velocity, area, ndays, dt, spinup_months, method=C.MRTM_AUTO):
+def route_device_batch(um, runoffs, flow_dist, str_velocity, area, ndays, dt, spinup_months, method=C.MRTM_AUTO,
+                       want_chs=True, want_avg=True):
     """
     Ensemble routing: `runoffs` is a list of Fields (one per member, same shape and leading dimension).
     Returns a list of (ChStorage Field, Avg_ChFlow Field, instream_flow tensor), bit-identical to one
-    `route_device` call per member; every warp advances two members at a time.
+    `route_device` call per member.  On a river forest two members share one launch of the skew kernel: their thread
+    blocks are co-resident on every SM and fill each other's idle issue slots (32 instead of 43 ms per member on the
+    0.5 degree world; `XANTHOS_MRTM_SKEW_MEMBERS=1` routes one member per launch).
     """
     import ctypes
     torch = C.torch_cuda()
@@ -148,15 +151,16 @@ def route_device_batch(um, runoffs, flow_dist, str_velocity, area, ndays, dt, sp
     L, V, A = C.dev_vector(flow_dist), C.dev_vector(str_velocity), C.dev_vector(area)
     nd, ndp = C.as_c(np.asarray(ndays).reshape(-1)[:m], np.int32)
     k = len(qs)
-    outs = [(C.Field.empty(n, m, ld), C.Field.empty(n, m, ld), torch.empty(n, dtype=torch.float64, device='cuda'))
-            for _ in range(k)]
+    outs = [(C.Field.empty(n, m, ld) if want_chs else None, C.Field.empty(n, m, ld) if want_avg else None,
+             torch.empty(n, dtype=torch.float64, device='cuda')) for _ in range(k)]
     arr = ctypes.c_void_p * k
 
     def ptrs(ts):
-        return arr(*[t.data_ptr() for t in ts])
+        return arr(*[None if t is None else t.data_ptr() for t in ts])
     C.check(C.lib().xan_mrtm_route_batch(um._plan, k, ptrs([q.t for q in qs]), C.ptr(L), C.ptr(V), C.ptr(A), None, ndp,
                                          m, int(spinup_months), ld, float(dt), int(method),
-                                         ptrs([o[0].t for o in outs]), ptrs([o[1].t for o in outs]),
+                                         ptrs([o[0].t if o[0] else None for o in outs]),
+                                         ptrs([o[1].t if o[1] else None for o in outs]),
                                          ptrs([o[2] for o in outs]), C.stream_ptr()))
     return outs
 
