@@ -427,7 +427,7 @@ struct SkewArgs {
         double2 *ring;
         int *progress;
     } more[SK_NM_MAX - 1];
-    int blocks_per_member;
+    int blocks_per_member, rotate;   // rotate: shift of the block -> warp-set map per member
 };
 
 __device__ __forceinline__ int sk_ld_relaxed_pred(const int *p, int pred, int dflt) {
@@ -978,7 +978,12 @@ __global__ void __launch_bounds__(MAXT, NM) mrtm_skew_kernel(const SkewArgs a0) 
             a.runoff = x.runoff; a.chs_prev = x.chs_prev; a.chs = x.chs; a.avg = x.avg; a.instream = x.instream;
             a.ring = x.ring; a.progress = x.progress; a.dbg = nullptr;
         }
-        skew_block<K, true>(a, (int)blockIdx.x - m * bpm, bpm);
+        // member m takes the plan's warp sets in rotated order: block i of every member tends to land on the same SM, and
+        // the same plan warp of two members is equally heavy (the clamping cells are a property of the network) - the
+        // rotation pairs a heavy warp with some other warp instead of its twin
+        int bx = (int)blockIdx.x - m * bpm + m * a0.rotate;
+        if (bx >= bpm) bx -= bpm;
+        skew_block<K, true>(a, bx, bpm);
     }
 }
 
@@ -1018,6 +1023,10 @@ static int launch_skew(SkewPlan *sp, SkewArgs &a, int sms, cudaStream_t s) {
     // every block of every member must be resident (the cut-edge pipeline needs every warp alive)
     if (per_sm < 1 || blocks * wpb < sp->nw || (long long)per_sm * sms < (long long)NM * blocks) return XAN_E_INVALID;
     a.blocks_per_member = blocks;
+    {
+        const char *er = getenv("XANTHOS_MRTM_SKEW_ROTATE");
+        a.rotate = er ? std::max(0, atoi(er)) % blocks : blocks / NM;
+    }
     void *kargs[] = {(void *)&a};
     // cooperative launch = all blocks co-resident; no grid.sync is used
     XAN_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)kernel, dim3(NM * blocks), dim3(wpb * 32), kargs, smem, s));

@@ -8,8 +8,11 @@ PET -> ABCD -> MRTM with their copies overlapped:
 
     h2d stream     : forcing of the next members  (8 fields each, pinned host -> HBM; transposed to month-major on the
                      compute stream)
-    compute stream : PM -> ABCD of members k and k+1, then ONE routing launch for both (`route_device_batch`: the thread
-                     blocks of the two members share the SMs), basin aggregates
+    compute stream : transposes, PM -> ABCD of members k and k+1, then ONE routing launch for both
+                     (`route_device_batch`: the thread blocks of the two members share the SMs), basin aggregates,
+                     output transposes.  `XANTHOS_ENSEMBLE_FRONT=1` moves PM -> ABCD of the NEXT pair to a stream of
+                     its own, beside the routing launch: measured slower (75.7 against 72.0 ms per pair - every block
+                     that shares an SM with the latency-bound routing chain slows it by more than it saves), so it is off.
     d2h stream     : requested outputs of the members before  (HBM -> pinned host, cell-major like the reference's arrays)
 
 The forcing of at most `prefetch_depth` (2) members is on its way ahead of the group being computed.  Only the variables named in `output_vars` are copied back (the reference
@@ -102,6 +105,8 @@ class EnsembleRunner:
             raise C.ValidationException("unknown output variable(s) {}; choose from {}".format(bad, OUTPUTS))
         self.s, self.output_vars, self.aggregates = statics, tuple(output_vars), bool(aggregates)
         self.h2d, self.d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        import os as _os
+        self.front = torch.cuda.Stream() if _os.environ.get('XANTHOS_ENSEMBLE_FRONT', '0') == '1' else None
         self.h2d_bytes = self.d2h_bytes = 0
         self._torch = torch
         import os
@@ -115,7 +120,7 @@ class EnsembleRunner:
         missing = [k for k in FORCING if k not in member]
         if missing:
             raise C.ValidationException("ensemble member lacks {}".format(missing))
-        compute = torch.cuda.current_stream()
+        compute = self.front if self.front is not None else torch.cuda.current_stream()   # the consumer of the staged tensors
         staged = {}
         # Only copy-engine work goes on the h2d stream.  The transposes to month-major run on the compute stream in front
         # of the member's kernels: a kernel on the h2d stream would wait for SM resources behind the routing kernel of
@@ -161,23 +166,36 @@ class EnsembleRunner:
         e.record(stream)
         return e
 
-    def _compute(self, uploads):
-        """Per member: wait for its upload, transposes, PM -> ABCD; then one routing call for the group and the basin
-        aggregates per member.  `uploads`: [(staged tensors, upload event)]."""
-        s = self.s
-        compute = self._torch.cuda.current_stream()
+    def _front(self, uploads):
+        """Front stage, per member: wait for its upload, transposes, PM -> ABCD.  `uploads`: [(staged tensors, upload event)].
+        Runs on the front stream (beside the routing launch of the group before); returns (PET Fields, ABCD results, event)."""
+        s, torch = self.s, self._torch
+        compute = torch.cuda.current_stream()
+        stream = self.front if self.front is not None else compute
         want = tuple(k for k, v in (('aet', 'aet'), ('q', 'q'), ('sav', 'soilmoisture')) if v in self.output_vars or k == 'q')
         pets, ress = [], []
-        while uploads:
-            staged, ev = uploads.pop(0)
-            compute.wait_event(ev)     # the first member's PET and runoff run under the second member's upload
-            fields = self._to_fields(staged)
-            del staged
-            pet = pm_mod.run_pmpet_device(s.data_ns(fields), s.ncell, s.nlcs, s.start_yr, s.end_yr, s.water_idx,
-                                          s.snow_idx, s.lc_years)
-            pets.append(pet)
-            ress.append(abcd_mod.run_device(s.plan, s.d_pars, pet, fields['precip'], fields['tmin'], s.nmonths,
-                                            s.runoff_spinup, want=want))
+        with torch.cuda.stream(stream):
+            while uploads:
+                staged, ev = uploads.pop(0)
+                stream.wait_event(ev)     # the first member's PET and runoff run under the second member's upload
+                fields = self._to_fields(staged)
+                del staged
+                pet = pm_mod.run_pmpet_device(s.data_ns(fields), s.ncell, s.nlcs, s.start_yr, s.end_yr, s.water_idx,
+                                              s.snow_idx, s.lc_years)
+                res = abcd_mod.run_device(s.plan, s.d_pars, pet, fields['precip'], fields['tmin'], s.nmonths,
+                                          s.runoff_spinup, want=want)
+                if stream is not compute:     # allocated on the front stream, read by the routing / output stage
+                    for f in [pet] + list(res.values()):
+                        f.t.record_stream(compute)
+                pets.append(pet)
+                ress.append(res)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return pets, ress, ev
+
+    def _back(self, pets, ress):
+        """One routing call for the group and the basin aggregates per member (compute stream)."""
+        s = self.s
         want_chs = 'chstorage' in self.output_vars
         if len(ress) == 1:
             routed = [mrtm_mod.route_device(s.um, ress[0]['q'], s.d_L, s.d_V, s.d_area, s.ndays, s.dt, s.routing_spinup,
@@ -250,13 +268,24 @@ class EnsembleRunner:
                     computed[old].synchronize()
                 uploaded[next_up] = self._upload(members[next_up])
                 next_up += 1
-        pump(g - 1)
-        for k0 in range(0, n, g):
+        fronts = {}
+
+        def start_front(k0):      # front stage of the group starting at member k0
             ks = list(range(k0, min(n, k0 + g)))
             if ks[-1] not in uploaded:
                 pump(ks[-1] - depth)
+            fronts[k0] = self._front([uploaded.pop(k) for k in ks])
+        pump(g - 1)
+        start_front(0)
+        for k0 in range(0, n, g):
+            ks = list(range(k0, min(n, k0 + g)))
+            pets, ress, fev = fronts.pop(k0)
             c0 = self._mark(compute)
-            results = self._compute([uploaded.pop(k) for k in ks])
+            compute.wait_event(fev)
+            results = self._back(pets, ress)
+            del pets, ress
+            if k0 + g < n:        # enqueued behind this group's routing launch, runs beside it on the device
+                start_front(k0 + g)
             downloads = [self._download(out, agg) for out, agg in results]
             del results
             cev = torch.cuda.Event(enable_timing=self.timeline is not None)
