@@ -20,8 +20,9 @@ ref = None
 for K in [int(v) for v in os.environ.get('KS', '2,4').split(',')]:
     os.environ['XANTHOS_MRTM_SKEW_K'] = os.environ['XANTHOS_MRTM_SKEW_KM'] = str(K)
     um = mrtm.upstream_genmatrix(upid)
-    for nm in (1, 2, 3, 4):
+    for nm, win in [(int(a), int(b)) for a in os.environ.get('NMS', '1,2,3,4').split(',') for b in os.environ.get('WINDOWS', '0').split(',')]:
         os.environ['XANTHOS_MRTM_SKEW_MEMBERS'] = str(nm)
+        os.environ['XANTHOS_MRTM_SKEW_WINDOW'] = str(win)
         mrtm.route_device_batch(um, qs, w.flow_dist, w.velocity, w.area, nd, DT, 2)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -35,6 +36,6 @@ for K in [int(v) for v in os.environ.get('KS', '2,4').split(',')]:
         same = all(torch.equal(o[0].t.view(torch.int64), r[0].view(torch.int64)) and
                    torch.equal(o[1].t.view(torch.int64), r[1].view(torch.int64)) and
                    torch.equal(o[2].view(torch.int64), r[2].view(torch.int64)) for o, r in zip(outs, ref))
-        print('K=%d members per launch=%d: %d members %.2f ms, %.2f ms per member, %.3e cell-months/s, bitwise same: %s'
-              % (K, nm, NMEM, ms, ms / NMEM, NMEM * w.ncell * M / (ms * 1e-3), same), flush=True)
+        print('K=%d window=%d members per launch=%d: %d members %.2f ms, %.2f ms per member, %.3e cell-months/s, bitwise same: %s'
+              % (K, win, nm, NMEM, ms, ms / NMEM, NMEM * w.ncell * M / (ms * 1e-3), same), flush=True)
         del outs

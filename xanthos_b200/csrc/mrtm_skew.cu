@@ -404,6 +404,7 @@ static SkewPlan *get_skew(xan_mrtm_plan *pl, int nm = 1) {
 // =============================================================================================
 // device
 // =============================================================================================
+constexpr int SK_WINDOW_DEFAULT = 1;   // pacing window in months (0: off; raised to the smallest deadlock-free value at launch)
 constexpr int SK_NM_MAX = 4;     // members per launch (co-resident blocks per SM)
 
 struct SkewArgs {
@@ -425,8 +426,10 @@ struct SkewArgs {
         const double *runoff, *chs_prev;
         double *chs, *avg, *instream;
         double2 *ring;
-        int *progress;
+        int *progress, *done;
     } more[SK_NM_MAX - 1];
+    int *done;                   // [M + 2] per member: warps that have crossed boundary b (pacing window), or null
+    int window;                  // a warp crosses boundary b only after every warp has crossed b - window (0: no pacing)
     int blocks_per_member, rotate;   // rotate: shift of the block -> warp-set map per member
 };
 
@@ -783,6 +786,7 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
     int b = 0, evt = a.step_start[0];
     double ev_nt_prev = 1.0, ev_secs_next = a.step_secs[M > 1 ? 1 : 0];
     size_t ev_next2_off = (size_t)a.step_month[M > 2 ? 2 : 0] * a.ld, ev_out_off = 0;
+    const bool paced = a.window > 0;
     bool ch1 = false, ch2 = false;   // some flow written one / two iterations ago has F' != F
     auto events = [&](const int n, const unsigned LAST) {   // LAST: byte offset of the table buffer written one iteration ago
         const long long c0 = dbg ? clock64() : 0;
@@ -792,7 +796,10 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
         for (int s = 0; s < K; ++s) {
             const int c = L.cell[s];
             if (c >= 0 && L.lag[s] == k) {
-                if (st && a.chs) stg_stream(a.chs + ev_out_off + c, L.S[s]);
+                if (st && a.chs) {
+                    if (paced) a.chs[ev_out_off + c] = L.S[s];
+                    else stg_stream(a.chs + ev_out_off + c, L.S[s]);
+                }
                 if (b == M && a.instream)   // the final flow F' of the last sub-step (= F when that iteration was a fast one)
                     a.instream[c] = sk_lds1(L.mp + (LAST + ((!LAZY || SK_LAGM == 2 || ch1) ? FPOFF : 0u) + (unsigned)s * 256u));
                 L.pend[s] = L.fav[s];
@@ -806,9 +813,28 @@ __device__ __forceinline__ void skew_run(const SkewArgs &a, const int w, const i
             for (int s = 0; s < K; ++s) {
                 const int c = L.cell[s];
                 if (c >= 0) {
-                    if (st && a.avg) stg_stream(a.avg + ev_out_off + c, L.pend[s] / ev_nt_prev);   // mrtm.py:80
+                    if (st && a.avg) {                                                              // mrtm.py:80
+                        if (paced) a.avg[ev_out_off + c] = L.pend[s] / ev_nt_prev;
+                        else stg_stream(a.avg + ev_out_off + c, L.pend[s] / ev_nt_prev);
+                    }
                     if (b + 1 < M) L.erln[s] = ((L.qn[s] * L.ar[s]) * (1e6 / 1e3)) / ev_secs_next;  // mrtm.py:45
                     if (b + 2 < M) L.qn[s] = a.runoff[ev_next2_off + c];                            // used a month later
+                }
+            }
+            if (paced) {
+                // Pacing: independent river trees are not coupled by any ring, and the warps of small trees run up to twice
+                // as fast as the slowest chain.  Cells that share a 32-byte sector of a month row then touch it months
+                // apart - each sector of the runoff is fetched from DRAM up to four times and every output sector
+                // written back half-filled (3.6 GB per launch instead of 1.55).  A warp crosses boundary b only after ALL
+                // warps have crossed b - window: the month rows in flight stay in L2.  The slowest warp never waits here.
+                if (lane == 0) atomicAdd(a.done + b, 1);
+                const int need = b - a.window;
+                if (need >= 0) {
+                    for (;;) {
+                        const int v = sk_ld_relaxed_pred(a.done + need, 1, 0);
+                        if (__all_sync(full, v >= a.nw)) break;
+                        __nanosleep(2000);
+                    }
                 }
             }
             ++b;   // constants of the next window, fetched a month ahead of their use
@@ -976,7 +1002,7 @@ __global__ void __launch_bounds__(MAXT, NM) mrtm_skew_kernel(const SkewArgs a0) 
         if (m > 0) {
             const SkewArgs::Member &x = a0.more[m - 1];
             a.runoff = x.runoff; a.chs_prev = x.chs_prev; a.chs = x.chs; a.avg = x.avg; a.instream = x.instream;
-            a.ring = x.ring; a.progress = x.progress; a.dbg = nullptr;
+            a.ring = x.ring; a.progress = x.progress; a.done = x.done; a.dbg = nullptr;
         }
         // member m takes the plan's warp sets in rotated order: block i of every member tends to land on the same SM, and
         // the same plan warp of two members is equally heavy (the clamping cells are a property of the network) - the
@@ -1153,6 +1179,22 @@ int route_skew(xan_mrtm_plan *pl, int nm, const double *const *d_runoff, const d
     XAN_CUDA_CHECK(cudaMemsetAsync(progress, 0, sizeof(int) * sp->nw * nm, s));
     a.progress = progress;
     for (int m = 1; m < nm; ++m) a.more[m - 1].progress = progress + (size_t)m * sp->nw;
+    // pacing window in months (XANTHOS_MRTM_SKEW_WINDOW, 0 = off; raised to the smallest safe value)
+    const char *ew = getenv("XANTHOS_MRTM_SKEW_WINDOW");
+    a.window = ew ? std::max(0, atoi(ew)) : SK_WINDOW_DEFAULT;
+    if (a.window > 0) {
+        // a consumer follows its producer by up to 3 hand-over chunks + the producer's largest lag, level after level:
+        // the leaves must be allowed that far ahead of the outlets, plus what the rings hold, or the throttles deadlock
+        const int depth_steps = sp->n_levels * (3 * SK_CH + sp->Dmax + 1) + RL;
+        a.window = std::max(a.window, ceil_div(depth_steps, std::max(nt_min, 1)) + 2);
+    }
+    int *done = nullptr;
+    if (a.window > 0) {
+        XAN_CUDA_CHECK(scratch_alloc(&done, sizeof(int) * (size_t)(M + 2) * nm, s));
+        XAN_CUDA_CHECK(cudaMemsetAsync(done, 0, sizeof(int) * (size_t)(M + 2) * nm, s));
+        a.done = done;
+        for (int m = 1; m < nm; ++m) a.more[m - 1].done = done + (size_t)m * (M + 2);
+    }
     const char *edbg = getenv("XANTHOS_MRTM_DEBUG");
     if (edbg) XAN_CUDA_CHECK(scratch_alloc(&a.dbg, sizeof(long long) * 5 * sp->nw, s));
     int rc = XAN_E_INVALID;
@@ -1179,6 +1221,7 @@ int route_skew(xan_mrtm_plan *pl, int nm, const double *const *d_runoff, const d
     if (a.dbg) cudaFreeAsync(a.dbg, s);
     cudaFreeAsync(ring, s);
     cudaFreeAsync(progress, s);
+    if (done) cudaFreeAsync(done, s);
     return rc;
 }
 
