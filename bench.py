@@ -551,19 +551,19 @@ def run_ours(args, rank, world_size, local_rank):
     if os.environ.get('XANTHOS_MRTM_AUTO', 'skew') == 'tree':
         mrtm_kernel = 'mrtm_warp_kernel<1,640>'
     elif MEMBERS_PER_STEP > 1 and os.environ.get('XANTHOS_MRTM_SKEW_MEMBERS', '2') != '1':
-        mrtm_kernel = 'mrtm_skew_kernel<%s,2,128> (K cells per lane, 2 members per launch)' % os.environ.get('XANTHOS_MRTM_SKEW_KM', '4')
+        mrtm_kernel = 'mrtm_skew_kernel<%s,2,128>' % os.environ.get('XANTHOS_MRTM_SKEW_KM', '4')   # <cells per lane, members per launch, threads>
     else:
         mrtm_kernel = 'mrtm_skew_kernel<%s,1,256>' % os.environ.get('XANTHOS_MRTM_SKEW_K', '2')
     # DRAM traffic per launch and pipe utilisation from the committed ncu --set full capture of the same workload
-    # (profiles/r02_kernels.json, written by tools/ncu_summary.py from the .ncu-rep of this round)
+    # (profiles/r02b_kernels.json, written by tools/ncu_summary.py from the .ncu-rep of this round)
     traffic, ncu_k, ncu_src = {}, {}, None
-    for fname in ('r02_kernels.json', 'r01c_traffic.json'):
+    for fname in ('r02b_kernels.json', 'r02_kernels.json', 'r01c_traffic.json'):
         try:
             with open(os.path.join(ROOT, 'profiles', fname)) as f:
                 tk = json.load(f)['kernels']
             find = lambda prefix: next((v for k, v in tk.items() if k.startswith(prefix)), None)       # noqa: E731
             pmk, spk, smk = find('pm_pet_fast_kernel'), find('abcd_spinup_kernel'), find('abcd_sim_kernel')
-            mrk = find(mrtm_kernel.split('<')[0])
+            mrk = find(mrtm_kernel) or find(mrtm_kernel.split('<')[0])
             if not (pmk and spk and smk and mrk):
                 continue
             ncu_k = {'pm_pet_kernel': pmk, 'abcd_spinup+reinit+sim': smk, 'mrtm_warp_kernel': mrk}

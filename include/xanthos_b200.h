@@ -197,10 +197,14 @@ int xan_mrtm_route(xan_mrtm_plan *plan, const double *d_runoff, const double *d_
 
 /* Ensemble variant of xan_mrtm_route: n_members independent scenarios (same topology, same static
  * fields, same calendar) in one call.  The h_* arguments are HOST arrays of n_members DEVICE
- * pointers (h_chs_prev, h_chs, h_avg, h_instream and any of their entries may be NULL).  Members are
- * advanced one after the other (two members per warp measured slower: 69 against 54 ms per member;
- * XANTHOS_MRTM_MEMBERS=2 keeps that path testable).
- * Results are bit-identical to n_members calls of xan_mrtm_route. */
+ * pointers (h_chs_prev, h_chs, h_avg, h_instream and any of their entries may be NULL).  On a river
+ * forest two members share one launch of the skew kernel: their thread blocks are co-resident on
+ * every SM and fill each other's idle issue slots (31 against 43 ms per member on the 0.5 degree
+ * world; XANTHOS_MRTM_SKEW_MEMBERS=1 routes one member per launch, =3 three where they fit).  With
+ * the warp-dataflow kernel (XANTHOS_MRTM_AUTO=tree) members are advanced one after the other (two
+ * members per warp measured slower: 69 against 54 ms per member; XANTHOS_MRTM_MEMBERS=2 keeps that
+ * path testable).  Results are bit-identical to n_members calls of xan_mrtm_route.  Concurrent calls
+ * on one plan from different streams are allowed: rings and counters are per-launch scratch. */
 int xan_mrtm_route_batch(xan_mrtm_plan *plan, int n_members, const double *const *h_runoff,
                          const double *d_flow_dist, const double *d_velocity, const double *d_area,
                          const double *const *h_chs_prev, const int *h_ndays, int nmonths,

@@ -292,6 +292,35 @@ def test_skew_routing_kernel_bitwise_against_oracle(K, monkeypatch):
             assert bitwise_equal(a, b) and bitwise_equal(a, c), (w.ncell, dt, name)
 
 
+@pytest.mark.parametrize("env", [{}, {'XANTHOS_MRTM_SKEW_WINDOW': '0'}, {'XANTHOS_MRTM_SKEW_KM': '2'},
+                                 {'XANTHOS_MRTM_SKEW_KM': '4', 'XANTHOS_MRTM_SKEW_MEMBERS': '3', 'XANTHOS_MRTM_SKEW_ROTATE': '0'},
+                                 {'XANTHOS_MRTM_SKEW_MEMBERS': '1'}])
+def test_skew_multi_member_launch_bitwise_against_oracle(env, monkeypatch):
+    """Several ensemble members per launch of the skew kernel (co-resident thread blocks, lazy F' stores, rotated warp
+    sets, month pacing window on / off, 2 or 4 cells per lane, 2 or 3 members per launch): every member equals
+    `oracle.mrtm.route` of its own runoff bit for bit - on a small world with cut edges and on the bench world."""
+    from xanthos_b200 import synthetic, _cuda as C
+    from xanthos_b200.routing import mrtm
+    from oracle import mrtm as omrtm
+    from oracle.calendar_utils import set_month_arrays
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for w, months, spin, nmem in [(synthetic.make_world(40, 80, 1500, 8, seed=5, coast_pull=0.0), 26, 12, 3),
+                                  (synthetic.make_world(seed=0), 6, 3, 2)]:
+        s = w.settings()
+        um = mrtm.upstream_genmatrix(mrtm.upstream(w.coords, mrtm.downstream(w.coords, w.flow_dir, s), s))
+        nd = set_month_arrays(36, 2003, 2005)[:months, 2]
+        qs = [synthetic.runoff_input(w, months, seed=30 + k) for k in range(nmem)]
+        outs = mrtm.route_device_batch(um, [C.Field.from_host(q) for q in qs], w.flow_dist, w.velocity, w.area, nd, 10800,
+                                       spin)
+        oup = omrtm.upstream_fast(w.coords, omrtm.downstream(w.coords, w.flow_dir, w.nrow, w.ncol), w.nrow, w.ncol)
+        rows = omrtm.csr_rows(oup)
+        for q, (chs, avg, inst) in zip(qs, outs):
+            want = omrtm.route(q, w.flow_dist, w.velocity, w.area, nd, 10800, rows, spin)
+            assert bitwise_equal(chs.to_host(), want[0]) and bitwise_equal(avg.to_host(), want[1])
+            assert bitwise_equal(inst.cpu().numpy(), want[2])
+
+
 def test_ensemble_runner_equals_the_plugin_calls_member_by_member():
     """xanthos_b200.ensemble.run_ensemble (overlapped H2D / compute / D2H over members, BASELINE config 5) returns, for
     every member, exactly what run_pmpet -> abcd_execute -> route return for that member alone; the basin aggregates
