@@ -134,6 +134,101 @@ def test_calibrate_class_single_basin_and_short_observations(tmp_path):
                              maxiter=2)
 
 
+def _streamflow_world(m=36):
+    from xanthos_b200 import synthetic
+    from oracle import mrtm as omrtm
+    from oracle.calendar_utils import set_month_arrays
+    w = synthetic.make_world(24, 48, 320, 5, seed=44)
+    ab = synthetic.abcd_inputs(w, m, seed=9)
+    tmin = np.nan_to_num(ab['tmin'])
+    ymd = set_month_arrays(m, 2001, 2000 + m // 12)
+    dsid = omrtm.downstream(w.coords, w.flow_dir, w.nrow, w.ncol)
+    rows = omrtm.csr_rows(omrtm.upstream_fast(w.coords, dsid, w.nrow, w.ncol))
+    spin_rt = 6
+
+    def route_fn(rsim):      # what Components.calculate_routing returns (components.py:262-296): Avg_ChFlow [ncell, nmonths]
+        return omrtm.route(rsim, w.flow_dist, w.velocity, w.area, ymd[:, 2], 10800, rows, spin_rt)[1]
+
+    class Comp:              # the instance behind router_func = Components.calculate_routing
+        def __init__(self):
+            self.data = SimpleNamespace(coords=w.coords, flow_dir=w.flow_dir, flow_dist=w.flow_dist,
+                                        str_velocity=w.velocity, area=w.area, basin_ids=w.basin_ids)
+            self.s = w.settings()
+            self.s.routing_spinup = spin_rt
+            self.yr_imth_dys = ymd
+            self.routing_timestep_hours = 3 * 3600
+            self.um = self.dsid = None
+
+        def calculate_routing(self, runoff):
+            raise AssertionError("the evaluator routes on the device; it only needs the instance")
+    return w, ab, tmin, dsid, route_fn, Comp(), m
+
+
+def test_streamflow_objective_equals_the_oracle_of_the_intended_semantics(tmp_path):
+    """`set_calibrate = 1` (calibrate_abcd.py:164-173, docs/calibration_tutorial.md): KGE between the routed flow at the
+    basin's outlet and observed streamflow.  The reference's own branch has no usable behaviour (oracle/calibrate.py
+    docstring); the CUDA path is compared with `oracle.calibrate.objective_kge_streamflow`, which keeps the reference's
+    steps (basin ABCD -> global array of zeros -> router -> KGE) and adds the one missing definition (the outlet cell).
+    One global pass per population slot evaluates that slot of EVERY basin: 3 basins x 3 candidates here."""
+    from xanthos_b200.calibrate import calibrate_abcd as cal
+    from oracle import calibrate as ocal
+    w, ab, tmin, dsid, route_fn, comp, m = _streamflow_world()
+    outlets = ocal.outlet_cells(w.basin_ids, dsid, w.area)
+    assert np.array_equal(outlets, cal.outlet_cells(w.basin_ids, dsid, w.area))
+    ev = cal.streamflow_evaluator(comp.calculate_routing, w.basin_ids, w.area, ab['precip'], ab['pet'], tmin, m, m)
+    assert np.array_equal(ev.outlets, outlets)
+    rng = np.random.default_rng(3)
+    basins = [1, 3, 4]
+    lo, hi = np.array([b[0] for b in cal.BOUNDS_SNOW]), np.array([b[1] for b in cal.BOUNDS_SNOW])
+    cand = lo + (hi - lo) * rng.random((len(basins), 3, 5))
+    _, series = ev.evaluate(basins, ab['pars'][[b - 1 for b in basins]][:, None, :], np.ones((len(basins), m)),
+                            want_series=True)
+    obs = series[:, 0, :] * (1 + rng.normal(0, 0.05, (len(basins), m)))          # "gauge" record per basin, m3/s
+    assert (obs > 0).all()
+    ed = ev.evaluate(basins, cand, obs)
+    for i, b in enumerate(basins):
+        idx = np.nonzero(w.basin_ids == b)[0]
+        for j in range(cand.shape[1]):
+            want = ocal.objective_kge_streamflow(cand[i, j], ab['pet'][idx], ab['precip'][idx], tmin[idx], m, m, idx,
+                                                 ab['pet'].shape, route_fn, outlets[b - 1], obs[i])
+            assert abs(ed[i, j] - want) <= 1e-9 * max(1.0, abs(want)), (b, j, ed[i, j], want)
+    # the reference-signature calls (one basin, one parameter vector; basin rows in, router_func = the bound method)
+    idx = np.where(w.basin_ids == 3)
+    one = cal.objective_kge(cand[1, 0], cal.basin_runoff, 1, ab['pet'][idx], ab['precip'][idx], tmin[idx], m, m,
+                            'm3_per_sec', w.area[idx], obs[1], idx, ab['pet'].shape, comp.calculate_routing)
+    assert abs(one - ed[1, 0]) <= 1e-9 * max(1.0, abs(one))
+    # Calibrate(...).calibrate_basin() with the streamflow target: result files, KGE = 1 - oracle objective at the stored
+    # parameters, at least as good as the parameters that produced the record
+    table = np.c_[np.full(m, 3.0), obs[1]]
+    c = cal.Calibrate(basin_num=3, basin_ids=w.basin_ids, basin_areas=w.area, precip=ab['precip'], pet=ab['pet'],
+                      obs=table, tmin=tmin, n_months=m, runoff_spinup=m, set_calibrate=1, obs_unit='m3_per_sec',
+                      out_dir=str(tmp_path), router_func=comp.calculate_routing)
+    c.calibrate_basin(popsize=4, maxiter=12, seed=7)
+    kge = np.load(os.path.join(str(tmp_path), 'kge_result_basin_3.npy'))
+    pars = np.load(os.path.join(str(tmp_path), 'abcdm_parameters_basin_3.npy'))
+    want = ocal.objective_kge_streamflow(pars[0], ab['pet'][idx], ab['precip'][idx], tmin[idx], m, m, idx[0],
+                                         ab['pet'].shape, route_fn, outlets[2], obs[1])
+    assert abs((1 - want) - kge[0]) < 1e-8
+    first = ocal.objective_kge_streamflow(ab['pars'][2], ab['pet'][idx], ab['precip'][idx], tmin[idx], m, m, idx[0],
+                                          ab['pet'].shape, route_fn, outlets[2], obs[1])
+    assert kge[0] > 0.5 and kge[0] >= (1 - first) - 0.1
+    # calibrate_all (what Components.calibrate calls, components.py:497) with the streamflow target, two basins at once
+    out2 = os.path.join(str(tmp_path), 'all')
+    os.makedirs(out2)
+    st = SimpleNamespace(set_calibrate=1, cal_basins=['3-4'], nmonths=m, runoff_spinup=m, obs_unit='m3_per_sec',
+                         calib_out_dir=out2)
+    data = SimpleNamespace(basin_ids=w.basin_ids, area=w.area, precip=ab['precip'], tmin=tmin, basin_names=None,
+                           cal_obs=np.r_[np.c_[np.full(m, 3.0), obs[1]], np.c_[np.full(m, 4.0), obs[2]]])
+    pars2, kge2 = cal.calibrate_all(st, data, ab['pet'], comp.calculate_routing, popsize=3, maxiter=5, seed=11)
+    for k, b in enumerate((3, 4)):
+        idb = np.nonzero(w.basin_ids == b)[0]
+        stored = np.load(os.path.join(out2, 'abcdm_parameters_basin_{}.npy'.format(b)))
+        assert np.array_equal(stored[0], pars2[k])
+        want = ocal.objective_kge_streamflow(pars2[k], ab['pet'][idb], ab['precip'][idb], tmin[idb], m, m, idb,
+                                             ab['pet'].shape, route_fn, outlets[b - 1], obs[k + 1])
+        assert abs((1 - want) - kge2[k]) < 1e-8
+
+
 def test_de_kernels_equal_the_scipy_pinned_oracle_bitwise():
     """xan_de_init / xan_de_trial / xan_de_select against oracle/de.py (which tests/test_oracle.py pins bit for bit to
     scipy's DifferentialEvolutionSolver, updating='deferred') for several problems and generations."""

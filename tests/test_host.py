@@ -336,3 +336,19 @@ def test_skew_plan_and_schedule_model_equal_the_oracle_bitwise(monkeypatch):
             want = omrtm.route(q, w.flow_dist, w.velocity, w.area, nd, dt, omrtm.csr_rows(oup), spin)
             for a, b, name in zip(got, want, ('ChStorage', 'Avg_ChFlow', 'instream_flow')):
                 assert bitwise_equal(a, b), (K, dt, name)
+
+
+def test_outlet_cells_of_the_streamflow_target_match_the_oracle():
+    """Host logic of the streamflow calibration target (INTENDED semantics, oracle/calibrate.py): the outlet of a basin
+    is its cell with the largest drainage area - vectorised product code against the sequential oracle."""
+    from xanthos_b200 import synthetic
+    from xanthos_b200.calibrate import calibrate_abcd as cal
+    from oracle import calibrate as ocal, mrtm as omrtm
+    for args in [(24, 48, 320, 5, 44), (40, 80, 1500, 8, 5), (90, 180, 6000, 30, 2)]:
+        w = synthetic.make_world(*args[:4], seed=args[4])
+        dsid = omrtm.downstream(w.coords, w.flow_dir, w.nrow, w.ncol)
+        a, b = cal.outlet_cells(w.basin_ids, dsid, w.area), ocal.outlet_cells(w.basin_ids, dsid, w.area)
+        assert np.array_equal(a, b)
+        assert (w.basin_ids[a] == np.arange(1, w.n_basins + 1)).all()          # the outlet of basin b lies in basin b
+        down = dsid[a] - 1                                                      # and drains out of the basin (or nowhere)
+        assert all(d < 0 or w.basin_ids[d] != w.basin_ids[c] for c, d in zip(a, down))

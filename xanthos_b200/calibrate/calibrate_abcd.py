@@ -15,8 +15,15 @@ basins of a call are advanced together.  Two drivers with the same semantics:
 `differential_evolution_device` (default; population and generation logic on the device, csrc/de.cu)
 and `differential_evolution_batched` (numpy, one host round trip per generation).
 
-Only the runoff target (`set_calibrate = 0`) is supported: the streamflow branch of the
-reference (:164-173) is broken.
+Targets: observed runoff (`set_calibrate = 0`, `BasinEvaluator`) and observed streamflow
+(`set_calibrate = 1`, `StreamflowEvaluator`).  The reference's streamflow branch (:164-173) hands
+the whole [ncell, nmonths] array returned by Components.calculate_routing to np.std / np.mean /
+np.corrcoef (moments over every cell of the globe, correlation with global cell 0 after a
+67,421 x 67,421 covariance matrix) and puts the basin's runoff at FLAT indices of the global
+array (np.put): it has no usable behaviour to reproduce.  What is implemented is the INTENDED
+objective of docs/calibration_tutorial.md - KGE between the routed flow at the basin's outlet
+cell and the observed streamflow in m3/s - restated in oracle/calibrate.py
+(`objective_kge_streamflow`, `outlet_cells`) and labelled as such.
 """
 
 import logging
@@ -85,6 +92,133 @@ class BasinEvaluator:
                                            C.ptr(d_pars), C.ptr(d_obs), self.n_months, self.spinup, self.pet.ld,
                                            self.unit_km3, C.ptr(d_ed), C.ptr(d_series), C.stream_ptr()))
         return d_ed
+
+
+def outlet_cells(basin_ids, dsid, area):
+    """
+    Outlet cell (0-based) of every basin id 1 .. max: the basin's cell with the largest drainage area (own area plus
+    everything upstream), lowest index on ties; -1 for ids without cells.  `dsid`: 1-based downstream id per cell,
+    0 = none (routing/mrtm.py `downstream`).  The reference names no cell (module docstring): INTENDED semantics.
+    """
+    basin_ids = np.asarray(basin_ids).astype(np.int64)
+    down = np.asarray(dsid).astype(np.int64) - 1
+    n = len(down)
+    acc = np.asarray(area, dtype=np.float64).copy()
+    has = down >= 0
+    indeg = np.bincount(down[has], minlength=n)
+    frontier = np.nonzero(indeg == 0)[0]
+    while len(frontier):               # leaves first, level by level; np.add.at adds the givers of a receiver in index order
+        give = frontier[has[frontier]]
+        recv = down[give]
+        np.add.at(acc, recv, acc[give])
+        np.subtract.at(indeg, recv, 1)
+        cand = np.unique(recv)
+        frontier = cand[indeg[cand] == 0]
+    nb = int(basin_ids.max())
+    out = np.full(nb, -1, dtype=np.int64)
+    order = np.lexsort((np.arange(n), -acc))                # largest drainage area first, lowest index on ties
+    ids = basin_ids[order]
+    first = np.unique(ids, return_index=True)
+    for b, i in zip(*first):
+        if 1 <= b <= nb:
+            out[b - 1] = order[i]
+    return out
+
+
+class StreamflowEvaluator:
+    """
+    KGE distance between the routed streamflow at every basin's outlet and its observed streamflow (m3/s) for a whole
+    differential-evolution population: INTENDED semantics of `set_calibrate = 1` (module docstring).
+
+    Routing never mixes basins, so ONE global pass evaluates candidate j of EVERY basin at once: for population slot j the
+    parameter table row of basin b is candidate j of b, `xan_abcd_run` gives the global runoff field, and the fields of
+    two slots share a launch of `xan_mrtm_route_batch` (members = population slots).  A generation of P candidates is
+    P ABCD runs + P / 2 routing launches whatever the number of basins (0.5 degree world, 360 + 360 months: P x 32 ms).
+    Same `evaluate` / `evaluate_device` interface as `BasinEvaluator`.
+    """
+
+    def __init__(self, basin_ids, basin_areas, precip, pet, tmin, n_months, runoff_spinup, um, dsid, flow_dist,
+                 str_velocity, ndays, dt, routing_spinup, obs_unit='m3_per_sec'):
+        from ..routing import mrtm as mrtm_mod
+        torch = C.torch_cuda()
+        if obs_unit != 'm3_per_sec':
+            raise C.ValidationException("obs_unit '{}' not supported for streamflow calibration".format(obs_unit))
+        self.basin_ids = np.asarray(basin_ids).astype(int)
+        self.n_rows = int(self.basin_ids.max())
+        rows = np.where(self.basin_ids >= 1, self.basin_ids - 1, -1).astype(np.int32)
+        self.plan = abcd_mod.basin_plan(rows, self.n_rows)
+        self.pet, self.precip = C.as_field(pet), C.as_field(precip)
+        self.tmin = None if tmin is None else C.as_field(tmin)
+        self.nosnow = tmin is None
+        self.n_months, self.spinup = int(n_months), int(runoff_spinup)
+        self.um, self._mrtm = um, mrtm_mod
+        self.d_L, self.d_V, self.d_A = C.dev_vector(flow_dist), C.dev_vector(str_velocity), C.dev_vector(basin_areas)
+        self.ndays = np.asarray(ndays, dtype=np.int32).reshape(-1)[:self.n_months]
+        self.dt, self.routing_spinup = float(dt), int(routing_spinup)
+        self.outlets = outlet_cells(self.basin_ids, dsid, basin_areas)
+        self.d_outlets = torch.from_numpy(np.maximum(self.outlets, 0)).cuda()
+        self._torch = torch
+
+    def evaluate(self, basin_nums, pars, obs, want_series=False):
+        """basin_nums [nb] (1-based), pars [nb, P, 4 or 5], obs [nb, n_months] -> distances [nb, P] (+ series)."""
+        torch = self._torch
+        pars = np.asarray(pars, dtype=np.float64)
+        nb, npar, k = pars.shape
+        if k == 4:
+            pars = np.concatenate([pars, np.zeros((nb, npar, 1))], axis=2)
+        d_pars = torch.from_numpy(np.ascontiguousarray(pars)).cuda()
+        d_obs = torch.from_numpy(np.ascontiguousarray(obs, dtype=np.float64)).cuda()
+        d_series = torch.empty((nb, npar, self.n_months), dtype=torch.float64, device='cuda') if want_series else None
+        ed = self.evaluate_device(basin_nums, d_pars, d_obs, d_series).cpu().numpy()
+        return (ed, d_series.cpu().numpy()) if want_series else ed
+
+    def evaluate_device(self, basin_nums, d_pars, d_obs, d_series=None):
+        torch = self._torch
+        nb, npar = int(d_pars.shape[0]), int(d_pars.shape[1])
+        if tuple(d_obs.shape) != (nb, self.n_months) or len(basin_nums) != nb or int(d_pars.shape[2]) != 5:
+            raise C.ValidationException("objective: parameters {} / observations {} do not match {} basins x {} months"
+                                        .format(tuple(d_pars.shape), tuple(d_obs.shape), len(basin_nums), self.n_months))
+        rows_h = np.asarray(basin_nums, dtype=np.int64) - 1
+        if (rows_h < 0).any() or (rows_h >= self.n_rows).any() or (self.outlets[rows_h] < 0).any():
+            raise C.ValidationException("streamflow calibration: a requested basin has no cells")
+        rows = torch.from_numpy(rows_h).cuda()
+        # rows of the basins that are not being calibrated: any valid parameter set (their flow is not looked at)
+        base = torch.tensor([0.5, 4.0, 0.5, 0.5, 0.5], dtype=torch.float64, device='cuda').repeat(self.n_rows, 1)
+        outl = self.d_outlets[rows]
+        mod = d_series if d_series is not None else torch.empty((nb, npar, self.n_months), dtype=torch.float64, device='cuda')
+        for j0 in range(0, npar, 2):
+            js = list(range(j0, min(npar, j0 + 2)))
+            qs = []
+            for j in js:
+                table = base.clone()
+                table[rows] = d_pars[:, j, :]
+                if self.nosnow:
+                    table = table[:, :4].contiguous()
+                qs.append(abcd_mod.run_device(self.plan, table, self.pet, self.precip, self.tmin, self.n_months,
+                                              self.spinup, want=('q',))['q'])
+            if len(qs) == 1:
+                routed = [self._mrtm.route_device(self.um, qs[0], self.d_L, self.d_V, self.d_A, self.ndays, self.dt,
+                                                  self.routing_spinup, want_chs=False)]
+            else:
+                routed = self._mrtm.route_device_batch(self.um, qs, self.d_L, self.d_V, self.d_A, self.ndays, self.dt,
+                                                       self.routing_spinup, want_chs=False)
+            for j, (_, avg, _) in zip(js, routed):
+                mod[:, j, :] = avg.t[:, outl].t()             # Avg_ChFlow [nmonths][ld] -> outlet series [nb, n_months]
+        return kge_distance_device(mod, d_obs)
+
+
+def kge_distance_device(mod, obs):
+    """Euclidean distance from the KGE optimum (calibrate_abcd.py:190-211) for mod [nb, P, M] against obs [nb, M]:
+    population standard deviations and means (np.std / np.mean), Pearson correlation (np.corrcoef)."""
+    torch = C.torch_cuda()
+    o = obs[:, None, :]
+    m_m, m_o = mod.mean(dim=2), o.mean(dim=2)
+    dm, do = mod - m_m[..., None], o - m_o[..., None]
+    var_m, var_o = (dm * dm).mean(dim=2), (do * do).mean(dim=2)
+    relvar = torch.sqrt(var_m) / torch.sqrt(var_o)
+    bias = m_m / m_o
+    r = (dm * do).mean(dim=2) / torch.sqrt(var_m * var_o)
+    return torch.sqrt((r - 1) ** 2 + (relvar - 1) ** 2 + (bias - 1) ** 2)
 
 
 def differential_evolution_batched(evaluate, n_problems, bounds, popsize=15, maxiter=1000, tol=0.01, atol=0.0,
@@ -234,6 +368,27 @@ def differential_evolution_device(ev, basin_nums, robs, bounds, popsize=15, maxi
                 nit=nit, nfev=nfev)
 
 
+def streamflow_evaluator(router_function, basin_ids, basin_areas, precip, pet, tmin, n_months, runoff_spinup,
+                         obs_unit='m3_per_sec'):
+    """
+    StreamflowEvaluator for the world behind `router_function` - the bound `Components.calculate_routing` that the
+    reference passes down as router_func (components.py:497, calibrate_abcd.py:216-232): its instance holds the flow
+    network, the channel geometry, the calendar and the routing time step.
+    """
+    from ..routing import mrtm as mrtm_mod
+    comp = getattr(router_function, '__self__', None)
+    if comp is None or not hasattr(comp, 'data') or not hasattr(comp, 's'):
+        raise C.ValidationException("streamflow calibration (set_calibrate = 1) needs router_function = "
+                                    "Components.calculate_routing of the run being calibrated")
+    if getattr(comp, 'um', None) is None or getattr(comp, 'dsid', None) is None:
+        comp.dsid = mrtm_mod.downstream(comp.data.coords, comp.data.flow_dir, comp.s)
+        comp.upid = mrtm_mod.upstream(comp.data.coords, comp.dsid, comp.s)
+        comp.um = mrtm_mod.upstream_genmatrix(comp.upid)
+    return StreamflowEvaluator(basin_ids, basin_areas, precip, pet, tmin, n_months, runoff_spinup, comp.um, comp.dsid,
+                               comp.data.flow_dist, comp.data.str_velocity, comp.yr_imth_dys[:, 2],
+                               comp.routing_timestep_hours, comp.s.routing_spinup, obs_unit)
+
+
 def _basin_obs(obs, basin_num, n_months):
     """Observed series of a basin (calibrate_abcd.py:88)."""
     return np.asarray(obs)[np.where(np.asarray(obs)[:, 0] == basin_num)][:n_months, 1]
@@ -267,9 +422,8 @@ class Calibrate:
 
     def __init__(self, basin_num, basin_ids, basin_areas, precip, pet, obs, tmin, n_months, runoff_spinup,
                  set_calibrate, obs_unit, out_dir, router_func=None):
-        if set_calibrate != 0:
-            raise NotImplementedError("only calibration against observed runoff (set_calibrate = 0) is supported; "
-                                      "the reference's streamflow branch is broken (calibrate_abcd.py:164-173)")
+        if set_calibrate not in (0, 1):
+            raise C.ValidationException("set_calibrate must be 0 (observed runoff) or 1 (observed streamflow)")
         self.basin_num = basin_num
         self.basin_ids = basin_ids
         self.basin_areas = basin_areas
@@ -294,9 +448,13 @@ class Calibrate:
     def calibrate_basin(self, popsize=15, polish=False, seed=None, maxiter=1000):
         """Calibrate the basin and save kge_result_basin_<n>.npy / abcd(m)_parameters_basin_<n>.npy (:90-131)."""
         st = time.time()
+        ev = None
+        if self.set_calibrate == 1:      # routed flow at the basin's outlet against observed streamflow (module docstring)
+            ev = streamflow_evaluator(self.router_func, self.basin_ids, self.basin_areas, self.precip, self.pet, self.tmin,
+                                      self.n_months, self.runoff_spinup, self.obs_unit)
         pars, kge, res = calibrate_basins([self.basin_num], self.basin_ids, self.basin_areas, self.precip, self.pet,
                                           self.obs, self.tmin, self.n_months, self.runoff_spinup, self.obs_unit,
-                                          popsize=popsize, maxiter=maxiter, seed=seed)
+                                          popsize=popsize, maxiter=maxiter, seed=seed, evaluator=ev)
         self.all_pars[0, :] = pars[0]
         self.kge_vals[0] = kge[0]
         par_names = 'abcd' + 'm' * (not self.nosnow)
@@ -315,26 +473,47 @@ def save_results(out_dir, basin_num, kge_vals, all_pars, par_names):
     np.save('{}/{}_parameters_basin_{}.npy'.format(out_dir, par_names, basin_num), all_pars)
 
 
+def _one_basin_world(set_calibrate, pet, precip, tmin, n_months, runoff_spinup, obs_unit, bsn_areas, basin_idx, arr_shp,
+                     routing_func):
+    """Evaluator and basin number for the reference-signature calls below (one basin, one parameter vector)."""
+    idx = np.asarray(basin_idx[0] if isinstance(basin_idx, tuple) else basin_idx)
+    n = len(idx)
+    if set_calibrate == 0:
+        return BasinEvaluator(np.ones(n, dtype=int), bsn_areas, precip, pet, tmin, n_months, runoff_spinup, obs_unit), 1
+    # streamflow target: the basin's rows go back into global arrays (as the reference does with the runoff, :169-171);
+    # the other cells get zero forcing - their flow stays in their own basins and is not looked at
+    comp = getattr(routing_func, '__self__', None)
+    if comp is None:
+        raise C.ValidationException("streamflow calibration needs routing_func = Components.calculate_routing")
+    ncell = int(arr_shp[0])
+
+    def spread(a):
+        g = np.zeros((ncell, np.asarray(a).shape[1]))
+        g[idx] = a
+        return g
+    ids = np.asarray(comp.data.basin_ids).astype(int)
+    ev = streamflow_evaluator(routing_func, ids, comp.data.area, spread(precip), spread(pet),
+                              None if tmin is None else spread(tmin), n_months, runoff_spinup, obs_unit)
+    return ev, int(ids[idx[0]])
+
+
 def basin_runoff(pars, set_calibrate, pet, precip, tmin, n_months, runoff_spinup, obs_unit, bsn_areas, basin_idx,
                  arr_shp, routing_func=None):
-    """Modelled runoff series of one basin for one parameter vector (calibrate_abcd.py:134-162)."""
-    if set_calibrate != 0:
-        raise NotImplementedError("streamflow calibration is not supported (broken in the reference)")
-    n = len(basin_idx[0]) if isinstance(basin_idx, tuple) else len(basin_idx)
-    ev = BasinEvaluator(np.ones(n, dtype=int), bsn_areas, precip, pet, tmin, n_months, runoff_spinup, obs_unit)
-    _, series = ev.evaluate([1], np.asarray(pars, dtype=float)[None, None, :], np.ones((1, int(n_months))),
+    """Modelled series of one basin for one parameter vector (calibrate_abcd.py:134-173): the basin's runoff for the
+    runoff target, the routed flow at its outlet (INTENDED semantics, module docstring) for the streamflow target."""
+    ev, b = _one_basin_world(set_calibrate, pet, precip, tmin, n_months, runoff_spinup, obs_unit, bsn_areas, basin_idx,
+                             arr_shp, routing_func)
+    _, series = ev.evaluate([b], np.asarray(pars, dtype=float)[None, None, :], np.ones((1, int(n_months))),
                             want_series=True)
     return series[0, 0]
 
 
 def objective_kge(pars, model_func, set_calibrate, pet, precip, tmin, n_months, runoff_spinup, obs_unit, bsn_areas,
                   bsn_Robs, basin_idx, arr_shp, routing_func=None):
-    """KGE distance between simulated and observed basin runoff (calibrate_abcd.py:176-213)."""
-    if set_calibrate != 0:
-        raise NotImplementedError("streamflow calibration is not supported (broken in the reference)")
-    n = len(basin_idx[0]) if isinstance(basin_idx, tuple) else len(basin_idx)
-    ev = BasinEvaluator(np.ones(n, dtype=int), bsn_areas, precip, pet, tmin, n_months, runoff_spinup, obs_unit)
-    ed = ev.evaluate([1], np.asarray(pars, dtype=float)[None, None, :], np.asarray(bsn_Robs, dtype=float)[None, :])
+    """KGE distance between simulated and observed basin series (calibrate_abcd.py:176-213)."""
+    ev, b = _one_basin_world(set_calibrate, pet, precip, tmin, n_months, runoff_spinup, obs_unit, bsn_areas, basin_idx,
+                             arr_shp, routing_func)
+    ed = ev.evaluate([b], np.asarray(pars, dtype=float)[None, None, :], np.asarray(bsn_Robs, dtype=float)[None, :])
     return float(ed[0, 0])
 
 
@@ -365,8 +544,6 @@ def calibrate_all(settings, data, pet, router_function, popsize=15, maxiter=1000
     one differential evolution at a time; here all of them advance together, one CUDA launch per
     generation, and the same per-basin result files are written.
     """
-    if settings.set_calibrate != 0:
-        raise NotImplementedError("only calibration against observed runoff (set_calibrate = 0) is supported")
     basins = expand_str_range(settings.cal_basins)
     for b in basins:
         name = data.basin_names[b - 1] if getattr(data, 'basin_names', None) is not None else ''
@@ -386,9 +563,13 @@ def calibrate_all(settings, data, pet, router_function, popsize=15, maxiter=1000
     npar = len(par_names)
     pars, kge, nfev = np.zeros((0, npar)), np.zeros(0), 0
     if mine:
+        ev = None
+        if settings.set_calibrate == 1:   # routed flow at every basin's outlet against observed streamflow (module docstring)
+            ev = streamflow_evaluator(router_function, data.basin_ids, data.area, data.precip, pet, data.tmin,
+                                      settings.nmonths, settings.runoff_spinup, settings.obs_unit)
         pars, kge, res = calibrate_basins(mine, data.basin_ids, data.area, data.precip, pet, data.cal_obs, data.tmin,
                                           settings.nmonths, settings.runoff_spinup, settings.obs_unit, popsize=popsize,
-                                          maxiter=maxiter, seed=seed)
+                                          maxiter=maxiter, seed=seed, evaluator=ev)
         nfev = int(res['nfev'].sum())
         for i, b in enumerate(mine):
             save_results(settings.calib_out_dir, b, np.array([kge[i]]), pars[i][None, :], par_names)

@@ -545,7 +545,7 @@ def write_example(root, world, start_yr, end_yr, pet='pm', routing=True, seed=1,
         'CalculateDroughtStats = {}'.format(int('drought' in (postproc or {}))),
         'CalculateAccessibleWater = {}'.format(int('accessible_water' in (postproc or {}))),
         'CalculateHydropowerPotential = 0', 'CalculateHydropowerActual = 0',
-        'Calibrate = {}'.format(int(calibrate))]
+        'Calibrate = {}'.format(int(bool(calibrate)))]
     if postproc and 'drought' in postproc:
         lines += ['[Drought]'] + ['{} = {}'.format(k, v) for k, v in postproc['drought'].items()]
     if postproc and 'accessible_water' in postproc:
@@ -563,8 +563,10 @@ def write_example(root, world, start_yr, end_yr, pet='pm', routing=True, seed=1,
         lines += ['[AccessibleWater]', 'ResCapacityFile = total_reservoir_storage_capacity_BM3.csv',
                   'BfiFile = bfi_per_basin.csv'] + ['{} = {}'.format(k, v) for k, v in postproc['accessible_water'].items()]
     if calibrate:
-        lines += ['[Calibrate]', 'set_calibrate = 0', 'observed = ' + os.path.join(root, 'input', 'obs.csv'),
-                  'obs_unit = km3_per_mth', 'calib_out_dir = ' + os.path.join(root, 'output', 'calib'),
+        streamflow = calibrate == 'streamflow'      # calibrate=True: runoff target; 'streamflow': set_calibrate = 1
+        lines += ['[Calibrate]', 'set_calibrate = {}'.format(int(streamflow)),
+                  'observed = ' + os.path.join(root, 'input', 'obs.csv'),
+                  'obs_unit = ' + ('m3_per_sec' if streamflow else 'km3_per_mth'), 'calib_out_dir = ' + os.path.join(root, 'output', 'calib'),
                   'calibration_basins = 1-{}'.format(world.n_basins)]
     if extra_lines:
         lines += list(extra_lines)
