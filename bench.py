@@ -388,7 +388,7 @@ def run_ours(args, rank, world_size, local_rank):
                                   world.flow_dist, world.velocity, um, ndays, DT, spin_ro, spin_rt)
     member_a = {k: host[k] for k in ens.FORCING}
     member_b = {k: pinned(np.roll(host[k], 7, axis=0)) for k in ens.FORCING}    # a second, different member
-    n_mem = max(6, min(args.steps, 12))
+    n_mem = max(6, min(args.steps, 24))
     sink = []
 
     def ensemble_ms(ma, mb, reps=3):
