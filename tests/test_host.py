@@ -8,6 +8,7 @@ import os
 import re
 import subprocess
 import sys
+from types import SimpleNamespace
 
 import numpy as np
 import pytest
@@ -352,3 +353,33 @@ def test_outlet_cells_of_the_streamflow_target_match_the_oracle():
         assert (w.basin_ids[a] == np.arange(1, w.n_basins + 1)).all()          # the outlet of basin b lies in basin b
         down = dsid[a] - 1                                                      # and drains out of the basin (or nowhere)
         assert all(d < 0 or w.basin_ids[d] != w.basin_ids[c] for c, d in zip(a, down))
+
+
+def test_routing_raster_vectorize_matches_the_oracle_and_the_live_reference():
+    """f2: `DataLoader.load_routing_data` for a 2-D DRT raster (flip, 68-row offset, Fortran-order sampling, rep_val;
+    data_load.py:392-425) against the oracle restatement, and the oracle against the reference's own `vectorize` /
+    `sub2ind` where the reference tree is present."""
+    from xanthos_b200.data_reader.data_load import DataLoader
+    from oracle import io_layout, ref_loader
+    rng = np.random.default_rng(12)
+    nrow, ncol, ncell = 360, 720, 5000
+    lin = rng.choice(nrow * ncol, ncell, replace=False)
+    coords = np.zeros((ncell, 5))
+    coords[:, 4], coords[:, 3] = lin % nrow + 1, lin // nrow + 1          # 1-based row / column (data_load.py:201-203)
+    raster = rng.normal(500.0, 800.0, (280, ncol))                        # values below rep_val and "missing" cells
+    raster[rng.random(raster.shape) < 0.05] = -9999
+    dl = DataLoader.__new__(DataLoader)
+    dl.s = SimpleNamespace(ncell=ncell, ngridrow=nrow, ngridcol=ncol)
+    dl.coords = coords
+    for rep in (None, 1000, 0):
+        got = dl.load_routing_data(raster, rep_val=rep)
+        want = io_layout.load_routing_vector(raster, coords, nrow, ncol, skip=68, rep_val=rep)
+        assert got.shape == (ncell,) and bitwise_equal(got, want)
+    if ref_loader.available():
+        ref_loader.load()
+        import xanthos.data_reader.data_load as rdl
+        import xanthos.utils.math as rmath
+        idx = rmath.sub2ind([nrow, ncol], coords[:, 4].astype(int) - 1, coords[:, 3].astype(int) - 1)
+        assert np.array_equal(idx, io_layout.sub2ind([nrow, ncol], coords[:, 4].astype(int) - 1, coords[:, 3].astype(int) - 1))
+        assert bitwise_equal(rdl.DataLoader.vectorize(raster, nrow, ncol, idx, skip=68),
+                             io_layout.vectorize(raster, nrow, ncol, idx, 68))
