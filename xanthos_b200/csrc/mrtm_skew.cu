@@ -48,7 +48,10 @@ constexpr int SK_XO = 16;        // exported cells (outgoing cut edges) per warp
 // 4 cells per lane (57.7 against 49.5 ms) and equal with 2 (44.5 ms), see DESIGN.md section 4.
 constexpr int SK_LAGM = XAN_SKEW_LAGM;
 constexpr int SK_DMAX = 62 / SK_LAGM - 1;   // largest piece height; lags reach SK_LAGM (SK_DMAX + 1) in warps with ghost entries
-constexpr int SK_CH = 64;        // sub-steps of a cut-edge series staged per hand-over
+#ifndef XAN_SKEW_CH
+#define XAN_SKEW_CH 64
+#endif
+constexpr int SK_CH = XAN_SKEW_CH;   // sub-steps of a cut-edge series staged per hand-over (power of two, >= 32)
 constexpr int SK_W = 4 * SK_CH;  // staged entries kept per ghost (a chunk is read for at most 2 SK_CH iterations)
 constexpr int SK_NB = 4;         // before / after terms of a wide row
 
