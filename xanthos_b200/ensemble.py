@@ -15,7 +15,8 @@ PET -> ABCD -> MRTM with their copies overlapped:
                      that shares an SM with the latency-bound routing chain slows it by more than it saves), so it is off.
     d2h stream     : requested outputs of the members before  (HBM -> pinned host, cell-major like the reference's arrays)
 
-The forcing of at most `prefetch_depth` (2) members is on its way ahead of the group being computed.  Only the variables named in `output_vars` are copied back (the reference
+The forcing of at most `prefetch_depth` (4 = two pairs) members is on its way ahead of the group being computed: on a
+shared host an upload now and then crawls for 100 - 300 ms, and one pair of look-ahead (72 ms of kernels) does not cover that.  Only the variables named in `output_vars` are copied back (the reference
 keeps PET, AET, Q, Sav, ChStorage and Avg_ChFlow of a scenario in host memory but writes `output_vars` only,
 data_writer/out_writer.py:60-110).  With torch.distributed initialised the members are dealt in contiguous blocks to the ranks
 (no collective in the data path) and the basin aggregates [n_members, 2, nmonths, n_basins] are gathered at the end.
@@ -96,7 +97,7 @@ class EnsembleStatics:
 
 
 class EnsembleRunner:
-    def __init__(self, statics, output_vars=('q', 'avgchflow'), aggregates=True, prefetch_depth=2, group=2):
+    def __init__(self, statics, output_vars=('q', 'avgchflow'), aggregates=True, prefetch_depth=4, group=2):
         torch = C.torch_cuda()
         self.prefetch_depth = max(1, int(prefetch_depth))   # members whose forcing may be on its way ahead of the compute
         self.group = max(1, int(group))                     # members routed by one launch
@@ -108,19 +109,30 @@ class EnsembleRunner:
         import os as _os
         self.front = torch.cuda.Stream() if _os.environ.get('XANTHOS_ENSEMBLE_FRONT', '0') == '1' else None
         self.h2d_bytes = self.d2h_bytes = 0
+        self._slots = None          # ring of device staging buffers for the uploads, depth + group slots
         self._torch = torch
         import os
         self.timeline = [] if os.environ.get('XANTHOS_ENSEMBLE_TIMELINE') else None   # per member: stage event pairs
 
     # ---- the three pipeline stages (everything is enqueued, nothing waits) ------------------------------------------
-    def _upload(self, member):
+    def _slot_buffer(self, slot, k):
+        """Device staging buffer of forcing field k in ring slot `slot` (made on first use, then reused for the whole
+        run: a `cudaMalloc` per upload now and then stalls for hundreds of ms while a routing launch is running)."""
+        torch = self._torch
+        if self._slots is None or len(self._slots) <= slot:
+            self._slots = (self._slots or []) + [dict() for _ in range(slot + 1 - len(self._slots or []))]
+        b = self._slots[slot].get(k)
+        if b is None:
+            b = self._slots[slot][k] = torch.empty(self.s.ncell * self.s.nmonths, dtype=torch.float64, device='cuda')
+        return b
+
+    def _upload(self, member, slot):
         torch = self._torch
         if callable(member):
             member = member()
         missing = [k for k in FORCING if k not in member]
         if missing:
             raise C.ValidationException("ensemble member lacks {}".format(missing))
-        compute = self.front if self.front is not None else torch.cuda.current_stream()   # the consumer of the staged tensors
         staged = {}
         # Only copy-engine work goes on the h2d stream.  The transposes to month-major run on the compute stream in front
         # of the member's kernels: a kernel on the h2d stream would wait for SM resources behind the routing kernel of
@@ -139,8 +151,11 @@ class EnsembleRunner:
                     a = torch.from_numpy(a)
                 if a.dtype not in (torch.float64, torch.float32):
                     a = a.to(torch.float64)
-                t = a.to(device='cuda', non_blocking=True)     # float32 arrays cross the link as float32 (see lossless_float32)
-                t.record_stream(compute)
+                # float32 arrays cross the link as float32 (see lossless_float32).  The destination is the ring slot's
+                # buffer: the slot is free, `run` has waited for the compute stage of its previous occupant
+                buf = self._slot_buffer(slot, k)
+                t = (buf.view(torch.float32)[:a.numel()] if a.dtype == torch.float32 else buf).view(a.shape)
+                t.copy_(a, non_blocking=True)
                 staged[k] = t
                 self.h2d_bytes += t.numel() * t.element_size()
             ev = torch.cuda.Event(enable_timing=self.timeline is not None)
@@ -266,7 +281,7 @@ class EnsembleRunner:
                 old = next_up - depth - g
                 if old >= 0:
                     computed[old].synchronize()
-                uploaded[next_up] = self._upload(members[next_up])
+                uploaded[next_up] = self._upload(members[next_up], next_up % (depth + g))
                 next_up += 1
         fronts = {}
 
