@@ -15,8 +15,8 @@ PET -> ABCD -> MRTM with their copies overlapped:
                      that shares an SM with the latency-bound routing chain slows it by more than it saves), so it is off.
     d2h stream     : requested outputs of the members before  (HBM -> pinned host, cell-major like the reference's arrays)
 
-The forcing of at most `prefetch_depth` (4 = two pairs) members is on its way ahead of the group being computed: on a
-shared host an upload now and then crawls for 100 - 300 ms, and one pair of look-ahead (72 ms of kernels) does not cover that.  Only the variables named in `output_vars` are copied back (the reference
+The forcing of at most `prefetch_depth` (4 = two pairs) members is on its way ahead of the group being computed, into a
+fixed ring of device staging buffers (no allocation inside the pipeline).  Only the variables named in `output_vars` are copied back (the reference
 keeps PET, AET, Q, Sav, ChStorage and Avg_ChFlow of a scenario in host memory but writes `output_vars` only,
 data_writer/out_writer.py:60-110).  With torch.distributed initialised the members are dealt in contiguous blocks to the ranks
 (no collective in the data path) and the basin aggregates [n_members, 2, nmonths, n_basins] are gathered at the end.
@@ -105,9 +105,13 @@ class EnsembleRunner:
         if bad:
             raise C.ValidationException("unknown output variable(s) {}; choose from {}".format(bad, OUTPUTS))
         self.s, self.output_vars, self.aggregates = statics, tuple(output_vars), bool(aggregates)
-        self.h2d, self.d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        # One pair of copy streams per process and device, not per runner: torch's caching allocator keeps freed blocks
+        # per STREAM, so every new stream starts with an empty pool - a runner per run_ensemble call with fresh streams
+        # left 6 - 9 GB of staging blocks cached under dead streams per call, and after a dozen calls the allocator had
+        # to cudaFree them (a device-wide synchronisation) in the middle of the uploads: 250 - 450 ms per stalled upload.
+        self.h2d, self.d2h = C.copy_stream('ensemble_h2d'), C.copy_stream('ensemble_d2h')
         import os as _os
-        self.front = torch.cuda.Stream() if _os.environ.get('XANTHOS_ENSEMBLE_FRONT', '0') == '1' else None
+        self.front = C.copy_stream('ensemble_front') if _os.environ.get('XANTHOS_ENSEMBLE_FRONT', '0') == '1' else None
         self.h2d_bytes = self.d2h_bytes = 0
         self._slots = None          # ring of device staging buffers for the uploads, depth + group slots
         self._torch = torch
@@ -134,6 +138,7 @@ class EnsembleRunner:
         if missing:
             raise C.ValidationException("ensemble member lacks {}".format(missing))
         staged = {}
+        bufs = {k: self._slot_buffer(slot, k) for k in FORCING}      # allocated on the compute stream (its pool is reused)
         # Only copy-engine work goes on the h2d stream.  The transposes to month-major run on the compute stream in front
         # of the member's kernels: a kernel on the h2d stream would wait for SM resources behind the routing kernel of
         # the previous member (one cooperative block per SM, the whole register file) and hold up the next copy.
@@ -153,7 +158,7 @@ class EnsembleRunner:
                     a = a.to(torch.float64)
                 # float32 arrays cross the link as float32 (see lossless_float32).  The destination is the ring slot's
                 # buffer: the slot is free, `run` has waited for the compute stage of its previous occupant
-                buf = self._slot_buffer(slot, k)
+                buf = bufs[k]
                 t = (buf.view(torch.float32)[:a.numel()] if a.dtype == torch.float32 else buf).view(a.shape)
                 t.copy_(a, non_blocking=True)
                 staged[k] = t
