@@ -590,8 +590,9 @@ def run_ours(args, rank, world_size, local_rank):
         latency_model = {'sub_steps': nsub, 'chain_cycles_isolated_warp_nt4': chain, 'sm_mhz': mhz, 'floor_ms': floor_ms,
                          'measured_ms': per_kernel['mrtm_warp_kernel']['ms'],
                          'members_per_launch': nmem,
-                         'frac_of_floor': floor_ms / per_kernel['mrtm_warp_kernel']['ms'],
-                         'us_per_sub_step': per_kernel['mrtm_warp_kernel']['ms'] * 1e3 / nsub,
+                         'measured_ms_per_member': per_kernel['mrtm_warp_kernel']['ms'] / nmem,
+                         'frac_of_floor': floor_ms / (per_kernel['mrtm_warp_kernel']['ms'] / nmem),
+                         'us_per_sub_step': per_kernel['mrtm_warp_kernel']['ms'] / nmem * 1e3 / nsub,
                          'source': 'profiles/r02_fp64_peak.json (tools/microbench/fp64_peak.cu)',
                          'note': 'the floor is the dependent chain of one isolated warp of the warp-dataflow kernel (row of 4 '
                                  'terms); the warps of an SM share its issue ports (DESIGN.md section 4)'}
