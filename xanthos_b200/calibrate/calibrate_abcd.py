@@ -133,7 +133,8 @@ class StreamflowEvaluator:
     Routing never mixes basins, so ONE global pass evaluates candidate j of EVERY basin at once: for population slot j the
     parameter table row of basin b is candidate j of b, `xan_abcd_run` gives the global runoff field, and the fields of
     two slots share a launch of `xan_mrtm_route_batch` (members = population slots).  A generation of P candidates is
-    P ABCD runs + P / 2 routing launches whatever the number of basins (0.5 degree world, 360 + 360 months: P x 32 ms).
+    P ABCD runs + P / 2 routing launches whatever the number of basins (0.5 degree world, 360 + 360 months, random
+    candidates: 57.5 ms per population slot, tools/calib_streamflow_bench.py).
     Same `evaluate` / `evaluate_device` interface as `BasinEvaluator`.
     """
 
