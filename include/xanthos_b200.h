@@ -173,6 +173,11 @@ int xan_mrtm_plan_packing(const xan_mrtm_plan *plan, int *h_lane_cell, int *h_ed
  * ghost_edge, ghost_lag [n_warps][info[9]]; exp_edge, exp_place [n_warps][info[10]]; Dw [n_warps];
  * edge_prod, edge_cons [n_cut_edges]. */
 int xan_mrtm_skew_info(xan_mrtm_plan *plan, int *info12);
+/* Pacing window the skew kernel would use for this plan: out4[0] = effective window in months for a requested window
+ * (0 = off; any other value is raised to the smallest deadlock-free one: pipeline depth of the linked warps + ring
+ * capacity, in months of nt_min sub-steps), [1] = sub-steps per hand-over chunk, [2] = ring entries per cut edge,
+ * [3] = default requested window.  Host only. */
+int xan_mrtm_skew_window(xan_mrtm_plan *plan, int requested, int nt_min, int *out4);
 int xan_mrtm_skew_tables(xan_mrtm_plan *plan, int *cell, int *lag, int *src, int *ghost_edge,
                          int *ghost_lag, int *exp_edge, int *exp_place, int *Dw, int *edge_prod,
                          int *edge_cons);

@@ -142,3 +142,84 @@ def route(t, q, flow_dist, velocity, area, ndays, dt, spinup, chs_prev=None):
             wr[:CAP, 0] = F
             wr[:CAP, 1] = Fp
     return chs, avg, inst
+
+
+def pacing_window(um, requested, nt_min):
+    """(effective window in months, sub-steps per hand-over chunk, ring entries, default request) of the library."""
+    from xanthos_b200 import _cuda as C
+    out = (ctypes.c_int * 4)()
+    C.check(C.lib().xan_mrtm_skew_window(um._plan, int(requested), int(nt_min), out))
+    return tuple(out)
+
+
+def handover_completes(t, nt, window, ch, rl):
+    """
+    Replays the hand-over protocol of `mrtm_skew_kernel` (no arithmetic) on the plan tables `t`: does every warp reach
+    the end of the run?  `nt`: sub-steps of every routing step (spin-up months, then months).  Per warp, as in the kernel:
+      * before the loop a warp with ghost entries waits for `min(T, ch)` sub-steps of its producers;
+      * at every chunk start n0 (multiples of `ch` up to T + Dw) a linked warp waits until its producers have handed over
+        `min(T, n0 + 2 ch)` sub-steps and its consumers have consumed `n0 - rl` (ring back-pressure), then publishes
+        `max(0, min(T, n0 - 1 - Dw))`;
+      * in iteration `start[b] + Dw` it counts itself past month boundary b and, with a pacing window W > 0, waits until
+        ALL warps are past boundary b - W;
+      * after the loop it publishes T.
+    Returns True when all warps finish, False on a deadlock (a full pass over the warps without any progress).
+    """
+    nw = t['info']['n_warps']
+    Dw = t['Dw'].astype(int)
+    prods = [[] for _ in range(nw)]
+    conss = [[] for _ in range(nw)]
+    for p, c in zip(t['edge_prod'], t['edge_cons']):
+        prods[int(c)].append(int(p))
+        conss[int(p)].append(int(c))
+    start = np.concatenate([[0], np.cumsum(nt)]).astype(int)
+    M, T = len(nt), int(start[-1])
+    # per warp: the ordered list of blocking points (kind, a, b, publish)
+    plans = []
+    for w in range(nw):
+        linked = bool(prods[w] or conss[w])
+        steps = []
+        if prods[w]:
+            steps.append((-1, 'P', min(T, ch), 0, None))
+        nlast = T + Dw[w]
+        for n0 in range(0, nlast + 1, ch):
+            if linked:
+                steps.append((n0 - 0.5, 'P', min(T, n0 + 2 * ch), n0 - rl, max(0, min(T, n0 - 1 - Dw[w]))))
+        for b in range(M + 1):
+            steps.append((start[b] + Dw[w], 'B', b, 0, None))
+        steps.sort(key=lambda s: s[0])
+        if linked:
+            steps.append((nlast + ch, 'F', 0, 0, T))
+        plans.append(steps)
+    progress = np.zeros(nw, dtype=int)
+    done = np.zeros(M + 2, dtype=int)
+    pc = [0] * nw
+    counted = [set() for _ in range(nw)]
+    live = set(range(nw))
+    while live:
+        moved = False
+        for w in list(live):
+            steps = plans[w]
+            while pc[w] < len(steps):
+                _, kind, a, b, pub = steps[pc[w]]
+                if kind == 'P':
+                    if any(progress[p] < a for p in prods[w]) or (b > 0 and any(progress[c] < b for c in conss[w])):
+                        break
+                    if pub is not None:
+                        progress[w] = pub
+                elif kind == 'B':
+                    if a not in counted[w]:
+                        counted[w].add(a)
+                        done[a] += 1
+                        moved = True
+                    if window > 0 and a - window >= 0 and done[a - window] < nw:
+                        break
+                else:
+                    progress[w] = pub
+                pc[w] += 1
+                moved = True
+            if pc[w] == len(steps):
+                live.discard(w)
+        if not moved:
+            return False
+    return True

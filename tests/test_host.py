@@ -383,3 +383,37 @@ def test_routing_raster_vectorize_matches_the_oracle_and_the_live_reference():
         assert np.array_equal(idx, io_layout.sub2ind([nrow, ncol], coords[:, 4].astype(int) - 1, coords[:, 3].astype(int) - 1))
         assert bitwise_equal(rdl.DataLoader.vectorize(raster, nrow, ncol, idx, skip=68),
                              io_layout.vectorize(raster, nrow, ncol, idx, 68))
+
+
+def test_pacing_window_of_the_skew_kernel_is_deadlock_free(monkeypatch):
+    """The month pacing window of `mrtm_skew_kernel` (a warp crosses boundary b only after every warp has crossed b - W)
+    against the ring back-pressure and the chunked hand-over of the cut edges: the protocol is replayed on the plan
+    tables (tests/skew_model.py::handover_completes).  With the window the library computes (`xan_mrtm_skew_window`:
+    pipeline depth of the linked warps + ring capacity) every warp finishes - for 2 and 4 cells per lane, 3-hourly and
+    hourly sub-steps, three networks including the 0.5 degree bench world - and a window shorter than the pipeline is
+    shown to deadlock there (it did on the GPU: DESIGN.md section 4)."""
+    import skew_model
+    from xanthos_b200 import synthetic
+    from xanthos_b200.routing import mrtm
+    from oracle.calendar_utils import set_month_arrays
+    worlds = [synthetic.make_world(40, 80, 1500, 8, seed=5, coast_pull=0.0), synthetic.make_world(90, 180, 6000, 30, seed=2),
+              synthetic.make_world(seed=0)]
+    nd = set_month_arrays(60, 2001, 2005)[:, 2]
+    for w in worlds:
+        s = w.settings()
+        up = mrtm.upstream(w.coords, mrtm.downstream(w.coords, w.flow_dir, s), s)
+        for K in ('2', '4'):
+            monkeypatch.setenv('XANTHOS_MRTM_SKEW_K', K)
+            um = mrtm.upstream_genmatrix(up)
+            t = skew_model.skew_tables(um)
+            for dt, months, spin in ((10800, 48, 12), (3600, 14, 4)):
+                nt = np.array([int(d * 24 * 3600 / dt) for d in list(nd[:spin]) + list(nd[:months])])
+                win, ch, rl, dflt = skew_model.pacing_window(um, 1, nt.min())
+                assert dflt >= 1 and win >= 3 and skew_model.pacing_window(um, 0, nt.min())[0] == 0
+                assert skew_model.pacing_window(um, 10 ** 6, nt.min())[0] == 10 ** 6          # a larger request is kept
+                assert skew_model.handover_completes(t, nt, win, ch, rl), (w.ncell, K, dt, win)
+                assert skew_model.handover_completes(t, nt, 0, ch, rl)                         # pacing off
+        if w.ncell > 60000:      # the outlets of the bench world run a dozen months behind the leaves
+            nt = np.array([int(d * 24 * 3600 / 10800) for d in list(nd[:12]) + list(nd[:48])])
+            assert t['info']['n_levels'] >= 10
+            assert not skew_model.handover_completes(t, nt, 2, ch, rl)

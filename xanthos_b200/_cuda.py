@@ -64,6 +64,7 @@ SIGNATURES = {
     'xan_mrtm_plan_info': (c_int, [_P, POINTER(c_int)]),
     'xan_mrtm_plan_packing': (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     'xan_mrtm_skew_info': (c_int, [_P, POINTER(c_int)]),
+    'xan_mrtm_skew_window': (c_int, [_P, c_int, c_int, POINTER(c_int)]),
     'xan_mrtm_skew_tables': (c_int, [_P] + [POINTER(c_int)] * 10),
     'xan_mrtm_route': (c_int, [_P, _P, _P, _P, _P, _P, POINTER(c_int), c_int, c_int, c_int, c_double, c_int,
                                _P, _P, _P, _P]),

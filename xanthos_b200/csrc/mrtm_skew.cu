@@ -1085,6 +1085,16 @@ static int launch_skew_nm(SkewPlan *sp, SkewArgs &a, int nm, int sms, cudaStream
     return XAN_E_INVALID;
 }
 
+// Effective pacing window in months.  A consumer follows its producer by up to 3 hand-over chunks + the producer's
+// largest lag, level after level: the leaves must be allowed that far ahead of the outlets, plus what the rings hold, or
+// the pacing and the ring back-pressure wait for each other.  (tests/test_host.py replays the hand-over protocol of the
+// kernel on the plan tables with this window - it completes - and with a smaller one - it deadlocks.)
+static int skew_window(const SkewPlan *sp, int requested, int nt_min, int RL) {
+    if (requested <= 0) return 0;
+    const int depth_steps = sp->n_levels * (3 * SK_CH + sp->Dmax + 1) + RL;
+    return std::max(requested, ceil_div(depth_steps, std::max(nt_min, 1)) + 2);
+}
+
 // Routes nm (1 .. SK_NM_MAX) members with one launch of the skew kernel.  Returns XAN_E_INVALID (without an error
 // message) when the plan or the calendar does not allow it (nm > 1: when nm blocks per SM do not fit or the variant is
 // not compiled), so that the caller can fall back to fewer members per launch / the warp-dataflow kernel.
@@ -1185,12 +1195,7 @@ int route_skew(xan_mrtm_plan *pl, int nm, const double *const *d_runoff, const d
     // pacing window in months (XANTHOS_MRTM_SKEW_WINDOW, 0 = off; raised to the smallest safe value)
     const char *ew = getenv("XANTHOS_MRTM_SKEW_WINDOW");
     a.window = ew ? std::max(0, atoi(ew)) : SK_WINDOW_DEFAULT;
-    if (a.window > 0) {
-        // a consumer follows its producer by up to 3 hand-over chunks + the producer's largest lag, level after level:
-        // the leaves must be allowed that far ahead of the outlets, plus what the rings hold, or the throttles deadlock
-        const int depth_steps = sp->n_levels * (3 * SK_CH + sp->Dmax + 1) + RL;
-        a.window = std::max(a.window, ceil_div(depth_steps, std::max(nt_min, 1)) + 2);
-    }
+    a.window = skew_window(sp, a.window, nt_min, RL);
     int *done = nullptr;
     if (a.window > 0) {
         XAN_CUDA_CHECK(scratch_alloc(&done, sizeof(int) * (size_t)(M + 2) * nm, s));
@@ -1244,6 +1249,16 @@ int xan_mrtm_skew_info(xan_mrtm_plan *pl, int *info) {
     const int v[12] = {sp->K, sp->nw, sp->n_edges, sp->n_levels, sp->G, sp->Dmax, sp->n_pieces, sp->nsrc(),
                        sp->zero_entry(), xan::SK_XG, xan::SK_XO, xan::SK_LAGM};
     for (int i = 0; i < 12; ++i) info[i] = v[i];
+    return XAN_OK;
+}
+
+int xan_mrtm_skew_window(xan_mrtm_plan *pl, int requested, int nt_min, int *out4) {
+    XAN_REQUIRE(pl && out4, "xan_mrtm_skew_window: null pointer");
+    xan::SkewPlan *sp = xan::get_skew(pl);
+    out4[0] = sp ? xan::skew_window(sp, requested, nt_min, 1024) : 0;
+    out4[1] = xan::SK_CH;
+    out4[2] = 1024;                 // ring entries per cut edge (XANTHOS_MRTM_SKEW_RING default)
+    out4[3] = xan::SK_WINDOW_DEFAULT;
     return XAN_OK;
 }
 
