@@ -8,13 +8,18 @@ Benchmark of the Xanthos hot path (BASELINE.json: cell-months/s for PM + ABCD + 
 Workload (config.workload = "pm_abcd_mrtm_360"): BASELINE.json configs[0]/[1] shape - Penman-Monteith
 PET -> ABCD runoff -> MRTM routing, 67,420 cells x 360 months (1971-2000), synthetic forcing,
 runoff spin-up 360 months, routing spin-up 360 months, 3-hour routing sub-steps, nlcs = 8.
-A "step" is one pass of that pipeline over one member.  At N > 1 every rank runs one member
-(ensemble sharding, weak scaling, no collective in the data path; the basin-aggregated runoff and
-streamflow [360 x 235] of every member are all-gathered over NCCL at the end of the step).
+A "step" is one pass of that pipeline over MEMBERS_PER_STEP = 2 scenario members of that shape (PM -> ABCD per
+member, ONE routing launch for both: their thread blocks share the SMs); `single_member_step` reports the
+one-member step of round 1.  At N > 1 every rank runs its own members (ensemble sharding, weak scaling, no
+collective in the data path; the basin-aggregated runoff and streamflow [360 x 235] of every member are
+all-gathered over NCCL at the end of the step).
 
-  value : cell-months/s with the forcing already resident in HBM (month-major fields), device time
-  e2e   : same metric through the reference-facing plug-in calls (run_pmpet / abcd_execute /
-          route) with pinned HOST buffers in and host ndarrays out; H2D and D2H inside the timing
+  value : cell-months/s (members x cells x months / step time) with the forcing already resident in HBM
+          (month-major fields), device time
+  e2e   : same metric through the public ensemble API (xanthos_b200.ensemble.run_ensemble): every member's forcing
+          from pinned HOST buffers, its outputs (q, avgchflow, basin aggregates) back to host ndarrays, H2D and D2H
+          inside the timing, median of five runs; e2e.single_member = the reference-facing plug-in calls
+          (run_pmpet / abcd_execute / route) on one member, nothing overlapped
   roofline, cpu_baseline, clocks, gpu_launches : as the measurement contract asks
   calib    : param-sets/s of one differential-evolution generation (235 basins x 64 candidates) and of a whole
              DE loop with the device and the numpy driver
