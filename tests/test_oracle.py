@@ -134,3 +134,41 @@ def test_de_oracle_latin_hypercube():
     p = de.lhs_init(3, S, D, 777)
     assert (p >= 0).all() and (p < 1).all()
     assert (np.sort(np.floor(p * S).astype(int), axis=1) == np.arange(S)[None, :, None]).all()   # every stratum once
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+def test_reference_streamflow_branch_has_no_usable_behaviour():
+    """Why the streamflow calibration target (`set_calibrate = 1`) is built to its INTENDED semantics and not to the
+    reference's (oracle/calibrate.py docstring): the live reference's own `basin_runoff` / `objective_kge`
+    (calibrate_abcd.py:164-213), run here on a small world with a real router, (1) put only the first n_b values of the
+    basin's [months, n_b] runoff at FLAT indices of the global [ncell, months] array - rows near the top of the grid, not
+    the basin's cells -, (2) hand the router's whole [ncell, months] Avg_ChFlow back as the "modelled series", and
+    (3) evaluate to NaN."""
+    import numpy as np
+    from types import SimpleNamespace
+    from xanthos_b200 import synthetic
+    from oracle.calendar_utils import set_month_arrays
+    ref = ref_loader.load()
+    w = synthetic.make_world(24, 48, 320, 5, seed=44)
+    m = 36
+    ab = synthetic.abcd_inputs(w, m, seed=9)
+    tmin = np.nan_to_num(ab['tmin'])
+    nd = set_month_arrays(m, 2001, 2003)[:, 2]
+    rows = omrtm.csr_rows(omrtm.upstream_fast(w.coords, omrtm.downstream(w.coords, w.flow_dir, w.nrow, w.ncol), w.nrow, w.ncol))
+    seen = {}
+
+    def router(rsim):          # stands for Components.calculate_routing (components.py:249-296): returns Avg_ChFlow
+        seen['rsim'] = np.array(rsim)
+        return omrtm.route(rsim, w.flow_dist, w.velocity, w.area, nd, 10800, rows, 6)[1]
+    idx = np.where(w.basin_ids == 3)
+    n_b = len(idx[0])
+    args = (ab['pet'][idx], ab['precip'][idx], tmin[idx], m, m, 'm3_per_sec', w.area[idx])
+    mod = ref.cal.basin_runoff(ab['pars'][2], 1, *args, idx, ab['pet'].shape, router)
+    assert np.shape(mod) == ab['pet'].shape                                   # (2): not a series of the basin
+    flat = np.nonzero(seen['rsim'].ravel())[0]
+    assert len(flat) <= n_b and flat.max() <= idx[0].max()                     # (1): n_b values at flat indices = cell ids
+    assert not np.array_equal(np.unique(flat // m), idx[0])                    # ... which are not the basin's rows
+    with np.errstate(all='ignore'):
+        ed = ref.cal.objective_kge(ab['pars'][2], ref.cal.basin_runoff, 1, *args, np.linspace(1.0, 2.0, m), idx,
+                                   ab['pet'].shape, router)
+    assert np.isnan(ed)                                                       # (3)
