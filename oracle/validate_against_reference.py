@@ -348,6 +348,19 @@ def main():
             bit = np.array_equal(np.asarray(r[k]), np.asarray(o[k]), equal_nan=True)
             print("  postproc {:18s} bitwise={}".format(k, bit))
             ok &= bit
+    # raster -> cell vector layout of the routing inputs (data_load.py:392-425, utils/math.py:40-50)
+    from . import io_layout
+    import xanthos.data_reader.data_load as rdl
+    import xanthos.utils.math as rmath
+    rng = np.random.default_rng(12)
+    lin = rng.choice(360 * 720, 4000, replace=False)
+    rows_, cols_ = lin % 360, lin // 360
+    raster = rng.normal(500.0, 800.0, (280, 720))
+    idx = rmath.sub2ind([360, 720], rows_, cols_)
+    bit = np.array_equal(idx, io_layout.sub2ind([360, 720], rows_, cols_)) and np.array_equal(
+        rdl.DataLoader.vectorize(raster, 360, 720, idx, skip=68), io_layout.vectorize(raster, 360, 720, idx, 68))
+    print("  io_layout vectorize / sub2ind bitwise={}".format(bit))
+    ok &= bit
     print("ORACLE PINNED" if ok else "ORACLE MISMATCH")
     return 0 if ok else 1
 
