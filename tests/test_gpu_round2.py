@@ -469,3 +469,9 @@ def test_ensemble_runner_equals_the_plugin_calls_member_by_member():
             idx = w.basin_ids == b + 1
             want = np.nansum(q[idx] * (w.area[idx] * 1e-6)[:, None], axis=0)
             assert max_rel(res['basin_aggregates'][k, 0, :, b], want, floor=1e-12) < 1e-12
+    # a longer run: the ring of upload staging buffers (prefetch depth + group = 6 slots) and the pinned output pool are
+    # reused, the member count is odd (four pairs and a single) - every member still equals its stand-alone result
+    long = ens.run_ensemble(st, [members[i % 3] for i in range(9)], output_vars=('q', 'avgchflow'))
+    for i in range(9):
+        assert bitwise_equal(long[i]['q'], res[i % 3]['q']) and bitwise_equal(long[i]['avgchflow'], res[i % 3]['avgchflow'])
+        assert bitwise_equal(long['basin_aggregates'][i], res['basin_aggregates'][i % 3])
