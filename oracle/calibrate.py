@@ -12,6 +12,9 @@ global cell 0 (after building a 67,421 x 67,421 covariance matrix, 36 GB), so
 it has no usable behaviour to pin; what is restated here is what
 docs/calibration_tutorial.md describes - the routed flow at the basin's outlet
 against the observed streamflow - and it is labelled as such everywhere.
+PARITY UNPINNED for `objective_kge_streamflow` / `outlet_cells` (no reference output exists to pin them to;
+tests/test_oracle.py::test_reference_streamflow_branch_has_no_usable_behaviour shows what the reference does);
+the runoff-target functions above are pinned to the live reference (validate_against_reference.py).
 """
 
 import numpy as np
